@@ -1,0 +1,200 @@
+/* b2q.h -- C ABI of libb2q.so: B200 (sm_100a) kernels for the int8 fake-quantization CustomOps of
+ * XiaotaoChen/resnet.mxnet.
+ *
+ * This is the drop-in boundary.  Every entry point takes plain device pointers, sizes and a CUDA stream
+ * (as void*); no framework types cross it.  The library never allocates or frees tensor memory and never
+ * synchronises the device: all work is enqueued on the caller's stream.  Tensors are float32, dense,
+ * row-major (NCHW activations, (Cout, Cin/g, kh, kw) weights) exactly as the reference's NDArrays.
+ *
+ * Each function names the reference code it replaces (paths relative to the reference repo root).
+ * Return value: 0 on success, non-zero on failure with a message in b2q_last_error() (thread-local).
+ *
+ * "Segmented" tensors: several entry points view a tensor as (outer, groups, inner), element (o, g, i) at
+ * ((o * groups) + g) * inner + i, with one threshold per g:
+ *     whole tensor                     outer=1      groups=1          inner=N
+ *     per-out-channel weight           outer=1      groups=Cout       inner=Cin/g*kh*kw
+ *     GDRQ grouped weight              outer=1      groups=Cout/gs    inner=gs*Cin/g*kh*kw
+ *     GDRQ grouped activation (NCHW)   outer=N      groups=C/gs       inner=gs*H*W
+ * which replaces the reference's swapaxes/reshape/broadcast_like chains (core/operator/GDRQ.py:88-118,
+ * symbol/quant_ops.py:20-24) without moving data.
+ */
+#ifndef B2Q_H_
+#define B2Q_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2Q_ABI_VERSION 1
+
+/* MXNet OpReqType (include/mxnet/op_attr_types.h [upstream]); CustomOp.assign() semantics. */
+#define B2Q_REQ_NULL 0
+#define B2Q_REQ_WRITE 1
+#define B2Q_REQ_INPLACE 2
+#define B2Q_REQ_ADD 3
+
+typedef struct b2q_ctx b2q_ctx; /* per-device handle: SM count + a small ring of reduction workspaces */
+
+/* ---- lifecycle / errors ------------------------------------------------------------------------ */
+int b2q_abi_version(void);
+const char* b2q_last_error(void);
+int b2q_create(int device, b2q_ctx** out);
+int b2q_destroy(b2q_ctx* ctx);
+int b2q_num_sms(b2q_ctx* ctx);
+/* run-time knobs for benchmarking sweeps: "blocks_per_sm" (grid = SMs x this), "reverse" (QDQ sweep walks
+ * descending addresses to reuse what the reduction left in L2), "fast_div" (reciprocal fast path on/off).
+ * Results never depend on them. */
+int b2q_set_option(b2q_ctx* ctx, const char* key, int value);
+int b2q_get_option(b2q_ctx* ctx, const char* key, int* value);
+/* number of kernels this library has launched through ctx since creation (bench.py's gpu_launches) */
+int64_t b2q_launch_count(b2q_ctx* ctx);
+
+/* ---- primitives ---------------------------------------------------------------------------------
+ * K1/K2  b2q_absmax_f32    stat[g] = max |x|          replaces mx.nd.abs -> mx.nd.max
+ *        (symbol/quant_ops.py:18-26,34-35; symbol/clip_grad_quantization_int8.py:23-34,39-40)
+ * K7     b2q_meanabs_f32   stat[g] = fl(sum|x| / n_g)  replaces mx.nd.abs -> mx.nd.mean
+ *        (core/operator/GDRQ.py:67-72,95-100; symbol/fold_bn_v1_gdrq.py:56-58,78-90)
+ * Both are deterministic (fixed partition, fixed combination order).                                */
+int b2q_absmax_f32(b2q_ctx* ctx, const float* x, int64_t outer, int64_t groups, int64_t inner,
+                   float* stat, void* stream);
+int b2q_meanabs_f32(b2q_ctx* ctx, const float* x, int64_t outer, int64_t groups, int64_t inner,
+                    float* stat, void* stream);
+
+/* K3  threshold update from an already reduced statistic (used after a cross-rank allreduce(max)).
+ * mode: B2Q_UPD_*.  aux is updated in place; p0/p1 are (ema_decay, 1-ema_decay) or (ktimes, lamda).
+ * clip_out (may be NULL) receives the batch threshold where the op clips with it
+ * (symbol/fold_bn_v1_gdrq.py:58,67).                                                                */
+#define B2Q_UPD_STORE 1        /* aux = stat                         quant_ops.py:31, clip_grad...py:26,34 */
+#define B2Q_UPD_EMA 2          /* aux = aux*d + stat*(1-d)           quant_ops.py:37, clip_grad...py:46    */
+#define B2Q_UPD_GDRQ_WEIGHT 3  /* aux = k*stat                       GDRQ.py:72-74                          */
+#define B2Q_UPD_GDRQ_ACT 4     /* aux = aux + lamda*(aux - k*stat)   GDRQ.py:72,76                          */
+#define B2Q_UPD_TWICE_STORE 5  /* aux = 2*stat                       fold_bn_v1_gdrq.py:58,61 / :82,90,95   */
+#define B2Q_UPD_TWICE_EMA 6    /* aux = aux*d + (2*stat)*(1-d)       fold_bn_v1_gdrq.py:58,64               */
+int b2q_threshold_update_f32(b2q_ctx* ctx, int mode, const float* stat, float* aux, float* clip_out,
+                             int64_t groups, float p0, float p1, void* stream);
+
+/* K4/K8  one-sweep clip + quantize-dequantize:  y = fl(roundf(fl(c(x) / q)) * q),  q = fl(thr[g]/qlevel)
+ * (qlevel <= 0: thr holds q itself).  Bit-exact with the reference's x/q -> round -> *q chain
+ * (quant_ops.py:28,40; clip_grad...py:36,48-51; GDRQ.py:79-86,109-114).
+ * clip_mode: B2Q_CLIP_*; clip thresholds come from clip_thr (NULL: same as thr).
+ * do_round=0 gives the clip-only output of GDRQ's delay_quant branch (GDRQ.py:81-82).
+ * codes (may be NULL): int32 side output of roundf(c(x)/q) for parity checks.
+ * prescale (may be NULL) multiplies row (o*groups+g) by gamma/sqrt(var+eps) before anything else
+ * (fold_bn_v1_gdrq.py:72-74): pass gamma, var (length outer*groups) and eps.                        */
+#define B2Q_CLIP_NONE 0
+#define B2Q_CLIP_SYM 1        /* mx.nd.clip(x, -T, T)                          */
+#define B2Q_CLIP_WHERE_LE 2   /* where(|x| <= T, x, T*sign(x))   GDRQ.py:109   */
+#define B2Q_CLIP_ZERO_T 3     /* mx.nd.clip(x, 0, T)             GDRQ.py:202   */
+#define B2Q_CLIP_PACT 4       /* where(x < T, x, T)              PACT.py:125   */
+#define B2Q_CLIP_WHERE_LT 5   /* where(|x| < T, x, T*sign(x))    PACT.py:193   */
+int b2q_qdq_f32(b2q_ctx* ctx, const float* x, float* y, int64_t outer, int64_t groups, int64_t inner,
+                const float* thr, const float* clip_thr, float qlevel, int clip_mode, int do_round,
+                int req, int32_t* codes, const float* prescale_gamma, const float* prescale_var,
+                float prescale_eps, void* stream);
+
+/* K5  straight-through backward: in_grad (req) out_grad      quant_ops.py:41-42, GDRQ.py:126        */
+int b2q_ste_bwd_f32(b2q_ctx* ctx, const float* dy, float* dx, int64_t n, int req, void* stream);
+
+/* K6  masked backward, one pass:  dx (req) dy * mask(x, thr[g])
+ * mask_mode B2Q_MASK_OPEN   [x > -T][x < T]   clip_grad_quantization_int8.py:61-67
+ *           B2Q_MASK_ABS_LE [|x| <= T]        GDRQ.py:132-133,145-148
+ *           B2Q_MASK_LT     [x < T]           GDRQ.py:207-208
+ * thr == NULL: thr_imm is used (CLIP_RELU_PY's constant threshold).                                  */
+#define B2Q_MASK_OPEN 1
+#define B2Q_MASK_ABS_LE 2
+#define B2Q_MASK_LT 3
+int b2q_mask_bwd_f32(b2q_ctx* ctx, const float* x, const float* dy, float* dx, int64_t outer,
+                     int64_t groups, int64_t inner, const float* thr, float thr_imm, int mask_mode,
+                     int req, void* stream);
+
+/* ---- fused per-operator entry points (what the Python CustomOp bodies call) ---------------------- */
+
+/* Quantization_int8.forward, non-delay branch          symbol/quant_ops.py:17-40
+ * ClipGrad_Quantization_int8.forward, non-delay branch symbol/clip_grad_quantization_int8.py:19-51
+ * variant 0 = Quantization_int8_V2, 1 = ClipGrad_Quantization_int8.
+ * aux: minmax state [1] or [rows] (per-channel weight).  rows*cols = numel.  init: ClipGrad first-batch flag.
+ * stat_out (may be NULL): if non-NULL the function ONLY reduces (max|x| -> stat_out[groups]) and returns,
+ * so the caller can allreduce(max) across ranks and finish with b2q_minmax_quant_finish_f32.          */
+int b2q_minmax_quant_fwd_f32(b2q_ctx* ctx, int variant, const float* x, float* y, float* aux,
+                             int64_t rows, int64_t cols, int is_weight, int per_channel, int is_train,
+                             int init, float ema_decay, float one_minus_decay, int req, void* stream);
+int b2q_minmax_quant_stat_f32(b2q_ctx* ctx, const float* x, int64_t rows, int64_t cols, int per_channel,
+                              float* stat_out, void* stream);
+int b2q_minmax_quant_finish_f32(b2q_ctx* ctx, int variant, const float* x, float* y, float* aux,
+                                const float* stat, int64_t rows, int64_t cols, int is_weight,
+                                int per_channel, int is_train, int init, float ema_decay,
+                                float one_minus_decay, int req, void* stream);
+/* ClipGrad_Quantization_int8.backward (act)            symbol/clip_grad_quantization_int8.py:61-67 */
+int b2q_clipgrad_bwd_f32(b2q_ctx* ctx, const float* x, const float* dy, float* dx, const float* aux,
+                         int64_t n, void* stream);
+
+/* GDRQ_PY.forward / backward                           core/operator/GDRQ.py:64-118 / :124-152
+ * alpha: [groups].  (outer, groups, inner) as in the header comment; group_size==-1 -> groups=1.      */
+int b2q_gdrq_fwd_f32(b2q_ctx* ctx, const float* x, float* y, float* alpha, int64_t outer, int64_t groups,
+                     int64_t inner, int is_weight, int fix_alpha, int do_round, float qlevel, float ktimes,
+                     float lamda, int req, void* stream);
+int b2q_gdrq_bwd_f32(b2q_ctx* ctx, const float* x, const float* dy, float* dx, const float* alpha,
+                     int64_t outer, int64_t groups, int64_t inner, int req, void* stream);
+
+/* GDRQ_Fold_BN.forward up to the convolution           symbol/fold_bn_v1_gdrq.py:53-96,113
+ * data_q  = QDQ(clip(data, +-2 mean|data|)) with the EMA scale in aux_data[1]      (:53-68)
+ * weight_q = QDQ(clip(w * gamma/sqrt(var+eps), +-T)), T = 2 mean|w'| per tensor or per row; aux_weight=T (:70-96)
+ * bias[c] = beta - mean*gamma/sqrt(var+eps)                                          (:113)
+ * The convolution itself (:99-110) stays a library call (cuDNN) made by the caller.                   */
+int b2q_foldbn_data_fwd_f32(b2q_ctx* ctx, const float* x, float* y, float* aux_data, int64_t n, int init,
+                            float ema_decay, float one_minus_decay, void* stream);
+int b2q_foldbn_weight_fwd_f32(b2q_ctx* ctx, const float* w, float* w_q, float* bias, float* aux_weight,
+                              const float* gamma, const float* beta, const float* mean, const float* var,
+                              float eps, int64_t cout, int64_t cols, int per_channel, int quantize,
+                              int is_train, void* stream);
+
+/* QUANT_STE_PY (PACT.py:245-252) and PACT forward (PACT.py:125-128,193-198) are b2q_absmax_f32 + b2q_qdq_f32.
+ * CLIP_RELU_PY.forward  core/operator/GDRQ.py:200-204: clip(x, 0, threshold) then QDQ with q (= threshold/L
+ * computed by the caller in double like the reference); backward is b2q_mask_bwd_f32(B2Q_MASK_LT, thr_imm). */
+int b2q_clip_relu_fwd_f32(b2q_ctx* ctx, const float* x, float* y, int64_t n, float threshold, float q,
+                          int req, void* stream);
+/* the remaining second-tier operators:                                                                 */
+/* WNQ_PY  core/operator/WNQ.py:51-85 */
+int b2q_wnq_fwd_f32(b2q_ctx* ctx, const float* x, float* y, int64_t rows, int64_t cols, int per_channel,
+                    float qlevel, int req, void* stream);
+int b2q_wnq_bwd_f32(b2q_ctx* ctx, const float* x, const float* dy, float* dx, int64_t rows, int64_t cols,
+                    int per_channel, int req, void* stream);
+/* PACT_PY / PACT_V2_PY backward  core/operator/PACT.py:142-144 / :201-203 (two_sided=1 for V2).
+ * dgamma (req_gamma) sum of the gradient routed to the clipped branch.                                 */
+int b2q_pact_bwd_f32(b2q_ctx* ctx, const float* x, const float* dy, float* dx, float* dgamma,
+                     const float* gamma, int64_t n, int two_sided, int req, int req_gamma, void* stream);
+/* DoReFa_PY  core/operator/PACT.py:44-50 / :76-77 */
+int b2q_dorefa_fwd_f32(b2q_ctx* ctx, const float* x, float* y, float* vmax_out, int64_t n, float qlevel,
+                       int req, void* stream);
+int b2q_dorefa_bwd_f32(b2q_ctx* ctx, const float* x, const float* dy, float* dx, const float* vmax,
+                       int64_t n, int req, void* stream);
+/* QIL_PY / QIL_V2_PY / QIL_V3_PY  core/operator/QIL.py:50-124, QIL_V2.py:34-71, QIL_V3.py:36-70
+ * variant 1/2/3; p0,p1 are the two learnable scalars in the reference's argument order
+ * (pruning_point,clipping_point | center,distance | ep,ed).  V1 clamps p0>=0, p1<=1 in place (QIL.py:51-54). */
+int b2q_qil_fwd_f32(b2q_ctx* ctx, int variant, const float* x, float* y, float* p0, float* p1, int64_t n,
+                    float qlevel, int req, void* stream);
+int b2q_qil_bwd_f32(b2q_ctx* ctx, int variant, const float* x, const float* dy, float* dx, const float* p0,
+                    const float* p1, float* dp0, float* dp1, int64_t n, int req, int req_p0, int req_p1,
+                    void* stream);
+
+/* ---- host-buffer path: the call a framework whose tensors live in HOST memory makes (bench.py "e2e") --
+ * Same semantics as the device entry points but x / y / aux are HOST pointers (pinned for full speed).
+ * Each call stages its tensor through one of two device staging sets on that set's own stream
+ * (H2D -> reduction + threshold update -> QDQ sweep -> D2H) and returns without waiting, so the D2H of one
+ * call overlaps the H2D of the next; b2q_host_sync() waits for all of them.  host_aux is read at enqueue
+ * order and written back by the same call; calls sharing an aux array must be separated by a sync.       */
+int b2q_minmax_quant_fwd_host_f32(b2q_ctx* ctx, int variant, const float* host_x, float* host_y,
+                                  float* host_aux, int64_t rows, int64_t cols, int is_weight,
+                                  int per_channel, int is_train, int init, float ema_decay,
+                                  float one_minus_decay);
+int b2q_ste_bwd_host_f32(b2q_ctx* ctx, const float* host_dy, float* host_dx, int64_t n);
+int b2q_clipgrad_bwd_host_f32(b2q_ctx* ctx, const float* host_x, const float* host_dy, float* host_dx,
+                              const float* host_aux, int64_t n);
+int b2q_host_sync(b2q_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2Q_H_ */

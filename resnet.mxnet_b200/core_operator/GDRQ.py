@@ -1,0 +1,103 @@
+"""Drop-in for ``core/operator/GDRQ.py``: op_types ``GDRQ_PY`` and ``CLIP_RELU_PY``.
+
+GDRQ_PY (GDRQ.py:50-152): threshold alpha from ktimes*mean|x| (weights: alpha := thr; activations:
+alpha += lamda*(alpha - thr), also in eval mode, as in the reference), clip to +-alpha, round to 2^nbits-1
+levels unless still in the delay_quant countdown.  Grouped mode indexes the NCHW / OIHW tensor directly as
+(outer, groups, inner) instead of the reference's swapaxes -> reshape -> ... -> swapaxes round trip (:88-118).
+"""
+from .. import _kernels as K
+from .. import _lib
+from ..operator import CustomOp, CustomOpProp, py_bool, py_literal, register
+
+
+class GDRQ_PY(CustomOp):
+    def __init__(self, nbits, group_size, is_weight, lamda, delay_quant, fix_alpha, ktimes):
+        self.nbits = nbits
+        self.group_size = group_size
+        self.is_weight = is_weight
+        self.lamda = lamda
+        self.delay_quant = delay_quant
+        self.QUANT_LEVEL = 2 ** (self.nbits) - 1
+        self.fix_alpha = fix_alpha
+        self.ktimes = ktimes
+
+    def forward(self, is_train, req, in_data, out_data, aux):
+        do_round = not (self.delay_quant > 0)          # GDRQ.py:81-85 / :110-114
+        if self.delay_quant > 0:
+            self.delay_quant -= 1
+        K.gdrq_fwd(in_data[0], out_data[0], aux[0], self.group_size, self.is_weight, self.fix_alpha, do_round,
+                   self.QUANT_LEVEL, self.ktimes, self.lamda, req[0])
+
+    def backward(self, req, out_grad, in_data, out_data, in_grad, aux):
+        if self.is_weight:
+            K.ste_bwd(out_grad[0], in_grad[0], req[0])  # :125-127
+        else:
+            K.gdrq_bwd(in_data[0], out_grad[0], in_grad[0], aux[0], self.group_size, req[0])   # :131-152
+
+
+@register("GDRQ_PY")
+class GDRQ_PYProp(CustomOpProp):
+    def __init__(self, nbits=4, group_size=-1, is_weight=False, lamda=0.001, delay_quant=0, fix_alpha=False, ktimes=3):
+        self.nbits = int(nbits)
+        self.group_size = int(group_size)
+        self.is_weight = py_bool(is_weight)
+        self.lamda = float(lamda)
+        self.delay_quant = int(delay_quant)
+        self.fix_alpha = py_bool(fix_alpha)
+        self.ktimes = float(ktimes)
+        super(GDRQ_PYProp, self).__init__(True)
+
+    def list_arguments(self):
+        return ["data"]
+
+    def list_outputs(self):
+        return ["output"]
+
+    def list_auxiliary_states(self):
+        return ["alpha"]
+
+    def infer_shape(self, in_shape):
+        shape = in_shape[0]
+        if self.group_size == -1:
+            aux_shape = [1]
+        else:
+            channels = shape[0] if self.is_weight else shape[1]
+            assert channels % self.group_size == 0, \
+                "the channels of weight or activation must be divisible by group size. channels({}) vs group size({})." \
+                .format(channels, self.group_size)
+            aux_shape = [channels // self.group_size]
+        return [shape], [shape], [aux_shape]
+
+    def create_operator(self, ctx, shapes, dtypes):
+        return GDRQ_PY(self.nbits, self.group_size, self.is_weight, self.lamda, self.delay_quant, self.fix_alpha,
+                       self.ktimes)
+
+
+class CLIP_RELU_PY(CustomOp):
+    """GDRQ.py:192-208."""
+
+    def __init__(self, nbits, threshold):
+        self.nbits = nbits
+        self.threshold = threshold
+        self.QUANT_LEVEL = 2 ** (self.nbits) - 1
+        self.count = 0
+
+    def forward(self, is_train, req, in_data, out_data, aux):
+        K.clip_relu_fwd(in_data[0], out_data[0], self.threshold, self.QUANT_LEVEL, req[0])
+
+    def backward(self, req, out_grad, in_data, out_data, in_grad, aux):
+        K.mask_bwd(in_data[0], out_grad[0], in_grad[0], None, self.threshold, _lib.MASK_LT, req[0])
+
+
+@register("CLIP_RELU_PY")
+class CLIP_RELU_PYProp(CustomOpProp):
+    def __init__(self, nbits="8", threshold="8.0"):
+        self.nbits = py_literal(nbits)
+        self.threshold = py_literal(threshold)
+        super(CLIP_RELU_PYProp, self).__init__(True)
+
+    def infer_shape(self, in_shape):
+        return [in_shape[0]], [in_shape[0]], []
+
+    def create_operator(self, ctx, shapes, dtypes):
+        return CLIP_RELU_PY(self.nbits, self.threshold)

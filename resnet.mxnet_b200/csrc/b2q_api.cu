@@ -1,0 +1,374 @@
+// libb2q.so -- lifecycle, primitives and the first-tier fused operator entry points (include/b2q.h).
+#include <cstring>
+#include <string>
+
+#include "b2q_common.cuh"
+#include "b2q_qdq.cuh"
+#include "b2q_reduce.cuh"
+
+static thread_local std::string g_last_error;
+
+void b2q_set_error(const std::string& msg) { g_last_error = msg; }
+
+#define B2Q_CTX(ctx)                                                       \
+    B2Q_REQUIRE((ctx) != nullptr, "null context");                         \
+    B2Q_CHECK_CUDA(cudaSetDevice((ctx)->device))
+
+static const Prescale kNoPrescale = {nullptr, nullptr, 0.f};
+static const FoldBias kNoBias = {nullptr, nullptr, nullptr};
+
+extern "C" {
+
+int b2q_abi_version(void) { return B2Q_ABI_VERSION; }
+
+const char* b2q_last_error(void) { return g_last_error.c_str(); }
+
+int b2q_create(int device, b2q_ctx** out) {
+    B2Q_REQUIRE(out != nullptr, "null out pointer");
+    int count = 0;
+    B2Q_CHECK_CUDA(cudaGetDeviceCount(&count));
+    B2Q_REQUIRE(device >= 0 && device < count, "no such CUDA device");
+    B2Q_CHECK_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    B2Q_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+    b2q_ctx* ctx = new b2q_ctx();
+    memset(ctx, 0, sizeof(*ctx));
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    ctx->blocks_per_sm = 8;
+    ctx->reverse = 1;
+    ctx->fast_div = 1;
+    cudaError_t e = cudaMalloc(&ctx->slots, sizeof(b2q_slot) * B2Q_NSLOTS);
+    if (e != cudaSuccess) {
+        delete ctx;
+        b2q_set_error(std::string("cudaMalloc(workspace) failed: ") + cudaGetErrorString(e));
+        return 1;
+    }
+    e = cudaMemset(ctx->slots, 0, sizeof(b2q_slot) * B2Q_NSLOTS);
+    if (e != cudaSuccess) {
+        cudaFree(ctx->slots);
+        delete ctx;
+        b2q_set_error(std::string("workspace init failed: ") + cudaGetErrorString(e));
+        return 1;
+    }
+    *out = ctx;
+    return 0;
+}
+
+int b2q_destroy(b2q_ctx* ctx) {
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    b2q_host_release(ctx);
+    cudaFree(ctx->slots);
+    delete ctx;
+    return 0;
+}
+
+int b2q_num_sms(b2q_ctx* ctx) { return ctx ? ctx->num_sms : -1; }
+
+int64_t b2q_launch_count(b2q_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+static int* option_slot(b2q_ctx* ctx, const char* key) {
+    if (!strcmp(key, "blocks_per_sm")) return &ctx->blocks_per_sm;
+    if (!strcmp(key, "reverse")) return &ctx->reverse;
+    if (!strcmp(key, "fast_div")) return &ctx->fast_div;
+    return nullptr;
+}
+
+int b2q_set_option(b2q_ctx* ctx, const char* key, int value) {
+    B2Q_REQUIRE(ctx && key, "null argument");
+    int* p = option_slot(ctx, key);
+    B2Q_REQUIRE(p != nullptr, "unknown option");
+    if (p == &ctx->blocks_per_sm) B2Q_REQUIRE(value >= 1 && value <= 32, "blocks_per_sm out of range");
+    *p = value;
+    return 0;
+}
+
+int b2q_get_option(b2q_ctx* ctx, const char* key, int* value) {
+    B2Q_REQUIRE(ctx && key && value, "null argument");
+    int* p = option_slot(ctx, key);
+    B2Q_REQUIRE(p != nullptr, "unknown option");
+    *value = *p;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// primitives
+// ------------------------------------------------------------------------------------------------
+static UpdateArgs stat_only(float* stat) {
+    UpdateArgs u;
+    memset(&u, 0, sizeof(u));
+    u.stat_out = stat;
+    return u;
+}
+
+int b2q_absmax_f32(b2q_ctx* ctx, const float* x, int64_t outer, int64_t groups, int64_t inner, float* stat,
+                   void* stream) {
+    B2Q_CTX(ctx);
+    B2Q_REQUIRE(x && stat, "null pointer");
+    return launch_reduce<true>(ctx, b2q_take_slot(ctx), x, outer, groups, inner, kNoPrescale, stat_only(stat),
+                               (cudaStream_t)stream);
+}
+
+int b2q_meanabs_f32(b2q_ctx* ctx, const float* x, int64_t outer, int64_t groups, int64_t inner, float* stat,
+                    void* stream) {
+    B2Q_CTX(ctx);
+    B2Q_REQUIRE(x && stat, "null pointer");
+    return launch_reduce<false>(ctx, b2q_take_slot(ctx), x, outer, groups, inner, kNoPrescale, stat_only(stat),
+                                (cudaStream_t)stream);
+}
+
+int b2q_threshold_update_f32(b2q_ctx* ctx, int mode, const float* stat, float* aux, float* clip_out,
+                             int64_t groups, float p0, float p1, void* stream) {
+    B2Q_CTX(ctx);
+    B2Q_REQUIRE(stat && aux, "null pointer");
+    B2Q_REQUIRE(mode >= B2Q_UPD_STORE && mode <= B2Q_UPD_TWICE_EMA, "bad update mode");
+    B2Q_REQUIRE(groups >= 1 && groups <= B2Q_MAX_GROUPS, "bad group count");
+    UpdateArgs u;
+    memset(&u, 0, sizeof(u));
+    u.mode = mode; u.write_aux = 1; u.use_aux_as_scale = 1; u.p0 = p0; u.p1 = p1; u.aux = aux; u.clip_out = clip_out;
+    threshold_update_kernel<<<(unsigned)((groups + 127) / 128), 128, 0, (cudaStream_t)stream>>>(stat, (int)groups, u);
+    B2Q_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int b2q_qdq_f32(b2q_ctx* ctx, const float* x, float* y, int64_t outer, int64_t groups, int64_t inner,
+                const float* thr, const float* clip_thr, float qlevel, int clip_mode, int do_round, int req,
+                int32_t* codes, const float* prescale_gamma, const float* prescale_var, float prescale_eps,
+                void* stream) {
+    B2Q_CTX(ctx);
+    if (req == B2Q_REQ_NULL) return 0;
+    B2Q_REQUIRE(x && y && thr, "null pointer");
+    QdqArgs a = {thr, clip_thr, 0.f, 0.f, qlevel, ctx->fast_div, codes, clip_mode, do_round, req};
+    Prescale ps = {prescale_gamma, prescale_var, prescale_eps};
+    return launch_qdq(ctx, x, y, outer, groups, inner, ps, kNoBias, a, (cudaStream_t)stream);
+}
+
+int b2q_ste_bwd_f32(b2q_ctx* ctx, const float* dy, float* dx, int64_t n, int req, void* stream) {
+    B2Q_CTX(ctx);
+    if (req == B2Q_REQ_NULL) return 0;
+    B2Q_REQUIRE(dy && dx && n >= 1, "bad argument");
+    if (dy == dx && req != B2Q_REQ_ADD) return 0;  // in-place identity
+    return launch_bwd_mask<0>(ctx, nullptr, dy, dx, 1, 1, n, nullptr, 0.f, req, (cudaStream_t)stream);
+}
+
+int b2q_mask_bwd_f32(b2q_ctx* ctx, const float* x, const float* dy, float* dx, int64_t outer, int64_t groups,
+                     int64_t inner, const float* thr, float thr_imm, int mask_mode, int req, void* stream) {
+    B2Q_CTX(ctx);
+    if (req == B2Q_REQ_NULL) return 0;
+    B2Q_REQUIRE(x && dy && dx, "null pointer");
+    B2Q_REQUIRE(outer >= 1 && groups >= 1 && inner >= 1, "empty tensor");
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (mask_mode) {
+        case B2Q_MASK_OPEN: return launch_bwd_mask<B2Q_MASK_OPEN>(ctx, x, dy, dx, outer, groups, inner, thr, thr_imm, req, st);
+        case B2Q_MASK_ABS_LE: return launch_bwd_mask<B2Q_MASK_ABS_LE>(ctx, x, dy, dx, outer, groups, inner, thr, thr_imm, req, st);
+        case B2Q_MASK_LT: return launch_bwd_mask<B2Q_MASK_LT>(ctx, x, dy, dx, outer, groups, inner, thr, thr_imm, req, st);
+        default: break;
+    }
+    b2q_set_error("b2q: unknown mask_mode");
+    return 2;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Quantization_int8_V2 / ClipGrad_Quantization_int8
+// ------------------------------------------------------------------------------------------------
+static int minmax_groups(int64_t rows, int64_t cols, int per_channel, int64_t* outer, int64_t* groups, int64_t* inner) {
+    *outer = 1;
+    if (per_channel) { *groups = rows; *inner = cols; }
+    else { *groups = 1; *inner = rows * cols; }
+    return 0;
+}
+
+// Threshold bookkeeping of the two minmax operators.  Returns which buffer the sweep scales with.
+static UpdateArgs minmax_update(int variant, int is_weight, int is_train, int init, float d, float omd, float* aux,
+                                b2q_slot* slot, const float** scale_src) {
+    UpdateArgs u;
+    memset(&u, 0, sizeof(u));
+    u.p0 = d; u.p1 = omd; u.aux = aux;
+    if (is_weight) {
+        u.mode = B2Q_UPD_STORE;
+        u.write_aux = is_train ? 1 : 0;
+        if (variant == 0) {               // quant_ops.py:26-31: scale with the fresh max, store it when training
+            u.use_aux_as_scale = 0;
+            u.scale_out = slot->scale;
+            *scale_src = slot->scale;
+        } else {                          // clip_grad...py:31-35: aux is the source of truth
+            u.use_aux_as_scale = 1;
+            *scale_src = aux;
+        }
+    } else {
+        u.mode = (variant == 1 && init) ? B2Q_UPD_STORE : B2Q_UPD_EMA;   // clip_grad...py:42-46 / quant_ops.py:37
+        u.write_aux = 1;
+        u.use_aux_as_scale = 1;
+        *scale_src = aux;
+    }
+    return u;
+}
+
+int b2q_minmax_quant_fwd_f32(b2q_ctx* ctx, int variant, const float* x, float* y, float* aux, int64_t rows,
+                             int64_t cols, int is_weight, int per_channel, int is_train, int init, float ema_decay,
+                             float one_minus_decay, int req, void* stream) {
+    B2Q_CTX(ctx);
+    B2Q_REQUIRE(x && y && aux, "null pointer");
+    B2Q_REQUIRE(variant == 0 || variant == 1, "variant must be 0 (Quantization_int8_V2) or 1 (ClipGrad)");
+    B2Q_REQUIRE(rows >= 1 && cols >= 1, "empty tensor");
+    B2Q_REQUIRE(!(per_channel && !is_weight), "per-channel thresholds are a weight-only feature");
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t outer, groups, inner;
+    minmax_groups(rows, cols, per_channel && is_weight, &outer, &groups, &inner);
+    const float* scale_src = aux;
+    // Does this call need a reduction?  weight: V2 always, ClipGrad only when training; act: when training.
+    const bool reduce = is_weight ? (variant == 0 || is_train) : (is_train != 0);
+    if (reduce) {
+        b2q_slot* slot = b2q_take_slot(ctx);
+        UpdateArgs u = minmax_update(variant, is_weight, is_train, init, ema_decay, one_minus_decay, aux, slot, &scale_src);
+        int rc = launch_reduce<true>(ctx, slot, x, outer, groups, inner, kNoPrescale, u, st);
+        if (rc) return rc;
+    }
+    // ClipGrad activations are clipped to +-aux and written with [:]= regardless of req (clip_grad...py:48-51)
+    const bool clip = (variant == 1 && !is_weight);
+    int eff_req = req;
+    if (clip) eff_req = B2Q_REQ_WRITE;
+    if (eff_req == B2Q_REQ_NULL) return 0;
+    QdqArgs a = {scale_src, nullptr, 0.f, 0.f, 127.f, ctx->fast_div, nullptr,
+                 clip ? B2Q_CLIP_SYM : B2Q_CLIP_NONE, 1, eff_req};
+    return launch_qdq(ctx, x, y, outer, groups, inner, kNoPrescale, kNoBias, a, st);
+}
+
+int b2q_minmax_quant_stat_f32(b2q_ctx* ctx, const float* x, int64_t rows, int64_t cols, int per_channel,
+                              float* stat_out, void* stream) {
+    B2Q_CTX(ctx);
+    B2Q_REQUIRE(x && stat_out, "null pointer");
+    int64_t outer, groups, inner;
+    minmax_groups(rows, cols, per_channel, &outer, &groups, &inner);
+    return launch_reduce<true>(ctx, b2q_take_slot(ctx), x, outer, groups, inner, kNoPrescale, stat_only(stat_out),
+                               (cudaStream_t)stream);
+}
+
+int b2q_minmax_quant_finish_f32(b2q_ctx* ctx, int variant, const float* x, float* y, float* aux, const float* stat,
+                                int64_t rows, int64_t cols, int is_weight, int per_channel, int is_train, int init,
+                                float ema_decay, float one_minus_decay, int req, void* stream) {
+    B2Q_CTX(ctx);
+    B2Q_REQUIRE(x && y && aux && stat, "null pointer");
+    B2Q_REQUIRE(variant == 0 || variant == 1, "variant must be 0 or 1");
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t outer, groups, inner;
+    minmax_groups(rows, cols, per_channel && is_weight, &outer, &groups, &inner);
+    B2Q_REQUIRE(groups <= B2Q_MAX_GROUPS, "too many channels");
+    b2q_slot* slot = b2q_take_slot(ctx);
+    const float* scale_src = aux;
+    UpdateArgs u = minmax_update(variant, is_weight, is_train, init, ema_decay, one_minus_decay, aux, slot, &scale_src);
+    threshold_update_kernel<<<(unsigned)((groups + 127) / 128), 128, 0, st>>>(stat, (int)groups, u);
+    B2Q_LAUNCH_CHECK(ctx);
+    const bool clip = (variant == 1 && !is_weight);
+    int eff_req = clip ? B2Q_REQ_WRITE : req;
+    if (eff_req == B2Q_REQ_NULL) return 0;
+    QdqArgs a = {scale_src, nullptr, 0.f, 0.f, 127.f, ctx->fast_div, nullptr,
+                 clip ? B2Q_CLIP_SYM : B2Q_CLIP_NONE, 1, eff_req};
+    return launch_qdq(ctx, x, y, outer, groups, inner, kNoPrescale, kNoBias, a, st);
+}
+
+int b2q_clipgrad_bwd_f32(b2q_ctx* ctx, const float* x, const float* dy, float* dx, const float* aux, int64_t n,
+                         void* stream) {
+    B2Q_CTX(ctx);
+    B2Q_REQUIRE(x && dy && dx && aux && n >= 1, "bad argument");
+    // written with [:]= in the reference (clip_grad...py:61-67): req is ignored
+    return launch_bwd_mask<B2Q_MASK_OPEN>(ctx, x, dy, dx, 1, 1, n, aux, 0.f, B2Q_REQ_WRITE, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// GDRQ_PY
+// ------------------------------------------------------------------------------------------------
+int b2q_gdrq_fwd_f32(b2q_ctx* ctx, const float* x, float* y, float* alpha, int64_t outer, int64_t groups,
+                     int64_t inner, int is_weight, int fix_alpha, int do_round, float qlevel, float ktimes,
+                     float lamda, int req, void* stream) {
+    B2Q_CTX(ctx);
+    B2Q_REQUIRE(x && y && alpha, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!fix_alpha) {  // GDRQ.py:70-76 / :97-104 -- runs in eval mode too
+        UpdateArgs u;
+        memset(&u, 0, sizeof(u));
+        u.mode = is_weight ? B2Q_UPD_GDRQ_WEIGHT : B2Q_UPD_GDRQ_ACT;
+        u.write_aux = 1; u.use_aux_as_scale = 1; u.p0 = ktimes; u.p1 = lamda; u.aux = alpha;
+        int rc = launch_reduce<false>(ctx, b2q_take_slot(ctx), x, outer, groups, inner, kNoPrescale, u, st);
+        if (rc) return rc;
+    }
+    if (req == B2Q_REQ_NULL) return 0;
+    // group_size == -1 clips with mx.nd.clip (GDRQ.py:79); grouped mode with where(|x|<=a, x, a*sign(x)) (:109)
+    const int clip = (groups == 1) ? B2Q_CLIP_SYM : B2Q_CLIP_WHERE_LE;
+    QdqArgs a = {alpha, nullptr, 0.f, 0.f, qlevel, ctx->fast_div, nullptr, clip, do_round, req};
+    return launch_qdq(ctx, x, y, outer, groups, inner, kNoPrescale, kNoBias, a, st);
+}
+
+int b2q_gdrq_bwd_f32(b2q_ctx* ctx, const float* x, const float* dy, float* dx, const float* alpha, int64_t outer,
+                     int64_t groups, int64_t inner, int req, void* stream) {
+    B2Q_CTX(ctx);
+    if (req == B2Q_REQ_NULL) return 0;
+    B2Q_REQUIRE(x && dy && dx && alpha, "null pointer");
+    return launch_bwd_mask<B2Q_MASK_ABS_LE>(ctx, x, dy, dx, outer, groups, inner, alpha, 0.f, req, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// GDRQ_Fold_BN
+// ------------------------------------------------------------------------------------------------
+int b2q_foldbn_data_fwd_f32(b2q_ctx* ctx, const float* x, float* y, float* aux_data, int64_t n, int init,
+                            float ema_decay, float one_minus_decay, void* stream) {
+    B2Q_CTX(ctx);
+    B2Q_REQUIRE(x && y && aux_data && n >= 1, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    b2q_slot* slot = b2q_take_slot(ctx);
+    UpdateArgs u;
+    memset(&u, 0, sizeof(u));
+    u.mode = init ? B2Q_UPD_TWICE_STORE : B2Q_UPD_TWICE_EMA;   // fold_bn_v1_gdrq.py:58-64
+    u.write_aux = 1; u.use_aux_as_scale = 1; u.p0 = ema_decay; u.p1 = one_minus_decay; u.aux = aux_data;
+    u.clip_out = slot->clip;                                    // :67 clips with the batch threshold
+    int rc = launch_reduce<false>(ctx, slot, x, 1, 1, n, kNoPrescale, u, st);
+    if (rc) return rc;
+    QdqArgs a = {aux_data, slot->clip, 0.f, 0.f, 127.f, ctx->fast_div, nullptr, B2Q_CLIP_SYM, 1, B2Q_REQ_WRITE};
+    return launch_qdq(ctx, x, y, 1, 1, n, kNoPrescale, kNoBias, a, st);
+}
+
+__global__ void foldbn_scale_only_kernel(const float* __restrict__ w, float* __restrict__ wq, float* __restrict__ bias,
+                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                         const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                                         int64_t cols) {
+    // quantize_flag == False: weight * factor and the folded bias only (fold_bn_v1_gdrq.py:70-74,113)
+    const int64_t row = blockIdx.x;
+    const float den = __fsqrt_rn(__fadd_rn(var[row], eps));
+    const float f = __fdiv_rn(gamma[row], den);
+    for (int64_t i = threadIdx.x; i < cols; i += blockDim.x) wq[row * cols + i] = __fmul_rn(w[row * cols + i], f);
+    if (threadIdx.x == 0 && bias) bias[row] = __fsub_rn(beta[row], __fdiv_rn(__fmul_rn(mean[row], gamma[row]), den));
+}
+
+int b2q_foldbn_weight_fwd_f32(b2q_ctx* ctx, const float* w, float* w_q, float* bias, float* aux_weight,
+                              const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                              int64_t cout, int64_t cols, int per_channel, int quantize, int is_train, void* stream) {
+    B2Q_CTX(ctx);
+    B2Q_REQUIRE(w && w_q && gamma && beta && mean && var, "null pointer");
+    B2Q_REQUIRE(cout >= 1 && cols >= 1, "empty weight");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!quantize) {
+        foldbn_scale_only_kernel<<<(unsigned)cout, 128, 0, st>>>(w, w_q, bias, gamma, beta, mean, var, eps, cols);
+        B2Q_LAUNCH_CHECK(ctx);
+        return 0;
+    }
+    B2Q_REQUIRE(aux_weight != nullptr, "null aux");
+    b2q_slot* slot = b2q_take_slot(ctx);
+    Prescale ps = {gamma, var, eps};
+    FoldBias fb = {bias, beta, mean};
+    // view: per-channel (1, cout, cols); per-tensor (cout, 1, cols) so that the prescale row is o*groups+g either way
+    const int64_t outer = per_channel ? 1 : cout, groups = per_channel ? cout : 1;
+    UpdateArgs u;
+    memset(&u, 0, sizeof(u));
+    u.mode = B2Q_UPD_TWICE_STORE;                 // fold_bn_v1_gdrq.py:82 / :90, aux stored only when training (:94-95)
+    u.write_aux = is_train ? 1 : 0;
+    u.use_aux_as_scale = 0;
+    u.aux = aux_weight;
+    u.scale_out = slot->scale;
+    int rc = launch_reduce<false>(ctx, slot, w, outer, groups, cols, ps, u, st);
+    if (rc) return rc;
+    QdqArgs a = {slot->scale, nullptr, 0.f, 0.f, 127.f, ctx->fast_div, nullptr, B2Q_CLIP_SYM, 1, B2Q_REQ_WRITE};
+    return launch_qdq(ctx, w, w_q, outer, groups, cols, ps, fb, a, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,191 @@
+// Shared device/host infrastructure of libb2q.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/b2q.h"
+
+#define B2Q_MAX_PIECES 16384   // per-launch partial results kept in a workspace slot
+#define B2Q_MAX_GROUPS 8192    // thresholds per tensor (channels / groups)
+#define B2Q_NSLOTS 64          // reductions that may be in flight at once through one ctx
+#define B2Q_THREADS 256
+
+// One in-flight reduction.  `ticket` counts finished blocks; the last block combines `partial` in a fixed
+// order, applies the threshold update and resets the ticket, so a slot is reusable without a memset.
+struct b2q_slot {
+    unsigned int ticket;
+    unsigned int pad[3];
+    float scale[B2Q_MAX_GROUPS];  // threshold T the following QDQ kernel scales with (when it is not aux)
+    float clip[B2Q_MAX_GROUPS];   // threshold the following QDQ kernel clips with (when it differs)
+    double partial[B2Q_MAX_PIECES];
+};
+
+struct b2q_ctx {
+    int device;
+    int num_sms;
+    b2q_slot* slots;      // device
+    unsigned int next_slot;
+    long long launches;
+    // tuning knobs (never change results)
+    int blocks_per_sm;
+    int reverse;
+    int fast_div;
+    void* host_state;     // staging buffers + streams of the host-buffer entry points (b2q_host.cu)
+};
+
+void b2q_set_error(const std::string& msg);
+int b2q_host_release(b2q_ctx* ctx);  // b2q_host.cu
+
+#define B2Q_CHECK_CUDA(expr)                                                                       \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            b2q_set_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " (" +       \
+                          __FILE__ + ":" + std::to_string(__LINE__) + ")");                        \
+            return 1;                                                                              \
+        }                                                                                          \
+    } while (0)
+
+#define B2Q_REQUIRE(cond, msg)                                                                     \
+    do {                                                                                           \
+        if (!(cond)) {                                                                             \
+            b2q_set_error(std::string("b2q: ") + (msg) + " [" #cond "]");                          \
+            return 2;                                                                              \
+        }                                                                                          \
+    } while (0)
+
+#define B2Q_LAUNCH_CHECK(ctx)                                                                      \
+    do {                                                                                           \
+        (ctx)->launches++;                                                                         \
+        B2Q_CHECK_CUDA(cudaGetLastError());                                                        \
+    } while (0)
+
+static inline b2q_slot* b2q_take_slot(b2q_ctx* ctx) {
+    unsigned int i = __atomic_fetch_add(&ctx->next_slot, 1u, __ATOMIC_RELAXED);
+    return ctx->slots + (i % B2Q_NSLOTS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+// 256-bit global accesses (sm_100 LDG.256 / STG.256) with explicit L1/L2 policies.
+// Loads  POL 0: plain                                  (reduction pass: lines should stay in L2)
+//            1: read-only path, no L1 allocation
+//            2: as 1, L2 evict_first                   (last use of the line: the QDQ / backward sweeps)
+//            3: no L1 allocation, L2 evict_last        (reduction pass, keep the tail for the QDQ sweep)
+// Stores POL 0: plain   1: no L1 allocation, L2 evict_first (pure streaming)   2: L2 evict_last
+struct f8 {
+    float v[8];
+};
+
+#define B2Q_LD8(Q)                                                                                       \
+    asm volatile("ld.global" Q ".v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"                                \
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]),   \
+                   "=f"(r.v[6]), "=f"(r.v[7])                                                            \
+                 : "l"(p))
+#define B2Q_ST8(Q)                                                                                       \
+    asm volatile("st.global" Q ".v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(r.v[0]),          \
+                 "f"(r.v[1]), "f"(r.v[2]), "f"(r.v[3]), "f"(r.v[4]), "f"(r.v[5]), "f"(r.v[6]), "f"(r.v[7]) \
+                 : "memory")
+
+template <int POL>
+__device__ __forceinline__ f8 ld_f8(const float* p) {
+    f8 r;
+    if (POL == 0) B2Q_LD8("");
+    else if (POL == 1) B2Q_LD8(".nc.L1::no_allocate.L2::evict_normal");
+    else if (POL == 2) B2Q_LD8(".nc.L1::no_allocate.L2::evict_first");
+    else B2Q_LD8(".L1::no_allocate.L2::evict_last");
+    return r;
+}
+
+template <int POL>
+__device__ __forceinline__ void st_f8(float* p, const f8& r) {
+    if (POL == 0) B2Q_ST8("");
+    else if (POL == 1) B2Q_ST8(".L1::no_allocate.L2::evict_first");
+    else B2Q_ST8(".L2::evict_last");
+}
+
+__device__ __forceinline__ void st_i8(int32_t* p, const int (&c)[8]) {
+    asm volatile("st.global.v8.s32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(c[0]), "r"(c[1]), "r"(c[2]),
+                 "r"(c[3]), "r"(c[4]), "r"(c[5]), "r"(c[6]), "r"(c[7])
+                 : "memory");
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide reduce (fixed tree => deterministic); result valid in thread 0.
+template <bool IS_MAX>
+__device__ __forceinline__ double block_reduce(double v, double* smem /* >= 32 doubles */) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    if (IS_MAX) v = (double)warp_max((float)v); else v = warp_sum(v);
+    if (lane == 0) smem[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        double w = (lane < nw) ? smem[lane] : 0.0;
+        if (IS_MAX) w = (double)warp_max((float)w); else w = warp_sum(w);
+        v = w;
+    }
+    __syncthreads();
+    return v;
+}
+
+// mx.nd.sign: sign(0) = 0
+__device__ __forceinline__ float mx_sign(float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); }
+
+// mx.nd.clip: comparisons, NaN passes through (src/operator/tensor/matrix_op-inl.h [upstream])
+__device__ __forceinline__ float mx_clip(float x, float lo, float hi) {
+    return x > hi ? hi : (x < lo ? lo : x);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Threshold update, shared by the reductions' last block and the stand-alone kernel.
+// Every step is a separately rounded float32 operation, as in the reference's chain of mx.nd calls.
+// ------------------------------------------------------------------------------------------------
+struct UpdateArgs {
+    int mode;        // B2Q_UPD_* or 0 (only emit stat)
+    int write_aux;   // aux is updated (is_train); otherwise aux is left alone
+    int use_aux_as_scale;  // the QDQ pass scales with aux (after update) rather than with the fresh statistic
+    float p0, p1;    // (ema_decay, 1-ema_decay) or (ktimes, lamda)
+    float* aux;      // [groups]
+    float* scale_out;  // [groups] threshold to scale with
+    float* clip_out;   // [groups] threshold to clip with (may be null)
+    float* stat_out;   // [groups] raw statistic (may be null)
+};
+
+__device__ __forceinline__ void apply_update(const UpdateArgs& u, int g, float stat) {
+    if (u.stat_out) u.stat_out[g] = stat;
+    if (u.mode == 0) return;
+    float fresh = stat;   // the batch threshold
+    float a = u.aux ? u.aux[g] : 0.f;
+    float next = a;
+    switch (u.mode) {
+        case B2Q_UPD_STORE: next = stat; break;
+        case B2Q_UPD_EMA: next = __fadd_rn(__fmul_rn(a, u.p0), __fmul_rn(stat, u.p1)); break;
+        case B2Q_UPD_GDRQ_WEIGHT: fresh = __fmul_rn(u.p0, stat); next = fresh; break;
+        case B2Q_UPD_GDRQ_ACT:
+            fresh = __fmul_rn(u.p0, stat);
+            next = __fadd_rn(a, __fmul_rn(u.p1, __fsub_rn(a, fresh)));
+            break;
+        case B2Q_UPD_TWICE_STORE: fresh = __fmul_rn(2.f, stat); next = fresh; break;
+        case B2Q_UPD_TWICE_EMA:
+            fresh = __fmul_rn(2.f, stat);
+            next = __fadd_rn(__fmul_rn(a, u.p0), __fmul_rn(fresh, u.p1));
+            break;
+        default: break;
+    }
+    if (u.write_aux && u.aux) u.aux[g] = next;
+    const float after = u.write_aux ? next : a;
+    if (u.scale_out) u.scale_out[g] = u.use_aux_as_scale ? after : fresh;
+    if (u.clip_out) u.clip_out[g] = fresh;
+}

@@ -1,0 +1,436 @@
+// K4/K8: the single-sweep clip + quantize-dequantize kernels, and K5/K6 backward passes.
+#pragma once
+#include "b2q_common.cuh"
+#include "b2q_reduce.cuh"
+
+// Compile-time tuning of the flat sweeps (tools/sweep.cu on B200 picks these; see profiles/).
+#ifndef B2Q_QDQ_UNROLL
+#define B2Q_QDQ_UNROLL 2
+#endif
+#ifndef B2Q_QDQ_LDPOL
+#define B2Q_QDQ_LDPOL 2   // x: read-only path, L2 evict_first (last forward use of the line)
+#endif
+#ifndef B2Q_QDQ_STPOL
+#define B2Q_QDQ_STPOL 0   // y: plain store -- the convolution reads it next, let it live in L2
+#endif
+#ifndef B2Q_BWD_UNROLL
+#define B2Q_BWD_UNROLL 2
+#endif
+#ifndef B2Q_BWD_LDPOL
+#define B2Q_BWD_LDPOL 2
+#endif
+#ifndef B2Q_BWD_STPOL
+#define B2Q_BWD_STPOL 0
+#endif
+
+// ------------------------------------------------------------------------------------------------
+// Exact emulation of the reference's three kernels   t = x / q ; c = round(t) ; y = c * q
+// (symbol/quant_ops.py:28,40) = fl(roundf(fl(x/q)) * q).
+//
+// IEEE division (~9 issue slots) plus roundf (~4) would make the sweep issue-bound at HBM speed, so the
+// common case uses the reciprocal: t' = fl(x * r), r = fl(1/q).  Both roundings are within 2^-24 relative, and
+// so is fl(x/q), hence |t' - fl(x/q)| <= 0.75 * 2^-22 * |t'| and rint(t') == roundf(fl(x/q)) whenever t' is
+// farther than |t'| * 2^-21 from the nearest half-integer (margin 2.6x).  Everything else -- exact ties,
+// near-ties, codes >= 2^20, NaN/Inf, q outside [2^-100, 2^100] -- takes the reference arithmetic verbatim.
+// The result is bit-identical to the slow path for every input; only how often the slow path runs
+// (~1e-4 of elements for |code| ~ 100) depends on the data.
+// ------------------------------------------------------------------------------------------------
+struct QScale {
+    float q;   // quantisation step fl(T / L)
+    float r;   // fl(1/q), or NaN when the fast path must not be used
+};
+
+__device__ __forceinline__ QScale make_qscale(float T, float qlevel, bool fast) {
+    QScale s;
+    s.q = qlevel > 0.f ? __fdiv_rn(T, qlevel) : T;
+    const float aq = fabsf(s.q);
+    s.r = (fast && aq > 0x1p-100f && aq < 0x1p100f) ? __frcp_rn(s.q) : __int_as_float(0x7fc00000);
+    return s;
+}
+
+// reference arithmetic, verbatim
+__device__ __forceinline__ float quant_code_exact(float x, float q) { return roundf(__fdiv_rn(x, q)); }
+
+// fast candidate + safety test.  safe <=> |t - rint(t)| + |t| * 2^-21 < 0.5  (false for NaN and |t| >= 2^20)
+__device__ __forceinline__ float quant_code_try(float x, float r, bool& safe) {
+    const float t = __fmul_rn(x, r);
+    const float c = rintf(t);
+    const float d = __fsub_rn(t, c);
+    safe = safe && (__fmaf_rn(fabsf(t), 0x1p-21f, fabsf(d)) < 0.5f);
+    return c;
+}
+
+__device__ __forceinline__ float quant_code(float x, const QScale& s) {
+    bool safe = true;
+    float c = quant_code_try(x, s.r, safe);
+    if (!safe) c = quant_code_exact(x, s.q);
+    return c;
+}
+
+// Eight elements at once: one divergence point per 256-bit word instead of one per element.
+// CLIP_SYM uses min/max on the fast path, which equals mx.nd.clip for T >= 0 and non-NaN x; the caller
+// disables the fast path (r = NaN) when T < 0, and NaN inputs fail the safety test by themselves.
+template <bool CLIP_SYM>
+__device__ __forceinline__ void qdq8(const f8& in, f8& out, float Tc, const QScale& s) {
+    bool safe = true;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float c = CLIP_SYM ? fminf(fmaxf(in.v[j], -Tc), Tc) : in.v[j];
+        out.v[j] = __fmul_rn(quant_code_try(c, s.r, safe), s.q);
+    }
+    if (!safe) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float c = CLIP_SYM ? mx_clip(in.v[j], -Tc, Tc) : in.v[j];
+            out.v[j] = __fmul_rn(quant_code_exact(c, s.q), s.q);
+        }
+    }
+}
+
+__device__ __forceinline__ float clip_value(int clip, float x, float T) {
+    switch (clip) {
+        case B2Q_CLIP_SYM: return mx_clip(x, -T, T);
+        case B2Q_CLIP_WHERE_LE: return (fabsf(x) <= T) ? x : __fmul_rn(T, mx_sign(x));
+        case B2Q_CLIP_ZERO_T: return mx_clip(x, 0.f, T);
+        case B2Q_CLIP_PACT: return (x < T) ? x : T;
+        case B2Q_CLIP_WHERE_LT: return (fabsf(x) < T) ? x : __fmul_rn(T, mx_sign(x));
+        default: return x;
+    }
+}
+
+__device__ __forceinline__ int32_t code_to_i32(float c) {
+    return __float2int_rn(c);  // saturating, NaN -> 0
+}
+
+struct QdqArgs {
+    const float* thr;       // [groups] scale threshold (device) or null -> thr_imm
+    const float* clip_thr;  // [groups] clip threshold (device) or null -> same as thr / clip_imm
+    float thr_imm, clip_imm;
+    float qlevel;
+    int fast;
+    int32_t* codes;
+    int clip_mode, do_round, req;   // used by the generic kernels only
+};
+
+__device__ __forceinline__ float qdq_generic(const QdqArgs& a, float x, float Tc, const QScale& s, float& code) {
+    const float c = clip_value(a.clip_mode, x, Tc);
+    if (!a.do_round) { code = 0.f; return c; }
+    code = quant_code(c, s);
+    return __fmul_rn(code, s.q);
+}
+
+// ------------------------------------------------------------------------------------------------
+// HOT kernel: whole tensor, clip none / symmetric, round, req=write, no codes.
+// Tiles are visited in DESCENDING address order: the reduction that precedes it walked ascending, so the
+// tail of x is still in the 126 MB L2.  x is loaded evict-first (last use); y is stored plainly because the
+// convolution reads it next.
+// ------------------------------------------------------------------------------------------------
+template <bool CLIP_SYM, int UNROLL, int LDPOL, int STPOL>
+__global__ void __launch_bounds__(B2Q_THREADS)
+qdq_flat_hot_kernel(const float* __restrict__ x, float* __restrict__ y, FlatSplit sp, QdqArgs a, int reverse) {
+    const float T = a.thr ? __ldg(a.thr) : a.thr_imm;
+    const float Tc = a.clip_thr ? __ldg(a.clip_thr) : (a.thr ? T : a.clip_imm);
+    const QScale s = make_qscale(T, a.qlevel, a.fast != 0 && !(CLIP_SYM && !(Tc >= 0.f)));
+    const float* xb = x + sp.head;
+    float* yb = y + sp.head;
+    const int64_t tile = (int64_t)B2Q_THREADS * UNROLL;
+    const int64_t ntiles = (sp.n8 + tile - 1) / tile;
+    for (int64_t tt = blockIdx.x; tt < ntiles; tt += gridDim.x) {
+        const int64_t t = reverse ? (ntiles - 1 - tt) : tt;
+        const int64_t base = t * tile + threadIdx.x;
+        f8 v[UNROLL];
+#pragma unroll
+        for (int k = 0; k < UNROLL; ++k) {
+            const int64_t i = base + (int64_t)k * B2Q_THREADS;
+            if (i < sp.n8) v[k] = ld_f8<LDPOL>(xb + 8 * i);
+        }
+#pragma unroll
+        for (int k = 0; k < UNROLL; ++k) {
+            const int64_t i = base + (int64_t)k * B2Q_THREADS;
+            if (i < sp.n8) {
+                f8 o;
+                qdq8<CLIP_SYM>(v[k], o, Tc, s);
+                st_f8<STPOL>(yb + 8 * i, o);
+            }
+        }
+    }
+    if (blockIdx.x == 0) {  // unaligned head / tail scalars
+        const int64_t tid = threadIdx.x;
+        int64_t idx = -1;
+        if (tid < sp.head) idx = tid;
+        else if (tid - sp.head < sp.tail) idx = sp.head + 8 * sp.n8 + (tid - sp.head);
+        if (idx >= 0) {
+            const float c = CLIP_SYM ? mx_clip(x[idx], -Tc, Tc) : x[idx];
+            y[idx] = __fmul_rn(quant_code(c, s), s.q);
+        }
+    }
+}
+
+// Generic whole-tensor sweep: any clip mode, optional rounding, req add, optional codes (runtime flags).
+template <int UNROLL>
+__global__ void __launch_bounds__(B2Q_THREADS)
+qdq_flat_generic_kernel(const float* __restrict__ x, float* __restrict__ y, FlatSplit sp, QdqArgs a) {
+    const float T = a.thr ? __ldg(a.thr) : a.thr_imm;
+    const float Tc = a.clip_thr ? __ldg(a.clip_thr) : (a.thr ? T : a.clip_imm);
+    const QScale s = make_qscale(T, a.qlevel, a.fast != 0);
+    const float* xb = x + sp.head;
+    float* yb = y + sp.head;
+    const bool add = (a.req == B2Q_REQ_ADD);
+    const int64_t tile = (int64_t)B2Q_THREADS * UNROLL;
+    const int64_t ntiles = (sp.n8 + tile - 1) / tile;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t base = t * tile + threadIdx.x;
+#pragma unroll
+        for (int k = 0; k < UNROLL; ++k) {
+            const int64_t i = base + (int64_t)k * B2Q_THREADS;
+            if (i < sp.n8) {
+                const f8 v = ld_f8<1>(xb + 8 * i);
+                f8 o;
+                int cc[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float code;
+                    o.v[j] = qdq_generic(a, v.v[j], Tc, s, code);
+                    cc[j] = code_to_i32(code);
+                }
+                if (add) {
+                    const f8 old = ld_f8<0>(yb + 8 * i);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o.v[j] = __fadd_rn(old.v[j], o.v[j]);
+                }
+                st_f8<0>(yb + 8 * i, o);
+                if (a.codes) st_i8(a.codes + sp.head + 8 * i, cc);
+            }
+        }
+    }
+    if (blockIdx.x == 0) {
+        const int64_t tid = threadIdx.x;
+        int64_t idx = -1;
+        if (tid < sp.head) idx = tid;
+        else if (tid - sp.head < sp.tail) idx = sp.head + 8 * sp.n8 + (tid - sp.head);
+        if (idx >= 0) {
+            float code;
+            float o = qdq_generic(a, x[idx], Tc, s, code);
+            if (add) o = __fadd_rn(y[idx], o);
+            y[idx] = o;
+            if (a.codes) a.codes[idx] = code_to_i32(code);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Segmented sweep over (outer, groups, inner) with one threshold per group and optional fold-BN prescale.
+// Also writes the folded bias when `bias` is given (fold_bn_v1_gdrq.py:113).
+// ------------------------------------------------------------------------------------------------
+struct FoldBias {
+    float* bias;         // [rows] or null
+    const float* beta;
+    const float* mean;
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(128)
+qdq_seg_kernel(const float* __restrict__ x, float* __restrict__ y, SegPlan pl, Prescale ps, FoldBias fb, QdqArgs a) {
+    const SegPiece pc = seg_piece(pl);
+    const float T = a.thr ? __ldg(a.thr + pc.g) : a.thr_imm;
+    const float Tc = a.clip_thr ? __ldg(a.clip_thr + pc.g) : (a.thr ? T : a.clip_imm);
+    const QScale qs = make_qscale(T, a.qlevel, a.fast != 0);
+    const bool add = (a.req == B2Q_REQ_ADD);
+    for (int64_t o = pc.o0; o < pc.o1; ++o) {
+        const int64_t row = o * pl.groups + pc.g;
+        const float* xb = x + row * pl.inner;
+        float* yb = y + row * pl.inner;
+        int32_t* cb = a.codes ? a.codes + row * pl.inner : nullptr;
+        const float f = ps.gamma ? prescale_factor(ps, row) : 1.f;
+        if (fb.bias && pc.p == 0 && threadIdx.x == 0) {
+            // bias = beta - mean*gamma/sqrt(var+eps), each step rounded (fold_bn_v1_gdrq.py:113)
+            const float den = __fsqrt_rn(__fadd_rn(ps.var[row], ps.eps));
+            fb.bias[row] = __fsub_rn(fb.beta[row], __fdiv_rn(__fmul_rn(fb.mean[row], ps.gamma[row]), den));
+        }
+        if (VEC == 4) {
+            const float4* x4 = reinterpret_cast<const float4*>(xb);
+            float4* y4 = reinterpret_cast<float4*>(yb);
+            for (int64_t i = (pc.i0 >> 2) + threadIdx.x; i < (pc.i1 >> 2); i += blockDim.x) {
+                float4 v = x4[i];
+                if (ps.gamma) { v.x = __fmul_rn(v.x, f); v.y = __fmul_rn(v.y, f); v.z = __fmul_rn(v.z, f); v.w = __fmul_rn(v.w, f); }
+                float4 r;
+                float cx, cy, cz, cw;
+                r.x = qdq_generic(a, v.x, Tc, qs, cx);
+                r.y = qdq_generic(a, v.y, Tc, qs, cy);
+                r.z = qdq_generic(a, v.z, Tc, qs, cz);
+                r.w = qdq_generic(a, v.w, Tc, qs, cw);
+                if (add) {
+                    const float4 old = y4[i];
+                    r.x = __fadd_rn(old.x, r.x); r.y = __fadd_rn(old.y, r.y);
+                    r.z = __fadd_rn(old.z, r.z); r.w = __fadd_rn(old.w, r.w);
+                }
+                y4[i] = r;
+                if (cb) {
+                    cb[4 * i + 0] = code_to_i32(cx); cb[4 * i + 1] = code_to_i32(cy);
+                    cb[4 * i + 2] = code_to_i32(cz); cb[4 * i + 3] = code_to_i32(cw);
+                }
+            }
+        } else {
+            for (int64_t i = pc.i0 + threadIdx.x; i < pc.i1; i += blockDim.x) {
+                float v = xb[i];
+                if (ps.gamma) v = __fmul_rn(v, f);
+                float c;
+                float r = qdq_generic(a, v, Tc, qs, c);
+                if (add) r = __fadd_rn(yb[i], r);
+                yb[i] = r;
+                if (cb) cb[i] = code_to_i32(c);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: straight-through backward (copy / accumulate), K6: masked backward.
+// ------------------------------------------------------------------------------------------------
+template <int MASK>
+__device__ __forceinline__ float mask_grad(float x, float dy, float T) {
+    // multiplications by 0.0/1.0 exactly as the reference does (keeps -0.0 and NaN propagation identical)
+    if (MASK == B2Q_MASK_OPEN)
+        return __fmul_rn(__fmul_rn(dy, (x > -T) ? 1.f : 0.f), (x < T) ? 1.f : 0.f);
+    if (MASK == B2Q_MASK_ABS_LE) return __fmul_rn(dy, (fabsf(x) <= T) ? 1.f : 0.f);
+    if (MASK == B2Q_MASK_LT) return __fmul_rn(dy, (x < T) ? 1.f : 0.f);
+    return dy;
+}
+
+// MASK == 0: plain STE copy (x unused).
+template <int MASK, bool ADD, int UNROLL, int LDPOL, int STPOL>
+__global__ void __launch_bounds__(B2Q_THREADS)
+bwd_flat_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, FlatSplit sp,
+                const float* thr, float thr_imm) {
+    const float T = (MASK != 0) ? (thr ? __ldg(thr) : thr_imm) : 0.f;
+    const float* xb = x + sp.head;
+    const float* gb = dy + sp.head;
+    float* ob = dx + sp.head;
+    const int64_t tile = (int64_t)B2Q_THREADS * UNROLL;
+    const int64_t ntiles = (sp.n8 + tile - 1) / tile;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t base = t * tile + threadIdx.x;
+        f8 xv[UNROLL], gv[UNROLL], ov[UNROLL];
+#pragma unroll
+        for (int k = 0; k < UNROLL; ++k) {
+            const int64_t i = base + (int64_t)k * B2Q_THREADS;
+            if (i < sp.n8) {
+                gv[k] = ld_f8<LDPOL>(gb + 8 * i);
+                if (MASK != 0) xv[k] = ld_f8<LDPOL>(xb + 8 * i);
+                if (ADD) ov[k] = ld_f8<0>(ob + 8 * i);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < UNROLL; ++k) {
+            const int64_t i = base + (int64_t)k * B2Q_THREADS;
+            if (i < sp.n8) {
+                f8 r = gv[k];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (MASK != 0) r.v[j] = mask_grad<MASK>(xv[k].v[j], gv[k].v[j], T);
+                    if (ADD) r.v[j] = __fadd_rn(ov[k].v[j], r.v[j]);
+                }
+                st_f8<STPOL>(ob + 8 * i, r);
+            }
+        }
+    }
+    if (blockIdx.x == 0) {
+        const int64_t tid = threadIdx.x;
+        int64_t idx = -1;
+        if (tid < sp.head) idx = tid;
+        else if (tid - sp.head < sp.tail) idx = sp.head + 8 * sp.n8 + (tid - sp.head);
+        if (idx >= 0) {
+            float r = (MASK != 0) ? mask_grad<MASK>(x[idx], dy[idx], T) : dy[idx];
+            if (ADD) r = __fadd_rn(dx[idx], r);
+            dx[idx] = r;
+        }
+    }
+}
+
+template <int MASK, bool ADD>
+__global__ void __launch_bounds__(128)
+bwd_seg_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, SegPlan pl,
+               const float* thr, float thr_imm) {
+    const SegPiece pc = seg_piece(pl);
+    const float T = thr ? __ldg(thr + pc.g) : thr_imm;
+    for (int64_t o = pc.o0; o < pc.o1; ++o) {
+        const int64_t off = (o * pl.groups + pc.g) * pl.inner;
+        for (int64_t i = pc.i0 + threadIdx.x; i < pc.i1; i += blockDim.x) {
+            float r = (MASK != 0) ? mask_grad<MASK>(x[off + i], dy[off + i], T) : dy[off + i];
+            if (ADD) r = __fadd_rn(dx[off + i], r);
+            dx[off + i] = r;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------------
+static inline bool same_misalignment(const void* a, const void* b) {
+    return (((uintptr_t)a ^ (uintptr_t)b) & 31) == 0;
+}
+
+static int launch_qdq(b2q_ctx* ctx, const float* x, float* y, int64_t outer, int64_t groups, int64_t inner,
+                      Prescale ps, FoldBias fb, QdqArgs a, cudaStream_t st) {
+    B2Q_REQUIRE(outer >= 1 && groups >= 1 && inner >= 1, "empty tensor");
+    B2Q_REQUIRE(a.req == B2Q_REQ_WRITE || a.req == B2Q_REQ_INPLACE || a.req == B2Q_REQ_ADD, "bad req");
+    B2Q_REQUIRE(a.clip_mode >= B2Q_CLIP_NONE && a.clip_mode <= B2Q_CLIP_WHERE_LT, "unknown clip_mode");
+    const int64_t n = outer * groups * inner;
+    if (groups == 1 && ps.gamma == nullptr) {
+        FlatSplit sp = b2q_flat_split(x, n);
+        bool ok = same_misalignment(x, y) && (!a.codes || ((((uintptr_t)x >> 2) & 7) == (((uintptr_t)a.codes >> 2) & 7)));
+        if (ok && sp.head <= B2Q_THREADS) {
+            const bool hot = a.do_round && a.req != B2Q_REQ_ADD && !a.codes &&
+                             (a.clip_mode == B2Q_CLIP_NONE || a.clip_mode == B2Q_CLIP_SYM);
+            if (hot) {
+                const int64_t grid = b2q_flat_grid(ctx, sp.n8, B2Q_QDQ_UNROLL);
+                if (a.clip_mode == B2Q_CLIP_SYM)
+                    qdq_flat_hot_kernel<true, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, B2Q_QDQ_STPOL>
+                        <<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, y, sp, a, ctx->reverse);
+                else
+                    qdq_flat_hot_kernel<false, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, B2Q_QDQ_STPOL>
+                        <<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, y, sp, a, ctx->reverse);
+            } else {
+                const int64_t grid = b2q_flat_grid(ctx, sp.n8, 2);
+                qdq_flat_generic_kernel<2><<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, y, sp, a);
+            }
+            B2Q_LAUNCH_CHECK(ctx);
+            return 0;
+        }
+        outer = 1; inner = n;  // mutually misaligned buffers: scalar segmented path
+    }
+    SegPlan pl = b2q_seg_plan(x, y, outer, groups, inner, ctx->num_sms * 8);
+    const unsigned grid = (unsigned)(groups * pl.S * pl.P);
+    if (pl.vec == 4) qdq_seg_kernel<4><<<grid, 128, 0, st>>>(x, y, pl, ps, fb, a);
+    else qdq_seg_kernel<1><<<grid, 128, 0, st>>>(x, y, pl, ps, fb, a);
+    B2Q_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+template <int MASK>
+static int launch_bwd_mask(b2q_ctx* ctx, const float* x, const float* dy, float* dx, int64_t outer, int64_t groups,
+                           int64_t inner, const float* thr, float thr_imm, int req, cudaStream_t st) {
+    const int64_t n = outer * groups * inner;
+    const bool add = (req == B2Q_REQ_ADD);
+    if (groups == 1) {
+        FlatSplit sp = b2q_flat_split(dy, n);
+        bool ok = same_misalignment(dy, dx) && (MASK == 0 || same_misalignment(dy, x));
+        if (ok && sp.head <= B2Q_THREADS) {
+            const int64_t grid = b2q_flat_grid(ctx, sp.n8, B2Q_BWD_UNROLL);
+            if (add) bwd_flat_kernel<MASK, true, B2Q_BWD_UNROLL, B2Q_BWD_LDPOL, B2Q_BWD_STPOL>
+                    <<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, dy, dx, sp, thr, thr_imm);
+            else bwd_flat_kernel<MASK, false, B2Q_BWD_UNROLL, B2Q_BWD_LDPOL, B2Q_BWD_STPOL>
+                    <<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, dy, dx, sp, thr, thr_imm);
+            B2Q_LAUNCH_CHECK(ctx);
+            return 0;
+        }
+        outer = 1; inner = n;
+    }
+    B2Q_REQUIRE(thr != nullptr || groups == 1, "grouped mask needs a device threshold vector");
+    SegPlan pl = b2q_seg_plan(nullptr, nullptr, outer, groups, inner, ctx->num_sms * 8);
+    const unsigned grid = (unsigned)(groups * pl.S * pl.P);
+    if (add) bwd_seg_kernel<MASK, true><<<grid, 128, 0, st>>>(x, dy, dx, pl, thr, thr_imm);
+    else bwd_seg_kernel<MASK, false><<<grid, 128, 0, st>>>(x, dy, dx, pl, thr, thr_imm);
+    B2Q_LAUNCH_CHECK(ctx);
+    return 0;
+}

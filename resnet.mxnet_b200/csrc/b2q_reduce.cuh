@@ -1,0 +1,276 @@
+// K1/K2/K7: max|x| and sum|x| reductions with the threshold update fused into the last block.
+#pragma once
+#include "b2q_common.cuh"
+
+// Compile-time tuning of the flat (whole-tensor) kernels; chosen from tools/sweep.cu runs on B200
+// (profiles/).  UNROLL = independent 256-bit accesses in flight per thread.
+#ifndef B2Q_REDUCE_UNROLL
+#define B2Q_REDUCE_UNROLL 4
+#endif
+#ifndef B2Q_REDUCE_LDPOL
+#define B2Q_REDUCE_LDPOL 0
+#endif
+
+// A flat float32 array split for 256-bit access: `head` scalars until 32-byte alignment, n8 groups of eight
+// floats, `tail` scalars.
+struct FlatSplit {
+    int64_t head, n8, tail;
+};
+
+static inline FlatSplit b2q_flat_split(const void* p, int64_t n) {
+    FlatSplit s;
+    int64_t mis = (int64_t)(((uintptr_t)p >> 2) & 7);
+    s.head = mis ? (8 - mis) : 0;
+    if (((uintptr_t)p & 3) != 0) s.head = n;  // not float aligned: all scalar
+    if (s.head > n) s.head = n;
+    s.n8 = (n - s.head) / 8;
+    s.tail = n - s.head - 8 * s.n8;
+    return s;
+}
+
+template <bool IS_MAX>
+__device__ __forceinline__ void acc1(double& a, float& m, float v) {
+    if (IS_MAX) m = fmaxf(m, fabsf(v)); else a += (double)fabsf(v);
+}
+
+template <bool IS_MAX>
+__device__ __forceinline__ void acc8(double& a, float& m, const f8& r) {
+    if (IS_MAX) {
+        const float m0 = fmaxf(fabsf(r.v[0]), fabsf(r.v[1])), m1 = fmaxf(fabsf(r.v[2]), fabsf(r.v[3]));
+        const float m2 = fmaxf(fabsf(r.v[4]), fabsf(r.v[5])), m3 = fmaxf(fabsf(r.v[6]), fabsf(r.v[7]));
+        m = fmaxf(m, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+    } else {
+        // double accumulation: every float32 -> double conversion and each pair sum below 2^53 ulps is exact
+        const double s0 = (double)fabsf(r.v[0]) + (double)fabsf(r.v[1]);
+        const double s1 = (double)fabsf(r.v[2]) + (double)fabsf(r.v[3]);
+        const double s2 = (double)fabsf(r.v[4]) + (double)fabsf(r.v[5]);
+        const double s3 = (double)fabsf(r.v[6]) + (double)fabsf(r.v[7]);
+        a += (s0 + s1) + (s2 + s3);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Whole-tensor reduction (groups == 1): the hot kernel for activations.
+// Grid-stride over tiles of THREADS*UNROLL 256-bit words in ASCENDING address order, so that the most
+// recently read part of x is what remains in L2 for the QDQ sweep that follows (which walks descending).
+// ------------------------------------------------------------------------------------------------
+template <bool IS_MAX, int UNROLL, int LDPOL>
+__global__ void __launch_bounds__(B2Q_THREADS)
+reduce_flat_kernel(const float* __restrict__ x, FlatSplit sp, b2q_slot* slot, UpdateArgs u, float count) {
+    __shared__ double smem[32];
+    __shared__ unsigned int s_ticket;
+    double acc = 0.0;
+    float mx = 0.f;
+    const float* xb = x + sp.head;
+    const int64_t tile = (int64_t)B2Q_THREADS * UNROLL;
+    const int64_t ntiles = (sp.n8 + tile - 1) / tile;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t base = t * tile + threadIdx.x;
+        f8 v[UNROLL];
+#pragma unroll
+        for (int k = 0; k < UNROLL; ++k) {
+            const int64_t i = base + (int64_t)k * B2Q_THREADS;
+            if (i < sp.n8) v[k] = ld_f8<LDPOL>(xb + 8 * i);
+            else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[k].v[j] = 0.f;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < UNROLL; ++k) acc8<IS_MAX>(acc, mx, v[k]);
+    }
+    if (blockIdx.x == 0) {  // the (at most 14) unaligned scalars
+        if ((int64_t)threadIdx.x < sp.head) acc1<IS_MAX>(acc, mx, x[threadIdx.x]);
+        if ((int64_t)threadIdx.x < sp.tail) acc1<IS_MAX>(acc, mx, x[sp.head + 8 * sp.n8 + threadIdx.x]);
+    }
+    double r = block_reduce<IS_MAX>(IS_MAX ? (double)mx : acc, smem);
+    if (threadIdx.x == 0) {
+        slot->partial[blockIdx.x] = r;
+        __threadfence();
+        s_ticket = atomicAdd(&slot->ticket, 1u);
+    }
+    __syncthreads();
+    if (s_ticket != gridDim.x - 1) return;
+    // ---- last block: combine in fixed order, update the threshold ----
+    __threadfence();
+    double a = 0.0;
+    float m = 0.f;
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
+        double p = __ldcg(&slot->partial[i]);
+        if (IS_MAX) m = fmaxf(m, (float)p); else a += p;
+    }
+    double tot = block_reduce<IS_MAX>(IS_MAX ? (double)m : a, smem);
+    if (threadIdx.x == 0) {
+        float stat = IS_MAX ? (float)tot : __fdiv_rn((float)tot, count);
+        apply_update(u, 0, stat);
+        slot->ticket = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Segmented reduction over a (outer, groups, inner) view.  Piece (g, s, p) covers outer-range s and
+// inner-range p of group g; partial[(g*S + s)*P + p].  Optional per-row prescale (fold-BN).
+// ------------------------------------------------------------------------------------------------
+struct SegPlan {
+    int64_t outer, groups, inner;
+    int S, P;            // splits of outer / inner
+    int64_t part;        // inner elements per p-part (multiple of 4)
+    int vec;             // 1 or 4
+};
+
+static inline SegPlan b2q_seg_plan(const void* x, const void* y, int64_t outer, int64_t groups, int64_t inner,
+                                   int target_pieces) {
+    SegPlan pl;
+    pl.outer = outer; pl.groups = groups; pl.inner = inner;
+    bool aligned = (((uintptr_t)x & 15) == 0) && (((uintptr_t)y & 15) == 0) && (inner % 4 == 0);
+    pl.vec = aligned ? 4 : 1;
+    int64_t want = (target_pieces + groups - 1) / groups;  // pieces per group
+    if (want < 1) want = 1;
+    int64_t S = outer < want ? outer : want;
+    if (S < 1) S = 1;
+    int64_t wantP = (want + S - 1) / S;
+    int64_t min_part = 2048;  // do not cut rows into pieces smaller than this many elements
+    int64_t maxP = (inner + min_part - 1) / min_part;
+    int64_t P = wantP < maxP ? wantP : maxP;
+    if (P < 1) P = 1;
+    while (groups * S * P > B2Q_MAX_PIECES && P > 1) --P;
+    while (groups * S * P > B2Q_MAX_PIECES && S > 1) --S;
+    int64_t part = (inner + P - 1) / P;
+    part = (part + 3) & ~(int64_t)3;
+    P = (inner + part - 1) / part;
+    if (P < 1) P = 1;
+    pl.S = (int)S; pl.P = (int)P; pl.part = part;
+    return pl;
+}
+
+struct SegPiece {
+    int64_t g, o0, o1, i0, i1;
+    int p;
+};
+
+__device__ __forceinline__ SegPiece seg_piece(const SegPlan& pl) {
+    SegPiece sp;
+    const int64_t piece = blockIdx.x;
+    const int SP = pl.S * pl.P;
+    sp.g = piece / SP;
+    const int s = (int)((piece / pl.P) % pl.S);
+    sp.p = (int)(piece % pl.P);
+    sp.o0 = (pl.outer * s) / pl.S;
+    sp.o1 = (pl.outer * (s + 1)) / pl.S;
+    sp.i0 = (int64_t)sp.p * pl.part;
+    sp.i1 = sp.i0 + pl.part;
+    if (sp.i1 > pl.inner) sp.i1 = pl.inner;
+    return sp;
+}
+
+struct Prescale {  // fold-BN factor gamma/sqrt(var+eps) per row (o*groups+g); gamma == nullptr: none
+    const float* gamma;
+    const float* var;
+    float eps;
+};
+
+__device__ __forceinline__ float prescale_factor(const Prescale& ps, int64_t row) {
+    // symbol/fold_bn_v1_gdrq.py:72  factor = bn_gamma / sqrt(bn_var + eps); each step rounded
+    return __fdiv_rn(ps.gamma[row], __fsqrt_rn(__fadd_rn(ps.var[row], ps.eps)));
+}
+
+template <bool IS_MAX, int VEC>
+__global__ void __launch_bounds__(128)
+reduce_seg_kernel(const float* __restrict__ x, SegPlan pl, Prescale ps, b2q_slot* slot, UpdateArgs u) {
+    __shared__ double smem[32];
+    __shared__ unsigned int s_ticket;
+    const SegPiece pc = seg_piece(pl);
+    double acc = 0.0;
+    float mx = 0.f;
+    for (int64_t o = pc.o0; o < pc.o1; ++o) {
+        const int64_t row = o * pl.groups + pc.g;
+        const float* base = x + row * pl.inner;
+        const float f = ps.gamma ? prescale_factor(ps, row) : 1.f;
+        if (VEC == 4) {
+            const float4* b4 = reinterpret_cast<const float4*>(base);
+            for (int64_t i = (pc.i0 >> 2) + threadIdx.x; i < (pc.i1 >> 2); i += blockDim.x) {
+                float4 v = b4[i];
+                if (ps.gamma) { v.x = __fmul_rn(v.x, f); v.y = __fmul_rn(v.y, f); v.z = __fmul_rn(v.z, f); v.w = __fmul_rn(v.w, f); }
+                acc1<IS_MAX>(acc, mx, v.x); acc1<IS_MAX>(acc, mx, v.y);
+                acc1<IS_MAX>(acc, mx, v.z); acc1<IS_MAX>(acc, mx, v.w);
+            }
+        } else {
+            for (int64_t i = pc.i0 + threadIdx.x; i < pc.i1; i += blockDim.x) {
+                float v = base[i];
+                if (ps.gamma) v = __fmul_rn(v, f);
+                acc1<IS_MAX>(acc, mx, v);
+            }
+        }
+    }
+    double r = block_reduce<IS_MAX>(IS_MAX ? (double)mx : acc, smem);
+    if (threadIdx.x == 0) {
+        slot->partial[blockIdx.x] = r;
+        __threadfence();
+        s_ticket = atomicAdd(&slot->ticket, 1u);
+    }
+    __syncthreads();
+    if (s_ticket != gridDim.x - 1) return;
+    __threadfence();
+    const int SP = pl.S * pl.P;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const float count = (float)(pl.outer * pl.inner);  // elements per group (float32(N) like MXNet's mean)
+    for (int64_t gg = wid; gg < pl.groups; gg += nw) {
+        double a = 0.0;
+        float m = 0.f;
+        for (int l = lane; l < SP; l += 32) {
+            double q = __ldcg(&slot->partial[gg * SP + l]);
+            if (IS_MAX) m = fmaxf(m, (float)q); else a += q;
+        }
+        if (IS_MAX) m = warp_max(m); else a = warp_sum(a);
+        if (lane == 0) {
+            float stat = IS_MAX ? m : __fdiv_rn((float)a, count);
+            apply_update(u, (int)gg, stat);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) slot->ticket = 0;
+}
+
+// Stand-alone K3 (after a cross-rank allreduce of the statistic).
+static __global__ void threshold_update_kernel(const float* __restrict__ stat, int groups, UpdateArgs u) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < groups) apply_update(u, g, stat[g]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------------
+static inline int64_t b2q_flat_grid(const b2q_ctx* ctx, int64_t n8, int unroll) {
+    const int64_t tile = (int64_t)B2Q_THREADS * unroll;
+    int64_t ntiles = (n8 + tile - 1) / tile;
+    int64_t grid = (int64_t)ctx->num_sms * ctx->blocks_per_sm;
+    if (grid > ntiles) grid = ntiles;
+    if (grid < 1) grid = 1;
+    if (grid > B2Q_MAX_PIECES) grid = B2Q_MAX_PIECES;
+    return grid;
+}
+
+template <bool IS_MAX>
+static int launch_reduce(b2q_ctx* ctx, b2q_slot* slot, const float* x, int64_t outer, int64_t groups,
+                         int64_t inner, Prescale ps, UpdateArgs u, cudaStream_t st) {
+    B2Q_REQUIRE(outer >= 1 && groups >= 1 && inner >= 1, "empty tensor in reduction");
+    B2Q_REQUIRE(groups <= B2Q_MAX_GROUPS, "too many groups/channels (max 8192)");
+    const int64_t n = outer * groups * inner;
+    if (groups == 1 && ps.gamma == nullptr) {
+        FlatSplit sp = b2q_flat_split(x, n);
+        if (sp.head <= B2Q_THREADS) {
+            const int64_t grid = b2q_flat_grid(ctx, sp.n8, B2Q_REDUCE_UNROLL);
+            reduce_flat_kernel<IS_MAX, B2Q_REDUCE_UNROLL, B2Q_REDUCE_LDPOL>
+                <<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, sp, slot, u, (float)n);
+            B2Q_LAUNCH_CHECK(ctx);
+            return 0;
+        }
+        outer = 1; inner = n;  // not even float-aligned: scalar segmented path
+    }
+    SegPlan pl = b2q_seg_plan(x, nullptr, outer, groups, inner, ctx->num_sms * 8);
+    const unsigned grid = (unsigned)(groups * pl.S * pl.P);
+    if (pl.vec == 4) reduce_seg_kernel<IS_MAX, 4><<<grid, 128, 0, st>>>(x, pl, ps, slot, u);
+    else reduce_seg_kernel<IS_MAX, 1><<<grid, 128, 0, st>>>(x, pl, ps, slot, u);
+    B2Q_LAUNCH_CHECK(ctx);
+    return 0;
+}

@@ -1,0 +1,328 @@
+"""CUDA kernels vs the NumPy oracle on seeded inputs: real layer shapes, odd sizes, misaligned views, exact
+ties, state machines, req modes; plus size-independent properties at full benchmark sizes.
+
+Bars (BASELINE.json north_star): absmax and integer codes bit-exact; EMA thresholds, fold-BN weights and
+dequantised outputs within 1e-6 relative (in practice bit-identical, which is what is asserted wherever the
+reduction is order-independent)."""
+import numpy as np
+import pytest
+
+from oracle import quant_oracle as qo
+from tests.golden_util import bits_equal
+
+pytestmark = pytest.mark.gpu
+F = np.float32
+
+
+@pytest.fixture(scope="module")
+def T():
+    import torch
+    return torch
+
+
+def dev(T, a):
+    return T.from_numpy(np.ascontiguousarray(a, dtype=F)).cuda()
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def make(op_type, **attrs):
+    import b200quant
+    prop = b200quant.get_prop(op_type)(**{k: str(v) for k, v in attrs.items()})
+    return prop.create_operator(None, None, None), qo.create(op_type, **{k: str(v) for k, v in attrs.items()})
+
+
+def run_pair(T, op, ref, x, aux0, is_train=True, req="write", y0=None):
+    xs = [x] if isinstance(x, np.ndarray) else x
+    aux_d = [dev(T, a) for a in aux0]
+    aux_r = [np.array(a, dtype=F) for a in aux0]
+    y0 = np.zeros(xs[0].shape, F) if y0 is None else y0
+    yd = dev(T, y0)
+    yr = y0.copy()
+    op.forward(is_train, [req], [dev(T, a) for a in xs], [yd], aux_d)
+    ref.forward(is_train, [req], [a.copy() for a in xs], [yr], aux_r)
+    return host(yd), yr, [host(a) for a in aux_d], aux_r
+
+
+SHAPES = [(256, 64, 7, 7), (3, 5, 7, 11), (1,), (7,), (8,), (9,), (33, 1, 3, 3), (4097,), (2, 3, 224, 224),
+          (32, 3, 32, 32), (32, 8, 16, 16), (32, 8), (1000, 2048), (64, 3, 7, 7)]
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=[str(s) for s in SHAPES])
+@pytest.mark.parametrize("op_type", ["Quantization_int8_V2", "ClipGrad_Quantization_int8"])
+def test_minmax_activation_bit_exact(T, op_type, shape):
+    rng = np.random.default_rng(5)
+    op, ref = make(op_type, quant_mode="minmax", is_weight=False, is_weight_perchannel=False, delay_quant=0,
+                   ema_decay=0.99)
+    aux_d = [dev(T, np.ones(1, F))]
+    aux_r = [np.ones(1, F)]
+    for step, train in enumerate([True, True, False, True]):
+        x = (rng.standard_normal(shape).astype(F) * F(1 + step)).astype(F)
+        yd = dev(T, np.zeros(shape, F))
+        yr = np.zeros(shape, F)
+        op.forward(train, ["write"], [dev(T, x)], [yd], aux_d)
+        ref.forward(train, ["write"], [x], [yr], aux_r)
+        assert bits_equal(host(aux_d[0]), aux_r[0]), "threshold differs at step %d" % step
+        assert bits_equal(host(yd), yr), "output differs at step %d" % step
+
+
+@pytest.mark.parametrize("shape", [(64, 3, 7, 7), (512, 512, 3, 3), (1024, 1, 3, 3), (1000, 2048), (10, 8), (5, 3, 1, 1)])
+@pytest.mark.parametrize("per_channel", [False, True])
+@pytest.mark.parametrize("op_type", ["Quantization_int8_V2", "ClipGrad_Quantization_int8"])
+def test_minmax_weight_bit_exact(T, op_type, per_channel, shape):
+    rng = np.random.default_rng(6)
+    fan_in = int(np.prod(shape[1:]))
+    op, ref = make(op_type, quant_mode="minmax", is_weight=True, is_weight_perchannel=per_channel, delay_quant=0,
+                   ema_decay=0.99)
+    naux = shape[0] if per_channel else 1
+    aux_d, aux_r = [dev(T, np.ones(naux, F))], [np.ones(naux, F)]
+    for train in (True, False):
+        w = (rng.standard_normal(shape) * np.sqrt(2.0 / fan_in)).astype(F)
+        yd, yr = dev(T, np.zeros(shape, F)), np.zeros(shape, F)
+        op.forward(train, ["write"], [dev(T, w)], [yd], aux_d)
+        ref.forward(train, ["write"], [w], [yr], aux_r)
+        assert bits_equal(host(aux_d[0]), aux_r[0])
+        assert bits_equal(host(yd), yr)
+
+
+def test_codes_bit_exact_and_unclipped(T):
+    """integer codes (round(x/q)) bit-exact, including codes beyond +-127 on the unclipped V2 activation path."""
+    import b200quant._kernels as K
+    from b200quant import _lib
+    rng = np.random.default_rng(7)
+    x = (rng.standard_normal((64, 32, 14, 14)) * 3).astype(F)
+    thr = np.array([0.5], F)
+    ref = qo.Quantization_int8("minmax", False, False, 0, 0.99)
+    yr = np.zeros_like(x)
+    ref.forward(False, ["write"], [x], [yr], [thr.copy()])
+    xd, yd, td = dev(T, x), dev(T, np.zeros_like(x)), dev(T, thr)
+    codes = T.zeros(x.shape, dtype=T.int32, device="cuda")
+    K.qdq(xd, yd, td, 127, _lib.CLIP_NONE, "write", codes=codes)
+    assert np.array_equal(codes.cpu().numpy(), ref.codes.astype(np.int32))
+    assert np.abs(ref.codes).max() > 127
+    assert bits_equal(host(yd), yr)
+
+
+def test_exact_ties_and_neighbours(T):
+    """x = (k + 0.5) q and its float neighbours: half-away-from-zero, IEEE division."""
+    import b200quant._kernels as K
+    from b200quant import _lib
+    for T_val in (1.0, 127.0 / 8, 0.37, 3.1e-3, 817.0):
+        thr = np.array([T_val], F)
+        q = F(thr[0]) / F(127)
+        k = np.arange(-130, 131, dtype=F)
+        base = ((k + F(0.5)) * q).astype(F)
+        xs = np.concatenate([base, np.nextafter(base, F(np.inf)), np.nextafter(base, F(-np.inf)),
+                             np.array([0.0, -0.0, 0.49999997 * q, -0.49999997 * q, 1e-30, -1e-30], F)]).astype(F)
+        pad = (-len(xs)) % 8
+        xs = np.concatenate([xs, np.zeros(pad, F)])
+        want, codes = qo.qdq(xs, qo.mx_div(thr, F(127)))
+        for fast in (1, 0):
+            _lib.context(0).set_option("fast_div", fast)
+            yd = dev(T, np.zeros_like(xs))
+            cd = T.zeros(len(xs), dtype=T.int32, device="cuda")
+            K.qdq(dev(T, xs), yd, dev(T, thr), 127, _lib.CLIP_NONE, "write", codes=cd)
+            assert bits_equal(host(yd), want), (T_val, fast)
+            assert np.array_equal(cd.cpu().numpy(), codes.astype(np.int32))
+            yd2 = dev(T, np.zeros_like(xs))          # hot kernel (no codes)
+            K.qdq(dev(T, xs), yd2, dev(T, thr), 127, _lib.CLIP_NONE, "write")
+            assert bits_equal(host(yd2), want), (T_val, fast)
+        _lib.context(0).set_option("fast_div", 1)
+
+
+def test_fast_path_equals_reference_arithmetic_on_large_random(T):
+    """the reciprocal fast path must be bit-identical to fdiv+roundf on 2^26 random elements (several scales)."""
+    import b200quant._kernels as K
+    from b200quant import _lib
+    ctx = _lib.context(0)
+    g = T.Generator(device="cuda").manual_seed(5)
+    n = 1 << 26
+    for scale, thr_v in ((1.0, 4.1), (37.0, 9.3), (1e-3, 2.2e-3)):
+        x = T.randn(n, device="cuda", generator=g) * scale
+        thr = T.tensor([thr_v], device="cuda")
+        outs = []
+        for clip in (_lib.CLIP_NONE, _lib.CLIP_SYM):
+            for fast in (1, 0):
+                ctx.set_option("fast_div", fast)
+                y = T.empty_like(x)
+                K.qdq(x, y, thr, 127, clip, "write")
+                outs.append(y)
+            assert T.equal(outs[-1].view(T.int32), outs[-2].view(T.int32))
+        ctx.set_option("fast_div", 1)
+
+
+def test_misaligned_views_and_tails(T):
+    rng = np.random.default_rng(8)
+    big = rng.standard_normal(70001).astype(F)
+    for off in (0, 1, 3, 5, 7):
+        for n in (1, 2, 7, 8, 9, 255, 256, 257, 4096 + 3, 65536 + 1):
+            x = big[off:off + n]
+            op, ref = make("ClipGrad_Quantization_int8", quant_mode="minmax", is_weight=False,
+                           is_weight_perchannel=False, delay_quant=0, ema_decay=0.99)
+            xd_full = dev(T, big)
+            yd_full = T.zeros(70001, device="cuda")
+            aux_d, aux_r = [dev(T, np.ones(1, F))], [np.ones(1, F)]
+            yr = np.zeros(n, F)
+            op.forward(True, ["write"], [xd_full[off:off + n]], [yd_full[off:off + n]], aux_d)
+            ref.forward(True, ["write"], [x.copy()], [yr], aux_r)
+            assert bits_equal(host(aux_d[0]), aux_r[0]), (off, n)
+            assert bits_equal(host(yd_full[off:off + n]), yr), (off, n)
+            assert float(yd_full[off + n:].abs().sum()) == 0.0 and float(yd_full[:off].abs().sum()) == 0.0
+            # mutually misaligned input / output
+            yd2 = T.zeros(70001, device="cuda")
+            op2, _ = make("Quantization_int8_V2", quant_mode="minmax", is_weight=False, is_weight_perchannel=False,
+                          delay_quant=0, ema_decay=0.99)
+            o2 = (off + 1) % 8
+            op2.forward(False, ["write"], [xd_full[off:off + n]], [yd2[o2:o2 + n]], [dev(T, np.full(1, 2.5, F))])
+            want, _ = qo.qdq(x, qo.mx_div(F(2.5), F(127)))
+            assert bits_equal(host(yd2[o2:o2 + n]), want), (off, n)
+
+
+@pytest.mark.parametrize("req", ["write", "add", "null"])
+def test_req_modes_forward_backward(T, req):
+    rng = np.random.default_rng(9)
+    shape = (4, 16, 9, 9)
+    for op_type in ("Quantization_int8_V2", "ClipGrad_Quantization_int8"):
+        op, ref = make(op_type, quant_mode="minmax", is_weight=False, is_weight_perchannel=False, delay_quant=0,
+                       ema_decay=0.99)
+        x, y0, dy, g0 = (rng.standard_normal(shape).astype(F) for _ in range(4))
+        xd, yd, aux_d = dev(T, x), dev(T, y0), [dev(T, np.ones(1, F))]
+        yr, aux_r = y0.copy(), [np.ones(1, F)]
+        op.forward(True, [req], [xd], [yd], aux_d)
+        ref.forward(True, [req], [x], [yr], aux_r)
+        assert bits_equal(host(yd), yr) and bits_equal(host(aux_d[0]), aux_r[0])
+        gd, gr = dev(T, g0), g0.copy()
+        op.backward([req], [dev(T, dy)], [xd], [yd], [gd], aux_d)
+        ref.backward([req], [dy], [x], [yr], [gr], aux_r)
+        assert bits_equal(host(gd), gr)
+
+
+def test_clipgrad_backward_mask_strict_and_signed_zero(T):
+    op, ref = make("ClipGrad_Quantization_int8", quant_mode="minmax", is_weight=False, is_weight_perchannel=False,
+                   delay_quant=0, ema_decay=0.99)
+    t = F(1.5)
+    x = np.array([-2, -1.5, np.nextafter(F(-1.5), F(0)), -0.0, 0.0, 1.0, np.nextafter(F(1.5), F(0)), 1.5, 2, 0.3] * 8, F)
+    dy = np.array([1, -1, 2, -2, 3, -3, 4, -4, 5, -0.0] * 8, F)
+    aux = np.array([t], F)
+    gd = dev(T, np.full(x.shape, 9, F))
+    gr = np.full(x.shape, 9, F)
+    op.backward(["write"], [dev(T, dy)], [dev(T, x)], [None], [gd], [dev(T, aux)])
+    ref.backward(["write"], [dy], [x], [None], [gr], [aux])
+    assert bits_equal(host(gd), gr)
+    assert gr[1] == 0 and gr[7] == 0 and gr[2] != 0 and gr[6] != 0
+
+
+GDRQ_CASES = [
+    dict(shape=(64, 32, 3, 3), is_weight=True, group_size=-1, nbits=4),
+    dict(shape=(64, 32, 3, 3), is_weight=True, group_size=8, nbits=4),
+    dict(shape=(16, 64, 14, 14), is_weight=False, group_size=-1, nbits=8),
+    dict(shape=(16, 64, 14, 14), is_weight=False, group_size=16, nbits=8),
+    dict(shape=(5, 12, 7, 7), is_weight=False, group_size=3, nbits=5),
+    dict(shape=(3, 1024, 7, 7), is_weight=False, group_size=1, nbits=8),
+]
+
+
+@pytest.mark.parametrize("c", GDRQ_CASES, ids=[str(i) for i in range(len(GDRQ_CASES))])
+def test_gdrq_forward_backward(T, c):
+    rng = np.random.default_rng(10)
+    op, ref = make("GDRQ_PY", nbits=c["nbits"], group_size=c["group_size"], is_weight=c["is_weight"], lamda=0.001,
+                   delay_quant=1, fix_alpha=False, ktimes=3)
+    shape = c["shape"]
+    ch = shape[0] if c["is_weight"] else shape[1]
+    g = 1 if c["group_size"] == -1 else ch // c["group_size"]
+    aux_d, aux_r = [dev(T, np.ones(g, F))], [np.ones(g, F)]
+    for step in range(3):
+        x = (rng.standard_normal(shape) * (0.5 + step)).astype(F)
+        dy = rng.standard_normal(shape).astype(F)
+        xd, yd, yr = dev(T, x), dev(T, np.zeros(shape, F)), np.zeros(shape, F)
+        op.forward(True, ["write"], [xd], [yd], aux_d)
+        ref.forward(True, ["write"], [x], [yr], aux_r)
+        # two-stage parity: mean-derived thresholds to 1e-6, then bit-exact given equal T
+        np.testing.assert_allclose(host(aux_d[0]), aux_r[0], rtol=1e-6)
+        if bits_equal(host(aux_d[0]), aux_r[0]):
+            assert bits_equal(host(yd), yr), step
+        else:  # pragma: no cover
+            np.testing.assert_allclose(host(yd), yr, rtol=1e-5, atol=1e-6)
+        gd, gr = dev(T, np.zeros(shape, F)), np.zeros(shape, F)
+        op.backward(["write"], [dev(T, dy)], [xd], [yd], [gd], aux_d)
+        ref.backward(["write"], [dy], [x], [yr], [gr], aux_r)
+        assert bits_equal(host(gd), gr)
+
+
+@pytest.mark.parametrize("cfg", [dict(n=4, cin=32, hw=14, cout=64, group=1, k=1, stride=1, pad=0, pc=True),
+                                 dict(n=4, cin=32, hw=14, cout=32, group=32, k=3, stride=1, pad=1, pc=True),
+                                 dict(n=2, cin=16, hw=9, cout=24, group=1, k=3, stride=2, pad=1, pc=False),
+                                 dict(n=2, cin=3, hw=17, cout=32, group=1, k=3, stride=2, pad=1, pc=True)])
+def test_foldbn_pieces_bit_exact(T, cfg):
+    rng = np.random.default_rng(11)
+    attrs = dict(quant_mode="minmax", is_weight_perchannel=cfg["pc"], delay_quant=0, ema_decay=0.99, name="f",
+                 num_filter=cfg["cout"], num_group=cfg["group"], kernel=(cfg["k"],) * 2, stride=(cfg["stride"],) * 2,
+                 pad=(cfg["pad"],) * 2, dilate=(1, 1), no_bias=True, eps=1e-5, momentum=0.9, fix_gamma=False,
+                 quantize_flag=True)
+    op, ref = make("GDRQ_Fold_BN", **attrs)
+    n, cin, hw, cout = cfg["n"], cfg["cin"], cfg["hw"], cfg["cout"]
+    oh = (hw + 2 * cfg["pad"] - cfg["k"]) // cfg["stride"] + 1
+    naux1 = cout if cfg["pc"] else 1
+    aux_d = [dev(T, np.ones(1, F)), dev(T, np.ones(naux1, F))]
+    aux_r = [np.ones(1, F), np.ones(naux1, F)]
+    for step in range(2):
+        ins = [rng.uniform(-1, 1, (n, cin, hw, hw)).astype(F),
+               (rng.standard_normal((cout, cin // cfg["group"], cfg["k"], cfg["k"])) * 0.2).astype(F),
+               rng.standard_normal((n, cout, oh, oh)).astype(F), rng.uniform(0.5, 1.5, cout).astype(F),
+               rng.standard_normal(cout).astype(F), rng.standard_normal(cout).astype(F),
+               rng.uniform(0.5, 1.5, cout).astype(F)]
+        yd, yr = dev(T, np.zeros((n, cout, oh, oh), F)), np.zeros((n, cout, oh, oh), F)
+        op.forward(True, ["write"], [dev(T, a) for a in ins], [yd], aux_d)
+        ref.forward(True, ["write"], [a.copy() for a in ins], [yr], aux_r)
+        for j in range(2):
+            np.testing.assert_allclose(host(aux_d[j]), aux_r[j], rtol=1e-6)
+        assert bits_equal(host(aux_d[0]), aux_r[0]) and bits_equal(host(aux_d[1]), aux_r[1])
+        assert bits_equal(host(op.data_q), ref.data_q)
+        assert bits_equal(host(op.weight_q), ref.weight_q)
+        assert bits_equal(host(op.bias), ref.bias)
+        np.testing.assert_allclose(host(yd), yr, rtol=1e-4, atol=1e-4)   # library convolution
+
+
+def test_reductions_are_deterministic_and_exact(T):
+    import b200quant._kernels as K
+    g = T.Generator(device="cuda").manual_seed(3)
+    x = T.randn(50_000_017, device="cuda", generator=g)
+    s1, s2, m1 = T.zeros(1, device="cuda"), T.zeros(1, device="cuda"), T.zeros(1, device="cuda")
+    K.meanabs(x, s1)
+    K.meanabs(x, s2)
+    K.absmax(x, m1)
+    assert T.equal(s1, s2)
+    assert float(m1) == float(x.abs().max())
+    want = np.float32(np.float32(x.abs().double().sum().item()) / np.float32(x.numel()))
+    assert float(s1) == float(want)
+
+
+@pytest.mark.parametrize("shape", [(256, 64, 112, 112), (256, 256, 56, 56)])
+def test_full_size_properties(T, shape):
+    """BASELINE.json full sizes (784 MiB tensors): idempotence (QDQ of a quantised tensor with the same scale is
+    the identity), codes integer and within range, absmax equals the library max."""
+    op_v2, _ = make("Quantization_int8_V2", quant_mode="minmax", is_weight=False, is_weight_perchannel=False,
+                    delay_quant=0, ema_decay=0.99)
+    op_cg, _ = make("ClipGrad_Quantization_int8", quant_mode="minmax", is_weight=False, is_weight_perchannel=False,
+                    delay_quant=0, ema_decay=0.99)
+    g = T.Generator(device="cuda").manual_seed(5)
+    x = T.empty(shape, device="cuda").uniform_(-1, 1, generator=g)
+    aux = T.ones(1, device="cuda")
+    y = T.empty_like(x)
+    op_cg.forward(True, ["write"], [x], [y], [aux])          # first batch: aux = max|x|
+    assert float(aux) == float(x.abs().max())
+    q = np.float32(aux.item()) / np.float32(127)
+    codes = y / float(q)
+    assert float((codes - codes.round()).abs().max()) < 1e-3
+    assert float(codes.abs().max()) <= 127.0 + 1e-3
+    assert float((y - x).abs().max()) <= float(q) * 0.5 * (1 + 1e-5)
+    y2 = T.empty_like(x)
+    op_v2.forward(False, ["write"], [y], [y2], [aux])        # same scale, already on the grid
+    assert T.equal(y2.view(T.int32), y.view(T.int32))
+    dy = T.empty_like(x).normal_(generator=g)
+    dx = T.empty_like(x)
+    op_cg.backward(["write"], [dy], [x], [y], [dx], [aux])
+    inside = (x > -aux) & (x < aux)
+    assert T.equal(dx, dy * inside)

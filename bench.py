@@ -1,0 +1,419 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's headline: ResNet-50 int8-QAT images/s through the fake-quant hot path.
+
+A "step" is one pass of the hot path over one batch: for every quantization node of symbol/resnet_int8.py at
+batch 256 (54 activation + 54 weight nodes, 2.730 G + 25.5 M float32 elements) the
+operator's forward (reduction + EMA threshold update + QDQ sweep) and then its backward (straight-through copy),
+called through the reference-facing CustomOp protocol -> ctypes -> libb2q.so.  Convolutions are library code
+and are not part of the path (nor of the reference arm).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One JSON line on stdout (rank 0).  Keys beyond the base contract:
+  roofline      dominant kernel (QDQ sweep): algorithmic bytes / CUDA-event time of its launches in a timed region
+  kernels       the same for every kernel kind
+  e2e           same step with HOST (pinned) buffers through the host-buffer C ABI: H2D + kernels + D2H per node
+  cpu_baseline  oracle/c (C/OpenMP restatement of the reference's MXNet CPU op chain) on a bounded sample
+  clocks        SM clock / throttle reasons sampled with NVML during the timed region
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "resnet50_int8_qat_quant_path_images_per_sec"
+UNIT = "img/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="resnet50_int8")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's, 256)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# clocks (NVML) sampled during the timed region
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index, period=0.05):
+        super(ClockSampler, self).__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz, self.ok = [], set(), None, False
+        self._halt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self._halt.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._halt.wait(self.period)
+
+    def finish(self):
+        self._halt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------
+def build_nodes(torch, nodes, op_type, device, host=False, seed=5):
+    """Allocate every node's tensors (inputs resident before the timed region) and create its operator through
+    the registered Prop with string attributes, as MXNet would."""
+    import b200quant
+    g = torch.Generator(device=device).manual_seed(seed)
+    out = []
+    for name, kind, shape in nodes:
+        is_w = kind == "weight"
+        prop = b200quant.get_prop(op_type)(quant_mode="minmax", is_weight=str(is_w), is_weight_perchannel="False",
+                                           delay_quant="0", ema_decay="0.99")
+        op = prop.create_operator(None, None, None)
+        if is_w:
+            fan_in = 1
+            for s in shape[1:]:
+                fan_in *= s
+            x = torch.empty(shape, device=device).normal_(0.0, (2.0 / fan_in) ** 0.5, generator=g)
+        else:
+            x = torch.empty(shape, device=device).uniform_(-1.0, 1.0, generator=g)   # data/imagenet.py:16
+        dy = torch.empty(shape, device=device).normal_(generator=g)
+        out.append(dict(name=name, kind=kind, shape=shape, op=op, x=x, y=torch.empty_like(x), dy=dy,
+                        dx=torch.empty_like(x), aux=torch.ones(1, device=device), n=x.numel()))
+    return out
+
+
+def run_step(nodes):
+    for nd in nodes:                                   # forward, network order
+        nd["op"].forward(True, ["write"], [nd["x"]], [nd["y"]], [nd["aux"]])
+    for nd in reversed(nodes):                         # backward
+        nd["op"].backward(["write"], [nd["dy"]], [nd["x"]], [nd["y"]], [nd["dx"]], [nd["aux"]])
+
+
+def time_steps(torch, dist, fn, steps, world):
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def host_step_factory(torch, nodes, ctx):
+    """e2e: the same step with HOST buffers.  One pinned (x, y, dx) triple per distinct shape and staging set;
+    every node copies its full input H2D and its full result D2H inside the timed region."""
+    import b200quant
+    pools = {}
+    hnodes = []
+    for i, nd in enumerate(nodes):
+        key = (nd["shape"], i & 1)
+        if key not in pools:
+            pools[key] = tuple(torch.empty(nd["shape"], dtype=torch.float32).pin_memory() for _ in range(3))
+            pools[key][0].copy_(nd["x"])
+        hx, hy, hdx = pools[key]
+        prop = b200quant.get_prop("Quantization_int8_V2")(quant_mode="minmax", is_weight=str(nd["kind"] == "weight"),
+                                                          is_weight_perchannel="False")
+        hnodes.append(dict(op=prop.create_operator(None, None, None), x=hx, y=hy, dx=hdx,
+                           aux=torch.ones(1).pin_memory(), n=nd["n"]))
+
+    def step():
+        for h in hnodes:
+            h["op"].forward(True, ["write"], [h["x"]], [h["y"]], [h["aux"]])
+        for h in reversed(hnodes):
+            h["op"].backward(["write"], [h["y"]], [h["x"]], [h["y"]], [h["dx"]], [h["aux"]])
+        ctx.host_sync()
+
+    bytes_in = sum(4 * h["n"] for h in hnodes) * 2       # x (forward) + dy (backward)
+    bytes_out = sum(4 * h["n"] for h in hnodes) * 2      # y + dx
+    return step, bytes_in, bytes_out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reference CPU path (oracle/c): the only place bench.py executes oracle code, and only as the timed baseline
+# ---------------------------------------------------------------------------------------------------------
+CPU_SAMPLE = [("act", (256, 64, 56, 56)), ("act", (256, 256, 14, 14)), ("act", (256, 2048)),
+              ("weight", (512, 512, 3, 3)), ("weight", (64, 3, 7, 7))]
+
+
+def cpu_reference_step(sample_state):
+    from oracle import c_oracle as co
+    for s in sample_state:
+        co.minmax_quant_fwd(0, s["x"], s["y"], s["aux"], s["w"], False, True, False, 0.99)
+    for s in reversed(sample_state):
+        co.ste_bwd(s["dy"], s["dx"])
+
+
+def cpu_reference_prepare():
+    import numpy as np
+    from b200quant.workloads import numel
+    rng = np.random.default_rng(5)
+    st = []
+    for kind, shape in CPU_SAMPLE:
+        x = rng.uniform(-1, 1, shape).astype(np.float32) if kind == "act" else \
+            (rng.standard_normal(shape) * (2.0 / numel(shape[1:])) ** 0.5).astype(np.float32)
+        st.append(dict(x=x, y=np.empty_like(x), dy=rng.standard_normal(shape).astype(np.float32),
+                       dx=np.empty_like(x), aux=np.ones(1, np.float32), w=(kind == "weight")))
+    return st, sum(numel(s) for _, s in CPU_SAMPLE)
+
+
+def cpu_baseline(total_elems, batch, steps=2, warmup=1):
+    from oracle import c_oracle as co
+    st, sample_elems = cpu_reference_prepare()
+    for _ in range(warmup):
+        cpu_reference_step(st)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_reference_step(st)
+    dt = (time.perf_counter() - t0) / steps
+    full = dt * total_elems / sample_elems
+    return dict(value=batch / full, unit=UNIT, cores=co.num_threads(), kind="port",
+                sample="fwd+bwd of %s (%d of the step's %d elements) per step, time scaled by element count; "
+                       "oracle/c = C/OpenMP restatement of the reference's mx.nd op chain, all host threads"
+                       % (", ".join("x".join(map(str, s)) for _, s in CPU_SAMPLE), sample_elems, total_elems),
+                sample_seconds=dt, ms_per_step_extrapolated=full * 1e3)
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from b200quant.workloads import WORKLOADS, summary
+    fn, batch, _ = WORKLOADS[args.workload]
+    batch = args.batch or batch
+    sm = summary(fn(batch))
+    total = sm["act_elems"] + sm["weight_elems"]
+    from oracle import c_oracle as co
+    st, sample_elems = cpu_reference_prepare()
+    for _ in range(max(1, min(args.warmup, 2))):
+        cpu_reference_step(st)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_step(st)
+    dt = (time.perf_counter() - t0) / args.steps
+    full = dt * total / sample_elems
+    value = batch / full
+    sample = ("each step = fwd+bwd of %s (%d of %d elements), time scaled by element count"
+              % (", ".join("x".join(map(str, s)) for _, s in CPU_SAMPLE), sample_elems, total))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": full * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%s quant path (fwd+bwd of all %d nodes), batch %d" %
+                                   (args.workload, sm["act_nodes"] + sm["weight_nodes"], batch),
+                       "reference": "oracle/c C+OpenMP restatement of the MXNet CPU CustomOp chain "
+                                    "(libmxnet is not installable here)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": co.num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return main_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the quantization operators have no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    device = torch.device("cuda", local)
+
+    import b200quant  # noqa: F401
+    from b200quant import _lib
+    from b200quant.dist import GradBucket, attach_threshold_sync
+    from b200quant.workloads import WORKLOADS, summary
+
+    fn, batch, op_type = WORKLOADS[args.workload]
+    batch = args.batch or batch
+    node_list = fn(batch)
+    sm = summary(node_list)
+    total_elems = sm["act_elems"] + sm["weight_elems"]
+    ctx = _lib.context(local)
+    nodes = build_nodes(torch, node_list, "Quantization_int8_V2", device, seed=5 + rank)
+
+    bucket = None
+    if world > 1:   # data parallel: thresholds allreduce(max) per activation node, weight grads allreduce(sum)
+        attach_threshold_sync([nd["op"] for nd in nodes])
+        wn = [nd for nd in nodes if nd["kind"] == "weight"]
+        bucket = GradBucket([nd["shape"] for nd in wn], device)
+        for nd, view in zip(wn, bucket.views):
+            nd["dx"] = view
+
+    def step():
+        run_step(nodes)
+        if bucket is not None:
+            bucket.allreduce()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+
+    # ---- main timed region (eager: every call goes through the CustomOp protocol) ----
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = ctx.launch_count()
+    ms_eager = time_steps(torch, dist, step, args.steps, world)
+    launches = ctx.launch_count() - l0
+    clocks = sampler.finish()
+    mode = "eager"
+    ms = ms_eager
+
+    # ---- the same step replayed from a CUDA graph (single GPU; the graph captures our kernels only) ----
+    ms_graph = None
+    if world == 1 and not args.no_graph:
+        try:
+            graph = torch.cuda.CUDAGraph()
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                step()
+                torch.cuda.synchronize()
+                with torch.cuda.graph(graph, stream=s):
+                    step()
+            torch.cuda.current_stream().wait_stream(s)
+            for _ in range(3):
+                graph.replay()
+            ms_graph = time_steps(torch, dist, graph.replay, args.steps, world)
+            if ms_graph < ms:
+                ms, mode = ms_graph, "cuda_graph"
+        except Exception as e:  # pragma: no cover
+            ms_graph = "failed: %s" % (str(e).splitlines()[0][:120],)
+
+    value = world * batch * args.steps / (ms / 1e3)
+
+    # ---- per-kernel timing for the roofline (second timed region, events around every flat-kernel launch) ----
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    ctx.set_option("timing", 1)
+    ctx.timing_read(0, reset=True)
+    for _ in range(min(args.steps, 5)):
+        step()
+    torch.cuda.synchronize()
+    kinds = {1: "reduce_flat (max|x| + EMA update)", 2: "qdq_flat_hot (QDQ sweep)", 3: "bwd_flat (STE copy)",
+             4: "bwd_flat (clip mask)", 5: "segmented/other"}
+    kernels = {}
+    for k, name in kinds.items():
+        kms, kbytes, kn = ctx.timing_read(k)
+        if kn:
+            kernels[name] = {"launches": kn, "ms_total": kms, "alg_bytes_total": kbytes,
+                             "achieved_gbs": kbytes / kms / 1e6, "frac_of_peak": kbytes / kms / 1e6 / peak_gbs}
+    ctx.timing_read(0, reset=True)
+    ctx.set_option("timing", 0)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_dominant_kernel.json")) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    dom = kernels.get(kinds[2], {})
+    roofline = {"bound": "hbm", "kernel": "qdq_flat_hot_kernel", "achieved": dom.get("achieved_gbs"),
+                "peak": peak_gbs, "unit": "GB/s", "frac": dom.get("frac_of_peak"), "traffic": traffic,
+                "peak_source": peak_src,
+                "alg_bytes_per_launch": (dom.get("alg_bytes_total", 0) / dom["launches"]) if dom else None,
+                "avg_launch_ms": (dom.get("ms_total", 0) / dom["launches"]) if dom else None}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%s quant path: fwd+bwd of all %d Quantization_int8_V2 nodes (%d act + %d weight), "
+                                   "per-GPU batch %d" % (args.workload, len(nodes), sm["act_nodes"], sm["weight_nodes"],
+                                                         batch),
+                       "elements_per_step": total_elems, "alg_bytes_per_step": 20 * total_elems,
+                       "parallelism": "dp%d" % world, "l2": "inputs larger than L2 (10.9 GB touched once per step)",
+                       "mode": mode},
+            "ms_per_step_eager": ms_eager / args.steps,
+            "ms_per_step_graph": (ms_graph / args.steps) if isinstance(ms_graph, float) else ms_graph,
+            "hbm_frac_whole_step": 20.0 * total_elems / (ms / args.steps / 1e3) / 1e9 / peak_gbs,
+            "roofline": roofline, "kernels": kernels, "clocks": clocks, "gpu_launches": launches}
+
+    # ---- e2e: host buffers through the host C ABI (rank-local; N ranks run it concurrently) ----
+    if not args.no_e2e:
+        hstep, b_in, b_out = host_step_factory(torch, nodes, ctx)
+        hstep()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            hstep()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        line["e2e"] = {"value": world * batch * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": b_in,
+                       "d2h_bytes_per_step": b_out, "steps": args.e2e_steps, "ms_per_step": dt / args.e2e_steps * 1e3,
+                       "path": "CustomOp.forward/backward with pinned HOST tensors -> b2q_*_host_f32"}
+
+    if rank == 0 and world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline(total_elems, batch)
+
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

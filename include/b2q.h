@@ -44,12 +44,18 @@ int b2q_create(int device, b2q_ctx** out);
 int b2q_destroy(b2q_ctx* ctx);
 int b2q_num_sms(b2q_ctx* ctx);
 /* run-time knobs for benchmarking sweeps: "blocks_per_sm" (grid = SMs x this), "reverse" (QDQ sweep walks
- * descending addresses to reuse what the reduction left in L2), "fast_div" (reciprocal fast path on/off).
+ * descending addresses to reuse what the reduction left in L2), "fast_div" (reciprocal fast path on/off),
+ * "timing" (see b2q_timing_read).
  * Results never depend on them. */
 int b2q_set_option(b2q_ctx* ctx, const char* key, int value);
 int b2q_get_option(b2q_ctx* ctx, const char* key, int* value);
 /* number of kernels this library has launched through ctx since creation (bench.py's gpu_launches) */
 int64_t b2q_launch_count(b2q_ctx* ctx);
+/* With option "timing"=1 every launch of the whole-tensor kernels is bracketed by CUDA events on the caller's
+ * stream.  b2q_timing_read sums them per kind (1 reduction, 2 QDQ sweep, 3 STE backward, 4 masked backward,
+ * 5 segmented/other, 0 all): device milliseconds, ALGORITHMIC bytes (4, 8, 8, 12 B/element) and launch count;
+ * reset!=0 clears the records.  Synchronises on the recorded events.  Not usable under stream capture.      */
+int b2q_timing_read(b2q_ctx* ctx, int kind, double* total_ms, double* total_bytes, int64_t* count, int reset);
 
 /* ---- primitives ---------------------------------------------------------------------------------
  * K1/K2  b2q_absmax_f32    stat[g] = max |x|          replaces mx.nd.abs -> mx.nd.max

@@ -41,6 +41,22 @@ def _rows_cols(shape):
     return rows, (n // rows if rows else 0), n
 
 
+def _host_device():
+    """Device whose staging buffers serve host-buffer calls: the process's current CUDA device."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            return torch.cuda.current_device()
+    except ImportError:  # pragma: no cover
+        pass
+    return 0
+
+
+def host_sync():
+    """Wait for every host-buffer call issued so far on the current device (they are asynchronous)."""
+    _lib.context(_host_device()).host_sync()
+
+
 def require_device(on_device, what):
     if not on_device:
         raise _lib.B2QError("%s has no host-buffer entry point; pass CUDA tensors (there is no CPU fallback)" % what)
@@ -61,9 +77,7 @@ def assign(dst, req, src):
     else:
         if r == 3:
             raise _lib.B2QError("assign(add) on host buffers is not supported")
-        ctx = _lib.context(0)
-        ctx.call("b2q_ste_bwd_host_f32", s.ptr, d.ptr, d.numel)
-        ctx.host_sync()
+        _lib.context(_host_device()).call("b2q_ste_bwd_host_f32", s.ptr, d.ptr, d.numel)
 
 
 def zero_(dst):
@@ -92,7 +106,7 @@ def minmax_quant_fwd(variant, x, y, aux, is_weight, per_channel, is_train, init,
     else:
         if _req(req) not in (1, 2):
             raise _lib.B2QError("host-buffer forward supports req=write only")
-        _lib.context(0).call("b2q_minmax_quant_fwd_host_f32", int(variant), xb.ptr, yb.ptr, ab.ptr, rows, cols,
+        _lib.context(_host_device()).call("b2q_minmax_quant_fwd_host_f32", int(variant), xb.ptr, yb.ptr, ab.ptr, rows, cols,
                              int(bool(is_weight)), int(bool(per_channel)), int(bool(is_train)), int(bool(init)),
                              d, omd)
 
@@ -126,7 +140,7 @@ def clipgrad_bwd(x, dy, dx, aux):
     if on_dev:
         _lib.context(dev).call("b2q_clipgrad_bwd_f32", xb.ptr, gb.ptr, ob.ptr, ab.ptr, xb.numel, current_stream(xb))
     else:
-        _lib.context(0).call("b2q_clipgrad_bwd_host_f32", xb.ptr, gb.ptr, ob.ptr, ab.ptr, xb.numel)
+        _lib.context(_host_device()).call("b2q_clipgrad_bwd_host_f32", xb.ptr, gb.ptr, ob.ptr, ab.ptr, xb.numel)
 
 
 def _gdrq_view(shape, group_size, is_weight):

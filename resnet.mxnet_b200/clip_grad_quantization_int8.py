@@ -22,8 +22,7 @@ class ClipGrad_Quantization_int8(Quantization_int8):
             self.delay_quant -= 1
             return
         first = bool(self.init) and bool(is_train) and not self.is_weight
-        K.minmax_quant_fwd(self.VARIANT, in_data[0], out_data[0], aux[0], self.is_weight,
-                           self.is_weight_perchannel, is_train, first, self.ema_decay, req[0])
+        self._quantize(is_train, req[0], in_data[0], out_data[0], aux[0], first)
         if first:
             self.init = False                       # :42-44
 

@@ -32,12 +32,8 @@ int b2q_create(int device, b2q_ctx** out) {
     cudaDeviceProp prop;
     B2Q_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
     b2q_ctx* ctx = new b2q_ctx();
-    memset(ctx, 0, sizeof(*ctx));
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
-    ctx->blocks_per_sm = 8;
-    ctx->reverse = 1;
-    ctx->fast_div = 1;
     cudaError_t e = cudaMalloc(&ctx->slots, sizeof(b2q_slot) * B2Q_NSLOTS);
     if (e != cudaSuccess) {
         delete ctx;
@@ -59,6 +55,8 @@ int b2q_destroy(b2q_ctx* ctx) {
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
     b2q_host_release(ctx);
+    for (const b2q_timing_rec& r : ctx->recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
     cudaFree(ctx->slots);
     delete ctx;
     return 0;
@@ -72,6 +70,7 @@ static int* option_slot(b2q_ctx* ctx, const char* key) {
     if (!strcmp(key, "blocks_per_sm")) return &ctx->blocks_per_sm;
     if (!strcmp(key, "reverse")) return &ctx->reverse;
     if (!strcmp(key, "fast_div")) return &ctx->fast_div;
+    if (!strcmp(key, "timing")) return &ctx->timing;
     return nullptr;
 }
 
@@ -81,6 +80,28 @@ int b2q_set_option(b2q_ctx* ctx, const char* key, int value) {
     B2Q_REQUIRE(p != nullptr, "unknown option");
     if (p == &ctx->blocks_per_sm) B2Q_REQUIRE(value >= 1 && value <= 32, "blocks_per_sm out of range");
     *p = value;
+    return 0;
+}
+
+int b2q_timing_read(b2q_ctx* ctx, int kind, double* total_ms, double* total_bytes, int64_t* count, int reset) {
+    B2Q_CTX(ctx);
+    B2Q_REQUIRE(kind >= 0 && kind < B2Q_NKINDS, "bad kind");
+    double ms = 0.0, bytes = 0.0;
+    int64_t n = 0;
+    for (const b2q_timing_rec& r : ctx->recs) {
+        if (kind != 0 && r.kind != kind) continue;
+        B2Q_CHECK_CUDA(cudaEventSynchronize(r.e1));
+        float t = 0.f;
+        B2Q_CHECK_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+        ms += t; bytes += r.bytes; ++n;
+    }
+    if (total_ms) *total_ms = ms;
+    if (total_bytes) *total_bytes = bytes;
+    if (count) *count = n;
+    if (reset) {
+        for (const b2q_timing_rec& r : ctx->recs) { ctx->event_pool.push_back(r.e0); ctx->event_pool.push_back(r.e1); }
+        ctx->recs.clear();
+    }
     return 0;
 }
 

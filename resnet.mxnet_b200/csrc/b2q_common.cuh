@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <vector>
 
 #include "../../include/b2q.h"
 
@@ -21,17 +22,54 @@ struct b2q_slot {
     double partial[B2Q_MAX_PIECES];
 };
 
+// Optional per-kernel timing (option "timing"): CUDA events around every launch of the flat kernels, read
+// back with b2q_timing_read().  bench.py uses it for the roofline numbers; it is off by default.
+#define B2Q_KIND_REDUCE_FLAT 1
+#define B2Q_KIND_QDQ_HOT 2
+#define B2Q_KIND_BWD_STE 3
+#define B2Q_KIND_BWD_MASK 4
+#define B2Q_KIND_OTHER 5
+#define B2Q_NKINDS 6
+
+struct b2q_timing_rec {
+    int kind;
+    double bytes;
+    cudaEvent_t e0, e1;
+};
+
 struct b2q_ctx {
-    int device;
-    int num_sms;
-    b2q_slot* slots;      // device
-    unsigned int next_slot;
-    long long launches;
-    // tuning knobs (never change results)
-    int blocks_per_sm;
-    int reverse;
-    int fast_div;
-    void* host_state;     // staging buffers + streams of the host-buffer entry points (b2q_host.cu)
+    int device = 0;
+    int num_sms = 0;
+    b2q_slot* slots = nullptr;      // device
+    unsigned int next_slot = 0;
+    long long launches = 0;
+    // run-time knobs (never change results)
+    int blocks_per_sm = 8;
+    int reverse = 1;
+    int fast_div = 1;
+    int timing = 0;
+    std::vector<b2q_timing_rec> recs;
+    std::vector<cudaEvent_t> event_pool;
+    void* host_state = nullptr;     // staging buffers + streams of the host-buffer entry points (b2q_host.cu)
+};
+
+struct b2q_timed_launch {
+    b2q_ctx* ctx;
+    cudaStream_t st;
+    cudaEvent_t e1;
+    bool on;
+    b2q_timed_launch(b2q_ctx* c, int kind, double bytes, cudaStream_t s) : ctx(c), st(s), e1(nullptr), on(c->timing != 0) {
+        if (!on) return;
+        cudaEvent_t ev[2];
+        for (int i = 0; i < 2; ++i) {
+            if (!c->event_pool.empty()) { ev[i] = c->event_pool.back(); c->event_pool.pop_back(); }
+            else cudaEventCreate(&ev[i]);
+        }
+        cudaEventRecord(ev[0], s);
+        e1 = ev[1];
+        c->recs.push_back({kind, bytes, ev[0], ev[1]});
+    }
+    ~b2q_timed_launch() { if (on) cudaEventRecord(e1, st); }
 };
 
 void b2q_set_error(const std::string& msg);

@@ -382,6 +382,7 @@ static int launch_qdq(b2q_ctx* ctx, const float* x, float* y, int64_t outer, int
         if (ok && sp.head <= B2Q_THREADS) {
             const bool hot = a.do_round && a.req != B2Q_REQ_ADD && !a.codes &&
                              (a.clip_mode == B2Q_CLIP_NONE || a.clip_mode == B2Q_CLIP_SYM);
+            b2q_timed_launch tl(ctx, hot ? B2Q_KIND_QDQ_HOT : B2Q_KIND_OTHER, 8.0 * (double)n, st);
             if (hot) {
                 const int64_t grid = b2q_flat_grid(ctx, sp.n8, B2Q_QDQ_UNROLL);
                 if (a.clip_mode == B2Q_CLIP_SYM)
@@ -401,6 +402,7 @@ static int launch_qdq(b2q_ctx* ctx, const float* x, float* y, int64_t outer, int
     }
     SegPlan pl = b2q_seg_plan(x, y, outer, groups, inner, ctx->num_sms * 8);
     const unsigned grid = (unsigned)(groups * pl.S * pl.P);
+    b2q_timed_launch tl(ctx, B2Q_KIND_OTHER, 8.0 * (double)n, st);
     if (pl.vec == 4) qdq_seg_kernel<4><<<grid, 128, 0, st>>>(x, y, pl, ps, fb, a);
     else qdq_seg_kernel<1><<<grid, 128, 0, st>>>(x, y, pl, ps, fb, a);
     B2Q_LAUNCH_CHECK(ctx);
@@ -417,6 +419,7 @@ static int launch_bwd_mask(b2q_ctx* ctx, const float* x, const float* dy, float*
         bool ok = same_misalignment(dy, dx) && (MASK == 0 || same_misalignment(dy, x));
         if (ok && sp.head <= B2Q_THREADS) {
             const int64_t grid = b2q_flat_grid(ctx, sp.n8, B2Q_BWD_UNROLL);
+            b2q_timed_launch tl(ctx, MASK == 0 ? B2Q_KIND_BWD_STE : B2Q_KIND_BWD_MASK, (MASK == 0 ? 8.0 : 12.0) * (double)n, st);
             if (add) bwd_flat_kernel<MASK, true, B2Q_BWD_UNROLL, B2Q_BWD_LDPOL, B2Q_BWD_STPOL>
                     <<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, dy, dx, sp, thr, thr_imm);
             else bwd_flat_kernel<MASK, false, B2Q_BWD_UNROLL, B2Q_BWD_LDPOL, B2Q_BWD_STPOL>

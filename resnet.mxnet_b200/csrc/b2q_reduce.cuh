@@ -260,6 +260,7 @@ static int launch_reduce(b2q_ctx* ctx, b2q_slot* slot, const float* x, int64_t o
         FlatSplit sp = b2q_flat_split(x, n);
         if (sp.head <= B2Q_THREADS) {
             const int64_t grid = b2q_flat_grid(ctx, sp.n8, B2Q_REDUCE_UNROLL);
+            b2q_timed_launch tl(ctx, B2Q_KIND_REDUCE_FLAT, 4.0 * (double)n, st);
             reduce_flat_kernel<IS_MAX, B2Q_REDUCE_UNROLL, B2Q_REDUCE_LDPOL>
                 <<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, sp, slot, u, (float)n);
             B2Q_LAUNCH_CHECK(ctx);
@@ -269,6 +270,7 @@ static int launch_reduce(b2q_ctx* ctx, b2q_slot* slot, const float* x, int64_t o
     }
     SegPlan pl = b2q_seg_plan(x, nullptr, outer, groups, inner, ctx->num_sms * 8);
     const unsigned grid = (unsigned)(groups * pl.S * pl.P);
+    b2q_timed_launch tl(ctx, B2Q_KIND_OTHER, 4.0 * (double)n, st);
     if (pl.vec == 4) reduce_seg_kernel<IS_MAX, 4><<<grid, 128, 0, st>>>(x, pl, ps, slot, u);
     else reduce_seg_kernel<IS_MAX, 1><<<grid, 128, 0, st>>>(x, pl, ps, slot, u);
     B2Q_LAUNCH_CHECK(ctx);

@@ -9,6 +9,8 @@ forward (fold_bn_v1_gdrq.py:32-120), three library calls and one convolution:
     conv   : library convolution (cuDNN through torch, or mx.nd.Convolution under MXNet) + bias (:99-120)
 backward (:122-129): gradient only to ``bn_output``; the six other inputs get zeros.
 """
+import os
+
 from . import _kernels as K
 from .operator import CustomOp, CustomOpProp, py_bool, py_literal, register
 
@@ -17,6 +19,8 @@ try:
     import torch.nn.functional as F
 except Exception:  # pragma: no cover
     torch = None
+
+ALLOW_TF32_CONV = os.environ.get("B2Q_CONV_TF32", "0") == "1"
 
 
 class GDRQ_Fold_BN(CustomOp):
@@ -48,8 +52,10 @@ class GDRQ_Fold_BN(CustomOp):
 
     def _conv(self, data, weight, bias):
         if torch is not None and isinstance(data, torch.Tensor):
-            return F.conv2d(data, weight, bias, stride=tuple(self.stride), padding=tuple(self.pad),
-                            dilation=tuple(self.dilate), groups=int(self.num_group))
+            # true float32 convolution like the reference's cuDNN v5/v6 call (README.md:8); TF32 is opt-in
+            with torch.backends.cudnn.flags(enabled=True, allow_tf32=ALLOW_TF32_CONV):
+                return F.conv2d(data, weight, bias, stride=tuple(self.stride), padding=tuple(self.pad),
+                                dilation=tuple(self.dilate), groups=int(self.num_group))
         import mxnet as mx  # pragma: no cover
         conv = mx.nd.Convolution(name=self.name, data=data, weight=weight, num_filter=self.num_filter,
                                  kernel=self.kernel, num_group=self.num_group, stride=self.stride, pad=self.pad,

@@ -29,14 +29,29 @@ class Quantization_int8(CustomOp):
         self.ema_decay = ema_decay
         self.QUANT_LEVEL = 127
         self.init = True
+        self.sync = None     # optional cross-rank threshold exchange (b200quant.dist.ThresholdSync)
+        self._stat = None
+
+    def _quantize(self, is_train, req, x, y, aux, first):
+        """One fused call; or, when a cross-rank sync is attached to a training activation node:
+        reduce -> allreduce(max) -> update + QDQ, so every rank applies the same threshold."""
+        if self.sync is not None and is_train and not self.is_weight:
+            if self._stat is None:
+                import torch
+                self._stat = torch.empty(1, dtype=torch.float32, device=x.device)
+            K.minmax_quant_stat(x, self._stat, False)
+            self.sync(self._stat)
+            K.minmax_quant_finish(self.VARIANT, x, y, aux, self._stat, False, False, True, first, self.ema_decay, req)
+        else:
+            K.minmax_quant_fwd(self.VARIANT, x, y, aux, self.is_weight, self.is_weight_perchannel, is_train, first,
+                               self.ema_decay, req)
 
     def forward(self, is_train, req, in_data, out_data, aux):
         if is_train and self.delay_quant > 0:      # :13-16 warm-up: pass through, count down
             self.assign(out_data[0], req[0], in_data[0])
             self.delay_quant -= 1
             return
-        K.minmax_quant_fwd(self.VARIANT, in_data[0], out_data[0], aux[0], self.is_weight,
-                           self.is_weight_perchannel, is_train, False, self.ema_decay, req[0])
+        self._quantize(is_train, req[0], in_data[0], out_data[0], aux[0], False)
 
     def backward(self, req, out_grad, in_data, out_data, in_grad, aux):
         K.ste_bwd(out_grad[0], in_grad[0], req[0])  # :41-42

@@ -317,7 +317,7 @@ def test_full_size_properties(T, shape):
     codes = y / float(q)
     assert float((codes - codes.round()).abs().max()) < 1e-3
     assert float(codes.abs().max()) <= 127.0 + 1e-3
-    assert float((y - x).abs().max()) <= float(q) * 0.5 * (1 + 1e-5)
+    assert float((y - x).abs().max()) <= float(q) * 0.5 + 2e-7   # + one ulp of |x| <= 1
     y2 = T.empty_like(x)
     op_v2.forward(False, ["write"], [y], [y2], [aux])        # same scale, already on the grid
     assert T.equal(y2.view(T.int32), y.view(T.int32))

@@ -185,6 +185,30 @@ int b2q_qil_bwd_f32(b2q_ctx* ctx, int variant, const float* x, const float* dy, 
                     const float* p1, float* dp0, float* dp1, int64_t n, int req, int req_p0, int req_p1,
                     void* stream);
 
+/* ---- multi-tensor: every weight of a network in two launches (forward) / one launch (backward) ---------
+ * The weight tensors of a network are ~1% of a step's bytes but, launched one by one (3 launches each), ~7% of its
+ * time.  A plan is built once from the (stable) parameter pointers; b2q_multi_weight_quant_fwd_f32 then runs the
+ * weight path of Quantization_int8_V2 (variant 0, symbol/quant_ops.py:17-31) or ClipGrad_Quantization_int8
+ * (variant 1, symbol/clip_grad_quantization_int8.py:19-36) for all of them: one max|w| launch + one QDQ launch;
+ * b2q_multi_weight_ste_bwd_f32 is their straight-through backward dx = dy (quant_ops.py:41-42).  Results are
+ * bit-identical to the per-tensor entry points.                                                               */
+typedef struct {
+    const float* x;      /* weight                                   */
+    float* y;            /* quantised weight                         */
+    float* aux;          /* minmax state: [1] or [rows]              */
+    const float* dy;     /* gradient w.r.t. y (may be NULL: no backward) */
+    float* dx;           /* gradient w.r.t. x (may be NULL)          */
+    int64_t rows;        /* out channels                             */
+    int64_t cols;        /* elements per out channel                 */
+    int32_t per_channel; /* is_weight_perchannel                     */
+    int32_t reserved;
+} b2q_weight_desc;
+typedef struct b2q_multi_plan b2q_multi_plan;
+int b2q_multi_plan_create(b2q_ctx* ctx, const b2q_weight_desc* descs, int count, b2q_multi_plan** out);
+int b2q_multi_plan_destroy(b2q_ctx* ctx, b2q_multi_plan* plan);
+int b2q_multi_weight_quant_fwd_f32(b2q_ctx* ctx, b2q_multi_plan* plan, int variant, int is_train, void* stream);
+int b2q_multi_weight_ste_bwd_f32(b2q_ctx* ctx, b2q_multi_plan* plan, void* stream);
+
 /* ---- host-buffer path: the call a framework whose tensors live in HOST memory makes (bench.py "e2e") --
  * Same semantics as the device entry points but x / y / aux are HOST pointers (pinned for full speed).
  * Each call stages its tensor through one of two device staging sets on that set's own stream

@@ -57,7 +57,18 @@ _CTX_FUNCS = {
     "b2q_ste_bwd_host_f32": [_P, _P, _L],
     "b2q_clipgrad_bwd_host_f32": [_P, _P, _P, _P, _L],
     "b2q_host_sync": [],
+    "b2q_multi_plan_create": [_P, _I, ctypes.POINTER(ctypes.c_void_p)],
+    "b2q_multi_plan_destroy": [_P],
+    "b2q_multi_weight_quant_fwd_f32": [_P, _I, _I, _P],
+    "b2q_multi_weight_ste_bwd_f32": [_P, _P],
 }
+
+
+class WeightDesc(ctypes.Structure):
+    """b2q_weight_desc (include/b2q.h)."""
+    _fields_ = [("x", ctypes.c_void_p), ("y", ctypes.c_void_p), ("aux", ctypes.c_void_p), ("dy", ctypes.c_void_p),
+                ("dx", ctypes.c_void_p), ("rows", ctypes.c_int64), ("cols", ctypes.c_int64),
+                ("per_channel", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 _PLAIN_FUNCS = {
     "b2q_abi_version": ([], _I),
     "b2q_last_error": ([], ctypes.c_char_p),

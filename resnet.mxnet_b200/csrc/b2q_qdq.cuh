@@ -370,7 +370,7 @@ static inline bool same_misalignment(const void* a, const void* b) {
     return (((uintptr_t)a ^ (uintptr_t)b) & 31) == 0;
 }
 
-static int launch_qdq(b2q_ctx* ctx, const float* x, float* y, int64_t outer, int64_t groups, int64_t inner,
+[[maybe_unused]] static int launch_qdq(b2q_ctx* ctx, const float* x, float* y, int64_t outer, int64_t groups, int64_t inner,
                       Prescale ps, FoldBias fb, QdqArgs a, cudaStream_t st) {
     B2Q_REQUIRE(outer >= 1 && groups >= 1 && inner >= 1, "empty tensor");
     B2Q_REQUIRE(a.req == B2Q_REQ_WRITE || a.req == B2Q_REQ_INPLACE || a.req == B2Q_REQ_ADD, "bad req");

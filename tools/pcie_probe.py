@@ -1,0 +1,50 @@
+"""What does the host link deliver?  Pinned H2D alone, D2H alone, and both directions at once (two streams)."""
+import json
+import os
+import sys
+import time
+
+import torch
+
+torch.cuda.set_device(0)
+n = 256 * 1024 * 1024  # 1 GiB of float32
+h_in = torch.empty(n, dtype=torch.float32).pin_memory()
+h_out = torch.empty(n, dtype=torch.float32).pin_memory()
+d_a = torch.empty(n, device="cuda")
+d_b = torch.empty(n, device="cuda")
+s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+res = {}
+
+
+def run(name, fn, reps=5):
+    fn()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / reps
+    res[name] = 4 * n / dt / 1e9
+    print("%-28s %7.1f GB/s per direction" % (name, res[name]), flush=True)
+
+
+def h2d():
+    with torch.cuda.stream(s1):
+        d_a.copy_(h_in, non_blocking=True)
+
+
+def d2h():
+    with torch.cuda.stream(s2):
+        h_out.copy_(d_b, non_blocking=True)
+
+
+def both():
+    h2d()
+    d2h()
+
+
+run("h2d only", h2d)
+run("d2h only", d2h)
+run("h2d + d2h concurrently", both)
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(res, open("gpurun_out/pcie_probe.json", "w"))

@@ -1,0 +1,147 @@
+// Stand-alone tuning sweep for the three flat kernels (not part of the library): instantiates the kernel templates of
+// resnet.mxnet_b200/csrc with different unroll / cache-policy / grid choices and times them with CUDA events,
+// rotating over enough buffers that nothing is served from L2.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo tools/sweep.cu -o tools/sweep && tools/sweep
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "../resnet.mxnet_b200/csrc/b2q_common.cuh"
+#include "../resnet.mxnet_b200/csrc/b2q_qdq.cuh"
+#include "../resnet.mxnet_b200/csrc/b2q_reduce.cuh"
+
+void b2q_set_error(const std::string& msg) { fprintf(stderr, "%s\n", msg.c_str()); }
+int b2q_host_release(b2q_ctx*) { return 0; }
+
+#define CK(x)                                                                          \
+    do {                                                                               \
+        cudaError_t e = (x);                                                           \
+        if (e != cudaSuccess) {                                                        \
+            fprintf(stderr, "%s: %s\n", #x, cudaGetErrorString(e));                    \
+            exit(1);                                                                   \
+        }                                                                              \
+    } while (0)
+
+static int g_sms = 148;
+static std::vector<float*> g_x, g_y;
+static b2q_slot* g_slot;
+static float* g_thr;
+static FILE* g_out;
+
+template <class F>
+static float time_launches(F launch, int reps) {
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i) launch(i);
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < reps; ++i) launch(i);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    return ms / reps;
+}
+
+static void report(const char* kernel, int64_t n, int unroll, int ldpol, int stpol, int bps, double bytes_per_elem, float ms) {
+    const double gbs = bytes_per_elem * (double)n / ms / 1e6;
+    printf("%-10s n=%-10lld U=%d LD=%d ST=%d bps=%-2d  %8.2f us  %8.1f GB/s\n", kernel, (long long)n, unroll, ldpol, stpol,
+           bps, ms * 1e3, gbs);
+    fprintf(g_out, "%s,%lld,%d,%d,%d,%d,%.3f,%.1f\n", kernel, (long long)n, unroll, ldpol, stpol, bps, ms * 1e3, gbs);
+    fflush(stdout);
+}
+
+template <int U, int L>
+static void sweep_reduce(int64_t n, int nbuf, int reps) {
+    for (int bps : {2, 3, 4, 6, 8}) {
+        UpdateArgs u = {};
+        u.mode = B2Q_UPD_EMA; u.write_aux = 1; u.use_aux_as_scale = 1; u.p0 = 0.99f; u.p1 = 0.01f; u.aux = g_thr;
+        float ms = time_launches([&](int i) {
+            const float* x = g_x[i % nbuf];
+            FlatSplit sp = b2q_flat_split(x, n);
+            const int64_t tile = (int64_t)B2Q_THREADS * U;
+            int64_t grid = std::min<int64_t>((sp.n8 + tile - 1) / tile, (int64_t)g_sms * bps);
+            reduce_flat_kernel<true, U, L><<<(unsigned)grid, B2Q_THREADS>>>(x, sp, g_slot, u, (float)n);
+        }, reps);
+        report("reduce", n, U, L, 0, bps, 4.0, ms);
+    }
+}
+
+template <int U, int L, int S>
+static void sweep_qdq(int64_t n, int nbuf, int reps) {
+    for (int bps : {3, 4, 5, 8, 10, 16}) {
+        QdqArgs a = {g_thr, nullptr, 0.f, 0.f, 127.f, 1, nullptr, B2Q_CLIP_SYM, 1, B2Q_REQ_WRITE};
+        float ms = time_launches([&](int i) {
+            const float* x = g_x[i % nbuf];
+            float* y = g_y[i % nbuf];
+            FlatSplit sp = b2q_flat_split(x, n);
+            const int64_t tile = (int64_t)B2Q_THREADS * U;
+            int64_t grid = std::min<int64_t>((sp.n8 + tile - 1) / tile, (int64_t)g_sms * bps);
+            qdq_flat_hot_kernel<true, U, L, S><<<(unsigned)grid, B2Q_THREADS>>>(x, y, sp, a, 1);
+        }, reps);
+        report("qdq", n, U, L, S, bps, 8.0, ms);
+    }
+}
+
+template <int U, int L, int S>
+static void sweep_copy(int64_t n, int nbuf, int reps) {
+    for (int bps : {3, 4, 5, 8, 10, 16}) {
+        float ms = time_launches([&](int i) {
+            const float* x = g_x[i % nbuf];
+            float* y = g_y[i % nbuf];
+            FlatSplit sp = b2q_flat_split(x, n);
+            const int64_t tile = (int64_t)B2Q_THREADS * U;
+            int64_t grid = std::min<int64_t>((sp.n8 + tile - 1) / tile, (int64_t)g_sms * bps);
+            bwd_flat_kernel<0, false, U, L, S><<<(unsigned)grid, B2Q_THREADS>>>(nullptr, x, y, sp, nullptr, 0.f);
+        }, reps);
+        report("ste_copy", n, U, L, S, bps, 8.0, ms);
+    }
+}
+
+int main(int argc, char** argv) {
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, 0));
+    g_sms = prop.multiProcessorCount;
+    system("mkdir -p gpurun_out");
+    g_out = fopen("gpurun_out/sweep.csv", "w");
+    fprintf(g_out, "kernel,n,unroll,ldpol,stpol,blocks_per_sm,us,alg_gbs\n");
+    CK(cudaMalloc(&g_slot, sizeof(b2q_slot)));
+    CK(cudaMemset(g_slot, 0, sizeof(b2q_slot)));
+    CK(cudaMalloc(&g_thr, 4));
+    float one = 1.0f;
+    CK(cudaMemcpy(g_thr, &one, 4, cudaMemcpyHostToDevice));
+    const int64_t sizes[] = {12845056, 51380224, 205520896};   // (256,256,14,14) (256,64,56,56) (256,256,56,56)
+    const int64_t maxn = 205520896;
+    const int total_bufs = 6;   // 6 x 822 MB input + 6 x 822 MB output
+    for (int i = 0; i < total_bufs; ++i) {
+        float *x, *y;
+        CK(cudaMalloc(&x, maxn * 4));
+        CK(cudaMalloc(&y, maxn * 4));
+        CK(cudaMemset(x, 0x3c, maxn * 4));   // 0x3c3c3c3c = 0.0115 : finite, nonzero
+        g_x.push_back(x);
+        g_y.push_back(y);
+    }
+    for (int64_t n : sizes) {
+        // carve more virtual buffers out of the big allocations for small sizes so that the rotation exceeds L2
+        std::vector<float*> bx = g_x, by = g_y;
+        std::vector<float*> vx, vy;
+        for (int i = 0; i < total_bufs; ++i)
+            for (int64_t off = 0; off + n <= maxn && (int)vx.size() < 48; off += n) { vx.push_back(bx[i] + off); vy.push_back(by[i] + off); }
+        g_x = vx; g_y = vy;
+        const int nbuf = (int)g_x.size();
+        const int reps = n > 100000000 ? 12 : 48;
+        printf("---- n = %lld (%d rotating buffers) ----\n", (long long)n, nbuf);
+        sweep_reduce<2, 0>(n, nbuf, reps); sweep_reduce<4, 0>(n, nbuf, reps); sweep_reduce<8, 0>(n, nbuf, reps);
+        sweep_reduce<4, 1>(n, nbuf, reps); sweep_reduce<4, 3>(n, nbuf, reps); sweep_reduce<2, 1>(n, nbuf, reps);
+        sweep_qdq<1, 2, 0>(n, nbuf, reps); sweep_qdq<2, 2, 0>(n, nbuf, reps); sweep_qdq<4, 2, 0>(n, nbuf, reps);
+        sweep_qdq<2, 1, 0>(n, nbuf, reps); sweep_qdq<2, 2, 1>(n, nbuf, reps); sweep_qdq<2, 0, 0>(n, nbuf, reps);
+        sweep_qdq<2, 2, 2>(n, nbuf, reps);
+        sweep_copy<1, 2, 0>(n, nbuf, reps); sweep_copy<2, 2, 0>(n, nbuf, reps); sweep_copy<4, 2, 0>(n, nbuf, reps);
+        sweep_copy<2, 1, 0>(n, nbuf, reps); sweep_copy<2, 2, 1>(n, nbuf, reps); sweep_copy<2, 0, 0>(n, nbuf, reps);
+        g_x = bx; g_y = by;
+    }
+    fclose(g_out);
+    return 0;
+}

@@ -68,6 +68,8 @@ int64_t b2q_launch_count(b2q_ctx* ctx) { return ctx ? ctx->launches : -1; }
 
 static int* option_slot(b2q_ctx* ctx, const char* key) {
     if (!strcmp(key, "blocks_per_sm")) return &ctx->blocks_per_sm;
+    if (!strcmp(key, "reduce_blocks_per_sm")) return &ctx->reduce_blocks_per_sm;
+    if (!strcmp(key, "deferred")) return &ctx->deferred;
     if (!strcmp(key, "reverse")) return &ctx->reverse;
     if (!strcmp(key, "fast_div")) return &ctx->fast_div;
     if (!strcmp(key, "timing")) return &ctx->timing;
@@ -78,7 +80,8 @@ int b2q_set_option(b2q_ctx* ctx, const char* key, int value) {
     B2Q_REQUIRE(ctx && key, "null argument");
     int* p = option_slot(ctx, key);
     B2Q_REQUIRE(p != nullptr, "unknown option");
-    if (p == &ctx->blocks_per_sm) B2Q_REQUIRE(value >= 1 && value <= 32, "blocks_per_sm out of range");
+    if (p == &ctx->blocks_per_sm || p == &ctx->reduce_blocks_per_sm)
+        B2Q_REQUIRE(value >= 1 && value <= 64, "blocks_per_sm out of range");
     *p = value;
     return 0;
 }
@@ -240,16 +243,25 @@ int b2q_minmax_quant_fwd_f32(b2q_ctx* ctx, int variant, const float* x, float* y
     const float* scale_src = aux;
     // Does this call need a reduction?  weight: V2 always, ClipGrad only when training; act: when training.
     const bool reduce = is_weight ? (variant == 0 || is_train) : (is_train != 0);
-    if (reduce) {
-        b2q_slot* slot = b2q_take_slot(ctx);
-        UpdateArgs u = minmax_update(variant, is_weight, is_train, init, ema_decay, one_minus_decay, aux, slot, &scale_src);
-        int rc = launch_reduce<true>(ctx, slot, x, outer, groups, inner, kNoPrescale, u, st);
-        if (rc) return rc;
-    }
     // ClipGrad activations are clipped to +-aux and written with [:]= regardless of req (clip_grad...py:48-51)
     const bool clip = (variant == 1 && !is_weight);
     int eff_req = req;
     if (clip) eff_req = B2Q_REQ_WRITE;
+    if (reduce) {
+        b2q_slot* slot = b2q_take_slot(ctx);
+        UpdateArgs u = minmax_update(variant, is_weight, is_train, init, ema_decay, one_minus_decay, aux, slot, &scale_src);
+        if (groups == 1 && (eff_req == B2Q_REQ_WRITE || eff_req == B2Q_REQ_INPLACE)) {
+            // fused: partial maxima + a sweep that finishes the threshold update itself (no serialized tail)
+            UpdateArgs ud = u;
+            ud.scale_out = nullptr;
+            int done = 0;
+            int rc = launch_fused_flat_fwd<true>(ctx, slot, x, y, inner, ud, 127.f, clip ? B2Q_CLIP_SYM : B2Q_CLIP_NONE, 0,
+                                                 st, &done);
+            if (rc || done) return rc;
+        }
+        int rc = launch_reduce<true>(ctx, slot, x, outer, groups, inner, kNoPrescale, u, st);
+        if (rc) return rc;
+    }
     if (eff_req == B2Q_REQ_NULL) return 0;
     QdqArgs a = {scale_src, nullptr, 0.f, 0.f, 127.f, ctx->fast_div, nullptr,
                  clip ? B2Q_CLIP_SYM : B2Q_CLIP_NONE, 1, eff_req};
@@ -311,7 +323,13 @@ int b2q_gdrq_fwd_f32(b2q_ctx* ctx, const float* x, float* y, float* alpha, int64
         memset(&u, 0, sizeof(u));
         u.mode = is_weight ? B2Q_UPD_GDRQ_WEIGHT : B2Q_UPD_GDRQ_ACT;
         u.write_aux = 1; u.use_aux_as_scale = 1; u.p0 = ktimes; u.p1 = lamda; u.aux = alpha;
-        int rc = launch_reduce<false>(ctx, b2q_take_slot(ctx), x, outer, groups, inner, kNoPrescale, u, st);
+        b2q_slot* slot = b2q_take_slot(ctx);
+        if (groups == 1 && do_round && (req == B2Q_REQ_WRITE || req == B2Q_REQ_INPLACE)) {
+            int done = 0;
+            int rc = launch_fused_flat_fwd<false>(ctx, slot, x, y, outer * inner, u, qlevel, B2Q_CLIP_SYM, 0, st, &done);
+            if (rc || done) return rc;
+        }
+        int rc = launch_reduce<false>(ctx, slot, x, outer, groups, inner, kNoPrescale, u, st);
         if (rc) return rc;
     }
     if (req == B2Q_REQ_NULL) return 0;
@@ -342,6 +360,11 @@ int b2q_foldbn_data_fwd_f32(b2q_ctx* ctx, const float* x, float* y, float* aux_d
     memset(&u, 0, sizeof(u));
     u.mode = init ? B2Q_UPD_TWICE_STORE : B2Q_UPD_TWICE_EMA;   // fold_bn_v1_gdrq.py:58-64
     u.write_aux = 1; u.use_aux_as_scale = 1; u.p0 = ema_decay; u.p1 = one_minus_decay; u.aux = aux_data;
+    {
+        int done = 0;
+        int rc = launch_fused_flat_fwd<false>(ctx, slot, x, y, n, u, 127.f, B2Q_CLIP_SYM, /*clip_with_fresh=*/1, st, &done);
+        if (rc || done) return rc;
+    }
     u.clip_out = slot->clip;                                    // :67 clips with the batch threshold
     int rc = launch_reduce<false>(ctx, slot, x, 1, 1, n, kNoPrescale, u, st);
     if (rc) return rc;

@@ -44,7 +44,9 @@ struct b2q_ctx {
     unsigned int next_slot = 0;
     long long launches = 0;
     // run-time knobs (never change results)
-    int blocks_per_sm = 8;
+    int blocks_per_sm = 16;          // flat QDQ / backward sweeps: grid = SMs x this (sweep: 16 best)
+    int reduce_blocks_per_sm = 4;    // flat reductions
+    int deferred = 1;                // consumer-side threshold update in the fused whole-tensor forward
     int reverse = 1;
     int fast_div = 1;
     int timing = 0;
@@ -201,29 +203,50 @@ struct UpdateArgs {
     float* stat_out;   // [groups] raw statistic (may be null)
 };
 
-__device__ __forceinline__ void apply_update(const UpdateArgs& u, int g, float stat) {
-    if (u.stat_out) u.stat_out[g] = stat;
-    if (u.mode == 0) return;
-    float fresh = stat;   // the batch threshold
-    float a = u.aux ? u.aux[g] : 0.f;
-    float next = a;
-    switch (u.mode) {
+// Pure part of the update: from the old aux value and the reduced statistic to (batch threshold, new aux).
+__device__ __forceinline__ void compute_update(int mode, float p0, float p1, float a, float stat, float& fresh,
+                                               float& next) {
+    fresh = stat;
+    next = a;
+    switch (mode) {
         case B2Q_UPD_STORE: next = stat; break;
-        case B2Q_UPD_EMA: next = __fadd_rn(__fmul_rn(a, u.p0), __fmul_rn(stat, u.p1)); break;
-        case B2Q_UPD_GDRQ_WEIGHT: fresh = __fmul_rn(u.p0, stat); next = fresh; break;
+        case B2Q_UPD_EMA: next = __fadd_rn(__fmul_rn(a, p0), __fmul_rn(stat, p1)); break;
+        case B2Q_UPD_GDRQ_WEIGHT: fresh = __fmul_rn(p0, stat); next = fresh; break;
         case B2Q_UPD_GDRQ_ACT:
-            fresh = __fmul_rn(u.p0, stat);
-            next = __fadd_rn(a, __fmul_rn(u.p1, __fsub_rn(a, fresh)));
+            fresh = __fmul_rn(p0, stat);
+            next = __fadd_rn(a, __fmul_rn(p1, __fsub_rn(a, fresh)));
             break;
         case B2Q_UPD_TWICE_STORE: fresh = __fmul_rn(2.f, stat); next = fresh; break;
         case B2Q_UPD_TWICE_EMA:
             fresh = __fmul_rn(2.f, stat);
-            next = __fadd_rn(__fmul_rn(a, u.p0), __fmul_rn(fresh, u.p1));
+            next = __fadd_rn(__fmul_rn(a, p0), __fmul_rn(fresh, p1));
             break;
         default: break;
     }
+}
+
+__device__ __forceinline__ void apply_update(const UpdateArgs& u, int g, float stat) {
+    if (u.stat_out) u.stat_out[g] = stat;
+    if (u.mode == 0) return;
+    const float a = u.aux ? u.aux[g] : 0.f;
+    float fresh, next;
+    compute_update(u.mode, u.p0, u.p1, a, stat, fresh, next);
     if (u.write_aux && u.aux) u.aux[g] = next;
     const float after = u.write_aux ? next : a;
     if (u.scale_out) u.scale_out[g] = u.use_aux_as_scale ? after : fresh;
     if (u.clip_out) u.clip_out[g] = fresh;
 }
+
+// Deferred ("consumer-side") threshold update for the fused whole-tensor forward: the reduction kernel only stores
+// its per-block partials and a snapshot of the old aux value; every block of the QDQ sweep that follows combines the
+// partials itself (same fixed order in every block => identical, deterministic result), derives the thresholds in
+// registers and block 0 writes the new aux.  This removes the serialized fence -> ticket -> last-block -> update
+// chain (~5 us, profiles/r01b_sweep.csv) from between the two kernels.
+struct DeferredUpdate {
+    const double* partial;   // [count_partials] written by reduce_flat_kernel<.., FINALIZE=false>
+    const float* aux_old;    // snapshot of aux[0] taken by the reduction kernel
+    int n_partials;
+    int is_max;
+    float count;             // elements (for means)
+    UpdateArgs u;            // mode / write_aux / use_aux_as_scale / p0 / p1 / aux (destination)
+};

@@ -125,11 +125,39 @@ __device__ __forceinline__ float qdq_generic(const QdqArgs& a, float x, float Tc
 // tail of x is still in the 126 MB L2.  x is loaded evict-first (last use); y is stored plainly because the
 // convolution reads it next.
 // ------------------------------------------------------------------------------------------------
-template <bool CLIP_SYM, int UNROLL, int LDPOL, int STPOL>
+template <bool CLIP_SYM, int UNROLL, int LDPOL, int STPOL, bool DEFERRED>
 __global__ void __launch_bounds__(B2Q_THREADS)
-qdq_flat_hot_kernel(const float* __restrict__ x, float* __restrict__ y, FlatSplit sp, QdqArgs a, int reverse) {
-    const float T = a.thr ? __ldg(a.thr) : a.thr_imm;
-    const float Tc = a.clip_thr ? __ldg(a.clip_thr) : (a.thr ? T : a.clip_imm);
+qdq_flat_hot_kernel(const float* __restrict__ x, float* __restrict__ y, FlatSplit sp, QdqArgs a, int reverse,
+                    DeferredUpdate d, int clip_with_fresh) {
+    float T, Tc;
+    if (DEFERRED) {
+        // combine the reduction's partials (every block, same fixed order), derive thresholds in registers
+        __shared__ double smem[32];
+        __shared__ float s_thr[2];
+        double acc = 0.0;
+        float m = 0.f;
+        for (int i = threadIdx.x; i < d.n_partials; i += blockDim.x) {
+            const double p = d.partial[i];
+            if (d.is_max) m = fmaxf(m, (float)p); else acc += p;
+        }
+        const double tot = d.is_max ? block_reduce<true>((double)m, smem) : block_reduce<false>(acc, smem);
+        if (threadIdx.x == 0) {
+            const float stat = d.is_max ? (float)tot : __fdiv_rn((float)tot, d.count);
+            const float a_old = d.u.aux ? d.aux_old[0] : 0.f;
+            float fresh, next;
+            compute_update(d.u.mode, d.u.p0, d.u.p1, a_old, stat, fresh, next);
+            const float after = d.u.write_aux ? next : a_old;
+            s_thr[0] = d.u.use_aux_as_scale ? after : fresh;
+            s_thr[1] = clip_with_fresh ? fresh : s_thr[0];
+            if (blockIdx.x == 0 && d.u.write_aux && d.u.aux) d.u.aux[0] = next;
+        }
+        __syncthreads();
+        T = s_thr[0];
+        Tc = s_thr[1];
+    } else {
+        T = a.thr ? __ldg(a.thr) : a.thr_imm;
+        Tc = a.clip_thr ? __ldg(a.clip_thr) : (a.thr ? T : a.clip_imm);
+    }
     const QScale s = make_qscale(T, a.qlevel, a.fast != 0 && !(CLIP_SYM && !(Tc >= 0.f)));
     const float* xb = x + sp.head;
     float* yb = y + sp.head;
@@ -385,12 +413,13 @@ static inline bool same_misalignment(const void* a, const void* b) {
             b2q_timed_launch tl(ctx, hot ? B2Q_KIND_QDQ_HOT : B2Q_KIND_OTHER, 8.0 * (double)n, st);
             if (hot) {
                 const int64_t grid = b2q_flat_grid(ctx, sp.n8, B2Q_QDQ_UNROLL);
+                DeferredUpdate none = {};
                 if (a.clip_mode == B2Q_CLIP_SYM)
-                    qdq_flat_hot_kernel<true, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, B2Q_QDQ_STPOL>
-                        <<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, y, sp, a, ctx->reverse);
+                    qdq_flat_hot_kernel<true, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, B2Q_QDQ_STPOL, false>
+                        <<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, y, sp, a, ctx->reverse, none, 0);
                 else
-                    qdq_flat_hot_kernel<false, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, B2Q_QDQ_STPOL>
-                        <<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, y, sp, a, ctx->reverse);
+                    qdq_flat_hot_kernel<false, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, B2Q_QDQ_STPOL, false>
+                        <<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, y, sp, a, ctx->reverse, none, 0);
             } else {
                 const int64_t grid = b2q_flat_grid(ctx, sp.n8, 2);
                 qdq_flat_generic_kernel<2><<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, y, sp, a);
@@ -406,6 +435,44 @@ static inline bool same_misalignment(const void* a, const void* b) {
     if (pl.vec == 4) qdq_seg_kernel<4><<<grid, 128, 0, st>>>(x, y, pl, ps, fb, a);
     else qdq_seg_kernel<1><<<grid, 128, 0, st>>>(x, y, pl, ps, fb, a);
     B2Q_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+// Fused whole-tensor forward: reduction (partials only) + QDQ sweep that finishes the threshold update itself.
+// Eligible when the sweep is the hot kernel (clip none / symmetric, rounding, req write) and the buffers allow the
+// 256-bit path; *done = 0 tells the caller to take the generic reduce -> update -> sweep route instead.
+template <bool IS_MAX>
+[[maybe_unused]] static int launch_fused_flat_fwd(b2q_ctx* ctx, b2q_slot* slot, const float* x, float* y, int64_t n,
+                                                  UpdateArgs u, float qlevel, int clip_mode, int clip_with_fresh,
+                                                  cudaStream_t st, int* done) {
+    *done = 0;
+    if (!ctx->deferred || !(clip_mode == B2Q_CLIP_NONE || clip_mode == B2Q_CLIP_SYM)) return 0;
+    if (u.stat_out != nullptr) return 0;
+    FlatSplit sp = b2q_flat_split(x, n);
+    if (!same_misalignment(x, y) || sp.head > B2Q_THREADS) return 0;
+    int np = 0;
+    int rc = launch_reduce_deferred<IS_MAX>(ctx, slot, x, n, u, st, &np);
+    if (rc || np == 0) return rc;
+    DeferredUpdate d;
+    d.partial = slot->partial;
+    d.aux_old = slot->scale;
+    d.n_partials = np;
+    d.is_max = IS_MAX ? 1 : 0;
+    d.count = (float)n;
+    d.u = u;
+    QdqArgs a = {nullptr, nullptr, 0.f, 0.f, qlevel, ctx->fast_div, nullptr, clip_mode, 1, B2Q_REQ_WRITE};
+    const int64_t grid = b2q_flat_grid(ctx, sp.n8, B2Q_QDQ_UNROLL);
+    {
+        b2q_timed_launch tl(ctx, B2Q_KIND_QDQ_HOT, 8.0 * (double)n, st);
+        if (clip_mode == B2Q_CLIP_SYM)
+            qdq_flat_hot_kernel<true, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, B2Q_QDQ_STPOL, true>
+                <<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, y, sp, a, ctx->reverse, d, clip_with_fresh);
+        else
+            qdq_flat_hot_kernel<false, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, B2Q_QDQ_STPOL, true>
+                <<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, y, sp, a, ctx->reverse, d, clip_with_fresh);
+        B2Q_LAUNCH_CHECK(ctx);
+    }
+    *done = 1;
     return 0;
 }
 

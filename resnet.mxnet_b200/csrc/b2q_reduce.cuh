@@ -10,6 +10,9 @@
 #ifndef B2Q_REDUCE_LDPOL
 #define B2Q_REDUCE_LDPOL 0
 #endif
+#ifndef B2Q_REDUCE_BPS
+#define B2Q_REDUCE_BPS 4     // blocks per SM for the flat reduction (sweep: 4 is best from 50 MB up)
+#endif
 
 // A flat float32 array split for 256-bit access: `head` scalars until 32-byte alignment, n8 groups of eight
 // floats, `tail` scalars.
@@ -54,7 +57,7 @@ __device__ __forceinline__ void acc8(double& a, float& m, const f8& r) {
 // Grid-stride over tiles of THREADS*UNROLL 256-bit words in ASCENDING address order, so that the most
 // recently read part of x is what remains in L2 for the QDQ sweep that follows (which walks descending).
 // ------------------------------------------------------------------------------------------------
-template <bool IS_MAX, int UNROLL, int LDPOL>
+template <bool IS_MAX, int UNROLL, int LDPOL, bool FINALIZE>
 __global__ void __launch_bounds__(B2Q_THREADS)
 reduce_flat_kernel(const float* __restrict__ x, FlatSplit sp, b2q_slot* slot, UpdateArgs u, float count) {
     __shared__ double smem[32];
@@ -84,6 +87,18 @@ reduce_flat_kernel(const float* __restrict__ x, FlatSplit sp, b2q_slot* slot, Up
         if ((int64_t)threadIdx.x < sp.tail) acc1<IS_MAX>(acc, mx, x[sp.head + 8 * sp.n8 + threadIdx.x]);
     }
     double r = block_reduce<IS_MAX>(IS_MAX ? (double)mx : acc, smem);
+    if (!FINALIZE) {
+        // deferred update: the consumer kernel combines the partials (see DeferredUpdate)
+        if (threadIdx.x == 0) {
+            slot->partial[blockIdx.x] = r;
+            if (blockIdx.x == 0 && u.aux) slot->scale[0] = u.aux[0];   // snapshot of the old threshold
+        }
+        return;
+    }
+    if (gridDim.x == 1) {   // single block: nothing to combine, no fence / ticket round trips
+        if (threadIdx.x == 0) apply_update(u, 0, IS_MAX ? (float)r : __fdiv_rn((float)r, count));
+        return;
+    }
     if (threadIdx.x == 0) {
         slot->partial[blockIdx.x] = r;
         __threadfence();
@@ -240,14 +255,31 @@ static __global__ void threshold_update_kernel(const float* __restrict__ stat, i
 // ------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------
-static inline int64_t b2q_flat_grid(const b2q_ctx* ctx, int64_t n8, int unroll) {
+static inline int64_t b2q_flat_grid(const b2q_ctx* ctx, int64_t n8, int unroll, int bps = 0) {
     const int64_t tile = (int64_t)B2Q_THREADS * unroll;
     int64_t ntiles = (n8 + tile - 1) / tile;
-    int64_t grid = (int64_t)ctx->num_sms * ctx->blocks_per_sm;
+    int64_t grid = (int64_t)ctx->num_sms * (bps > 0 ? bps : ctx->blocks_per_sm);
     if (grid > ntiles) grid = ntiles;
     if (grid < 1) grid = 1;
     if (grid > B2Q_MAX_PIECES) grid = B2Q_MAX_PIECES;
     return grid;
+}
+
+// Reduction half of the fused whole-tensor forward with the update deferred to the consumer.  Returns the number of
+// partials through *n_partials (0: tensor not eligible, caller must use launch_reduce).
+template <bool IS_MAX>
+static int launch_reduce_deferred(b2q_ctx* ctx, b2q_slot* slot, const float* x, int64_t n, UpdateArgs u,
+                                  cudaStream_t st, int* n_partials) {
+    *n_partials = 0;
+    FlatSplit sp = b2q_flat_split(x, n);
+    if (sp.head > B2Q_THREADS) return 0;
+    const int64_t grid = b2q_flat_grid(ctx, sp.n8, B2Q_REDUCE_UNROLL, ctx->reduce_blocks_per_sm);
+    b2q_timed_launch tl(ctx, B2Q_KIND_REDUCE_FLAT, 4.0 * (double)n, st);
+    reduce_flat_kernel<IS_MAX, B2Q_REDUCE_UNROLL, B2Q_REDUCE_LDPOL, false>
+        <<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, sp, slot, u, (float)n);
+    B2Q_LAUNCH_CHECK(ctx);
+    *n_partials = (int)grid;
+    return 0;
 }
 
 template <bool IS_MAX>
@@ -259,9 +291,9 @@ static int launch_reduce(b2q_ctx* ctx, b2q_slot* slot, const float* x, int64_t o
     if (groups == 1 && ps.gamma == nullptr) {
         FlatSplit sp = b2q_flat_split(x, n);
         if (sp.head <= B2Q_THREADS) {
-            const int64_t grid = b2q_flat_grid(ctx, sp.n8, B2Q_REDUCE_UNROLL);
+            const int64_t grid = b2q_flat_grid(ctx, sp.n8, B2Q_REDUCE_UNROLL, ctx->reduce_blocks_per_sm);
             b2q_timed_launch tl(ctx, B2Q_KIND_REDUCE_FLAT, 4.0 * (double)n, st);
-            reduce_flat_kernel<IS_MAX, B2Q_REDUCE_UNROLL, B2Q_REDUCE_LDPOL>
+            reduce_flat_kernel<IS_MAX, B2Q_REDUCE_UNROLL, B2Q_REDUCE_LDPOL, true>
                 <<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, sp, slot, u, (float)n);
             B2Q_LAUNCH_CHECK(ctx);
             return 0;

@@ -91,3 +91,107 @@ class Custom(nn.Module):
 
     def extra_repr(self):
         return "op_type=%s, %s" % (self.op_type, ", ".join("%s=%s" % kv for kv in sorted(self.attrs.items())))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Layer wrappers with the reference's naming contract
+# ----------------------------------------------------------------------------------------------------------
+_STYLES = {
+    # symbol/quant_ops.py:87-94: nodes <name>_weight_quant / <name>_data_quant, op Quantization_int8_V2
+    "quant_ops": ("Quantization_int8_V2", "_weight_quant", "_data_quant"),
+    # symbol/int8_api.py:29-36: nodes <name>_weight / <name>_data, op ClipGrad_Quantization_int8
+    "int8_api": ("ClipGrad_Quantization_int8", "_weight", "_data"),
+}
+
+
+class _QuantLayer(nn.Module):
+    def _make_nodes(self, name, style, quant_mod, delay_quant, is_weight_perchannel, ema_decay):
+        if is_weight_perchannel:
+            assert quant_mod == "minmax", "currenet weight perchannel only support minmax node with weight"
+        op_type, wsuf, dsuf = _STYLES[style]
+        self.layer_name = name
+        self.weight_node_name = name + wsuf
+        self.data_node_name = name + dsuf
+        self.weight_quant = Custom(op_type, quant_mode=quant_mod, is_weight=True,
+                                   is_weight_perchannel=is_weight_perchannel, ema_decay=ema_decay,
+                                   delay_quant=delay_quant)
+        self.data_quant = Custom(op_type, quant_mode=quant_mod, is_weight=False, is_weight_perchannel=False,
+                                 ema_decay=ema_decay, delay_quant=delay_quant)
+
+    def mx_names(self):
+        """MXNet checkpoint names of this layer's parameters / aux states (arg:<..>, aux:<..>)."""
+        args = {self.layer_name + "_weight": self.weight}
+        if getattr(self, "bias", None) is not None:
+            args[self.layer_name + "_bias"] = self.bias
+        aux = {}
+        for node, mod in ((self.weight_node_name, self.weight_quant), (self.data_node_name, self.data_quant)):
+            for aname in mod.aux_names:
+                if getattr(mod, aname, None) is not None:
+                    aux[node + "_" + aname] = getattr(mod, aname)
+        return args, aux
+
+
+class QuantConv2d(_QuantLayer):
+    """``quant_conv`` (symbol/quant_ops.py:81-107) / ``clipgrad_quant_conv`` (symbol/int8_api.py:19-50) as a torch
+    module: weight Variable ``<name>_weight`` -> weight-quant node, input -> data-quant node, Convolution."""
+
+    def __init__(self, name, in_channels, num_filter, kernel, stride=(1, 1), pad=(0, 0), no_bias=True, dilate=(1, 1),
+                 num_group=1, quant_mod="minmax", delay_quant=0, is_weight_perchannel=False, ema_decay=0.99,
+                 style="quant_ops"):
+        super(QuantConv2d, self).__init__()
+        self.stride, self.pad, self.dilate, self.num_group = tuple(stride), tuple(pad), tuple(dilate), int(num_group)
+        self.weight = nn.Parameter(torch.empty(num_filter, in_channels // num_group, kernel[0], kernel[1]))
+        nn.init.kaiming_normal_(self.weight, mode="fan_in", nonlinearity="relu")   # Xavier(gaussian, in, 2), train.py:221
+        self.bias = None if no_bias else nn.Parameter(torch.zeros(num_filter))
+        self._make_nodes(name, style, quant_mod, delay_quant, is_weight_perchannel, ema_decay)
+
+    def forward(self, x):
+        return torch.nn.functional.conv2d(self.data_quant(x), self.weight_quant(self.weight), self.bias, self.stride,
+                                          self.pad, self.dilate, self.num_group)
+
+
+class QuantLinear(_QuantLayer):
+    """``quant_fc`` (symbol/quant_ops.py:109-121) / ``clipgrad_quant_fc`` (symbol/int8_api.py:52-71)."""
+
+    def __init__(self, name, in_features, num_hidden, no_bias=False, quant_mod="minmax", delay_quant=0,
+                 is_weight_perchannel=False, ema_decay=0.99, style="quant_ops"):
+        super(QuantLinear, self).__init__()
+        self.weight = nn.Parameter(torch.empty(num_hidden, in_features))
+        nn.init.kaiming_normal_(self.weight, mode="fan_in", nonlinearity="relu")
+        self.bias = None if no_bias else nn.Parameter(torch.zeros(num_hidden))
+        self._make_nodes(name, style, quant_mod, delay_quant, is_weight_perchannel, ema_decay)
+
+    def forward(self, x):
+        return torch.nn.functional.linear(self.data_quant(x.flatten(1)), self.weight_quant(self.weight), self.bias)
+
+
+def export_mx_params(model):
+    """(arg_params, aux_params) name -> tensor maps in the reference's checkpoint naming (train.py:218,224-227),
+    plus the per-op Python state the reference forgets to save (delay_quant countdown, first-batch init flag)."""
+    arg_params, aux_params, op_state = {}, {}, {}
+    for mod in model.modules():
+        if isinstance(mod, _QuantLayer):
+            a, x = mod.mx_names()
+            arg_params.update({k: v.detach() for k, v in a.items()})
+            aux_params.update({k: v.detach() for k, v in x.items()})
+            op_state[mod.weight_node_name] = mod.weight_quant.get_extra_state()
+            op_state[mod.data_node_name] = mod.data_quant.get_extra_state()
+    return arg_params, aux_params, op_state
+
+
+class SimpleCifarNet(nn.Module):
+    """symbol/simple.py:10-18 with every conv / FC routed through quant_conv / quant_fc (BASELINE.json config 1)."""
+
+    def __init__(self, num_classes=10, style="quant_ops", **quant_kw):
+        super(SimpleCifarNet, self).__init__()
+        self.stage1_conv = QuantConv2d("stage1_conv", 3, 8, (3, 3), (2, 2), (1, 1), True, style=style, **quant_kw)
+        self.stage1_bn = nn.BatchNorm2d(8, eps=1e-3, momentum=0.1)   # mx BatchNorm defaults: eps 1e-3, momentum 0.9
+        self.stage2_conv = QuantConv2d("stage2_conv", 8, 8, (3, 3), (2, 2), (1, 1), True, style=style, **quant_kw)
+        self.stage2_bn = nn.BatchNorm2d(8, eps=1e-3, momentum=0.1)
+        self.fc1 = QuantLinear("fc1", 8, num_classes, style=style, **quant_kw)
+
+    def forward(self, x):
+        x = torch.relu(self.stage1_bn(self.stage1_conv(x)))
+        x = torch.relu(self.stage2_bn(self.stage2_conv(x)))
+        x = x.mean(dim=(2, 3))                       # global average pool (simple.py:14)
+        return self.fc1(x)

@@ -53,7 +53,7 @@ static void report(const char* kernel, int64_t n, int unroll, int ldpol, int stp
     fflush(stdout);
 }
 
-template <int U, int L>
+template <int U, int L, bool FIN>
 static void sweep_reduce(int64_t n, int nbuf, int reps) {
     for (int bps : {2, 3, 4, 6, 8}) {
         UpdateArgs u = {};
@@ -63,31 +63,62 @@ static void sweep_reduce(int64_t n, int nbuf, int reps) {
             FlatSplit sp = b2q_flat_split(x, n);
             const int64_t tile = (int64_t)B2Q_THREADS * U;
             int64_t grid = std::min<int64_t>((sp.n8 + tile - 1) / tile, (int64_t)g_sms * bps);
-            reduce_flat_kernel<true, U, L><<<(unsigned)grid, B2Q_THREADS>>>(x, sp, g_slot, u, (float)n);
+            reduce_flat_kernel<true, U, L, FIN><<<(unsigned)grid, B2Q_THREADS>>>(x, sp, g_slot, u, (float)n);
         }, reps);
-        report("reduce", n, U, L, 0, bps, 4.0, ms);
+        report(FIN ? "reduce" : "reduce_nofin", n, U, L, 0, bps, 4.0, ms);
     }
 }
 
 template <int U, int L, int S>
 static void sweep_qdq(int64_t n, int nbuf, int reps) {
-    for (int bps : {3, 4, 5, 8, 10, 16}) {
+    for (int bps : {4, 5, 8, 16, 24, 32, 64}) {
         QdqArgs a = {g_thr, nullptr, 0.f, 0.f, 127.f, 1, nullptr, B2Q_CLIP_SYM, 1, B2Q_REQ_WRITE};
+        DeferredUpdate none = {};
         float ms = time_launches([&](int i) {
             const float* x = g_x[i % nbuf];
             float* y = g_y[i % nbuf];
             FlatSplit sp = b2q_flat_split(x, n);
             const int64_t tile = (int64_t)B2Q_THREADS * U;
             int64_t grid = std::min<int64_t>((sp.n8 + tile - 1) / tile, (int64_t)g_sms * bps);
-            qdq_flat_hot_kernel<true, U, L, S><<<(unsigned)grid, B2Q_THREADS>>>(x, y, sp, a, 1);
+            qdq_flat_hot_kernel<true, U, L, S, false><<<(unsigned)grid, B2Q_THREADS>>>(x, y, sp, a, 1, none, 0);
         }, reps);
         report("qdq", n, U, L, S, bps, 8.0, ms);
     }
 }
 
+// the fused forward as the library runs it: reduction + sweep on the SAME tensor, (a) update finalised by the
+// reduction's last block, (b) update deferred to the sweep
+template <bool DEFER>
+static void sweep_pair(int64_t n, int nbuf, int reps, int rbps, int qbps, int reverse) {
+    UpdateArgs u = {};
+    u.mode = B2Q_UPD_EMA; u.write_aux = 1; u.use_aux_as_scale = 1; u.p0 = 0.99f; u.p1 = 0.01f; u.aux = g_thr;
+    float ms = time_launches([&](int i) {
+        const float* x = g_x[i % nbuf];
+        float* y = g_y[i % nbuf];
+        FlatSplit sp = b2q_flat_split(x, n);
+        int64_t rgrid = std::min<int64_t>((sp.n8 + B2Q_THREADS * 4 - 1) / (B2Q_THREADS * 4), (int64_t)g_sms * rbps);
+        int64_t qgrid = std::min<int64_t>((sp.n8 + B2Q_THREADS * 2 - 1) / (B2Q_THREADS * 2), (int64_t)g_sms * qbps);
+        QdqArgs a = {g_thr, nullptr, 0.f, 0.f, 127.f, 1, nullptr, B2Q_CLIP_SYM, 1, B2Q_REQ_WRITE};
+        if (DEFER) {
+            reduce_flat_kernel<true, 4, 0, false><<<(unsigned)rgrid, B2Q_THREADS>>>(x, sp, g_slot, u, (float)n);
+            DeferredUpdate d;
+            d.partial = g_slot->partial; d.aux_old = g_slot->scale; d.n_partials = (int)rgrid; d.is_max = 1;
+            d.count = (float)n; d.u = u;
+            qdq_flat_hot_kernel<true, 2, 2, 0, true><<<(unsigned)qgrid, B2Q_THREADS>>>(x, y, sp, a, reverse, d, 0);
+        } else {
+            DeferredUpdate none = {};
+            reduce_flat_kernel<true, 4, 0, true><<<(unsigned)rgrid, B2Q_THREADS>>>(x, sp, g_slot, u, (float)n);
+            qdq_flat_hot_kernel<true, 2, 2, 0, false><<<(unsigned)qgrid, B2Q_THREADS>>>(x, y, sp, a, reverse, none, 0);
+        }
+    }, reps);
+    char name[64];
+    snprintf(name, sizeof(name), "pair_%s_rev%d_r%d", DEFER ? "defer" : "final", reverse, rbps);
+    report(name, n, 0, 0, 0, qbps, 12.0, ms);
+}
+
 template <int U, int L, int S>
 static void sweep_copy(int64_t n, int nbuf, int reps) {
-    for (int bps : {3, 4, 5, 8, 10, 16}) {
+    for (int bps : {4, 5, 8, 16, 24, 32, 64}) {
         float ms = time_launches([&](int i) {
             const float* x = g_x[i % nbuf];
             float* y = g_y[i % nbuf];
@@ -133,13 +164,16 @@ int main(int argc, char** argv) {
         const int nbuf = (int)g_x.size();
         const int reps = n > 100000000 ? 12 : 48;
         printf("---- n = %lld (%d rotating buffers) ----\n", (long long)n, nbuf);
-        sweep_reduce<2, 0>(n, nbuf, reps); sweep_reduce<4, 0>(n, nbuf, reps); sweep_reduce<8, 0>(n, nbuf, reps);
-        sweep_reduce<4, 1>(n, nbuf, reps); sweep_reduce<4, 3>(n, nbuf, reps); sweep_reduce<2, 1>(n, nbuf, reps);
-        sweep_qdq<1, 2, 0>(n, nbuf, reps); sweep_qdq<2, 2, 0>(n, nbuf, reps); sweep_qdq<4, 2, 0>(n, nbuf, reps);
-        sweep_qdq<2, 1, 0>(n, nbuf, reps); sweep_qdq<2, 2, 1>(n, nbuf, reps); sweep_qdq<2, 0, 0>(n, nbuf, reps);
-        sweep_qdq<2, 2, 2>(n, nbuf, reps);
-        sweep_copy<1, 2, 0>(n, nbuf, reps); sweep_copy<2, 2, 0>(n, nbuf, reps); sweep_copy<4, 2, 0>(n, nbuf, reps);
-        sweep_copy<2, 1, 0>(n, nbuf, reps); sweep_copy<2, 2, 1>(n, nbuf, reps); sweep_copy<2, 0, 0>(n, nbuf, reps);
+        sweep_reduce<4, 0, true>(n, nbuf, reps); sweep_reduce<4, 0, false>(n, nbuf, reps);
+        sweep_reduce<2, 0, false>(n, nbuf, reps);
+        sweep_qdq<1, 2, 0>(n, nbuf, reps); sweep_qdq<2, 2, 0>(n, nbuf, reps); sweep_qdq<2, 2, 1>(n, nbuf, reps);
+        sweep_copy<1, 2, 0>(n, nbuf, reps); sweep_copy<2, 2, 0>(n, nbuf, reps); sweep_copy<2, 2, 1>(n, nbuf, reps);
+        for (int qbps : {8, 16, 32})
+            for (int rev : {0, 1}) {
+                sweep_pair<false>(n, nbuf, reps, 4, qbps, rev);
+                sweep_pair<true>(n, nbuf, reps, 4, qbps, rev);
+            }
+        sweep_pair<true>(n, nbuf, reps, 2, 16, 1); sweep_pair<true>(n, nbuf, reps, 8, 16, 1);
         g_x = bx; g_y = by;
     }
     fclose(g_out);

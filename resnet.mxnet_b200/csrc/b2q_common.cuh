@@ -16,7 +16,8 @@
 // order, applies the threshold update and resets the ticket, so a slot is reusable without a memset.
 struct b2q_slot {
     unsigned int ticket;
-    unsigned int pad[3];
+    unsigned int pad;
+    unsigned long long max64;     // (epoch << 32 | float bits) for the deferred max reduction: atomicMax, never reset
     float scale[B2Q_MAX_GROUPS];  // threshold T the following QDQ kernel scales with (when it is not aux)
     float clip[B2Q_MAX_GROUPS];   // threshold the following QDQ kernel clips with (when it differs)
     double partial[B2Q_MAX_PIECES];
@@ -42,9 +43,10 @@ struct b2q_ctx {
     int num_sms = 0;
     b2q_slot* slots = nullptr;      // device
     unsigned int next_slot = 0;
+    unsigned int slot_epoch[B2Q_NSLOTS] = {};   // per-slot use counter: tags deferred max reductions (b2q_slot::max64)
     long long launches = 0;
     // run-time knobs (never change results)
-    int blocks_per_sm = 16;          // flat QDQ / backward sweeps: grid = SMs x this (sweep: 16 best)
+    int blocks_per_sm = 64;          // flat QDQ / backward sweeps: grid = SMs x this (sweep: many short blocks win)
     int reduce_blocks_per_sm = 4;    // flat reductions
     int deferred = 1;                // consumer-side threshold update in the fused whole-tensor forward
     int reverse = 1;
@@ -237,13 +239,15 @@ __device__ __forceinline__ void apply_update(const UpdateArgs& u, int g, float s
     if (u.clip_out) u.clip_out[g] = fresh;
 }
 
-// Deferred ("consumer-side") threshold update for the fused whole-tensor forward: the reduction kernel only stores
-// its per-block partials and a snapshot of the old aux value; every block of the QDQ sweep that follows combines the
-// partials itself (same fixed order in every block => identical, deterministic result), derives the thresholds in
-// registers and block 0 writes the new aux.  This removes the serialized fence -> ticket -> last-block -> update
-// chain (~5 us, profiles/r01b_sweep.csv) from between the two kernels.
+// Deferred ("consumer-side") threshold update for the fused whole-tensor forward: the reduction kernel publishes only
+// its result (max: one atomicMax per block on an epoch-tagged 64-bit word, exact and order independent, no reset
+// needed because a newer epoch always wins; sums: per-block double partials combined by every consumer block in the
+// same fixed order) plus a snapshot of the old aux value.  The QDQ sweep that follows derives the thresholds in
+// registers and its block 0 writes the new aux.  This removes the serialized fence -> ticket -> last-block -> update
+// chain (~3 us per node, profiles/r01b_sweep.csv) from between the two kernels.
 struct DeferredUpdate {
-    const double* partial;   // [count_partials] written by reduce_flat_kernel<.., FINALIZE=false>
+    const double* partial;   // sums: [n_partials] written by reduce_flat_kernel<false, .., FINALIZE=false>
+    const unsigned long long* max64;   // max: epoch-tagged atomicMax word written by reduce_flat_kernel<true, ..>
     const float* aux_old;    // snapshot of aux[0] taken by the reduction kernel
     int n_partials;
     int is_max;

@@ -1,14 +1,18 @@
 // Host-buffer entry points: the call a framework makes when its tensors live in host memory
 // (bench.py's "e2e" leg).
 //
-// A three-stream software pipeline over a ring of device staging sets keeps both PCIe directions busy:
-//     h2d stream   : host x (and dy) -> set.a / set.b              continuous host-to-device traffic
+// A three-stream software pipeline keeps both PCIe directions busy:
+//     h2d stream   : host x (and dy) -> device staging             continuous host-to-device traffic
 //     compute strm : reduction + threshold update + QDQ sweep / backward mask on the staged tensors
-//     d2h stream   : set output -> host y / dx, aux -> host       continuous device-to-host traffic
-// Call k uses set k % B2Q_HOST_SETS; events chain h2d -> compute -> d2h within a set and d2h(k) -> h2d(k + SETS)
-// across reuses.  Every call returns after enqueueing; b2q_host_sync() waits for all of them.  Calls that touch the
-// same host aux array must be separated by b2q_host_sync().
+//     d2h stream   : staged output -> host y / dx, aux -> host      continuous device-to-host traffic
+// Staging memory is a byte-granular RING (not a fixed number of max-size slots): every call reserves exactly its
+// tensor's size, so many small tensors can be in flight while the D2H of a large one drains, and the h2d stream only
+// waits (stream-side, never the host) for the calls whose space it is about to overwrite.  Every call returns after
+// enqueueing; b2q_host_sync() waits for all of them.  Calls that touch the same host aux array must be separated by
+// b2q_host_sync().
 #include <cstring>
+#include <deque>
+#include <vector>
 
 #include "b2q_common.cuh"
 
@@ -16,26 +20,43 @@
     B2Q_REQUIRE((ctx) != nullptr, "null context"); \
     B2Q_CHECK_CUDA(cudaSetDevice((ctx)->device))
 
-#define B2Q_HOST_SETS 4
+#define B2Q_HOST_AUX_SLOTS 64
+#define B2Q_HOST_MIN_RING (256ll << 20)   // elements: 1 GiB per staging buffer at least
 
-struct HostStage {
-    float* a = nullptr;      // staged input
-    float* b = nullptr;      // staged second input (dy) or output
-    float* c = nullptr;      // output of two-input ops
-    float* aux = nullptr;    // device mirror of the aux vector
-    cudaEvent_t h2d_done = nullptr, comp_done = nullptr, d2h_done = nullptr;
-    bool used = false;
+struct HostSeg {
+    size_t off, len;       // elements
+    cudaEvent_t done;      // recorded on the d2h stream after the call's last copy-out
+};
+
+struct HostStage {         // what one call works on
+    float* a;
+    float* b;
+    float* c;
+    float* aux;
+    cudaEvent_t h2d_done, comp_done, d2h_done;
 };
 
 struct HostState {
-    HostStage set[B2Q_HOST_SETS];
-    size_t cap = 0;          // elements per staging buffer
-    bool have_c = false;
-    unsigned next = 0;
+    float* a = nullptr;    // ring: staged inputs
+    float* b = nullptr;    // ring: second input (dy) or output
+    float* c = nullptr;    // ring: output of two-input ops (allocated on first use)
+    size_t cap = 0, head = 0;
+    std::deque<HostSeg> inflight;
+    std::vector<cudaEvent_t> events;       // recycled
+    float* aux = nullptr;                  // B2Q_HOST_AUX_SLOTS x B2Q_MAX_GROUPS
+    cudaEvent_t aux_done[B2Q_HOST_AUX_SLOTS] = {};
+    bool aux_used[B2Q_HOST_AUX_SLOTS] = {};
+    unsigned calls = 0;
     cudaStream_t h2d = nullptr, comp = nullptr, d2h = nullptr;
 };
 
 static HostState* host_state(b2q_ctx* ctx) { return reinterpret_cast<HostState*>(ctx->host_state); }
+
+static int new_event(HostState* hs, cudaEvent_t* e) {
+    if (!hs->events.empty()) { *e = hs->events.back(); hs->events.pop_back(); return 0; }
+    B2Q_CHECK_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    return 0;
+}
 
 static int host_init(b2q_ctx* ctx) {
     if (ctx->host_state) return 0;
@@ -44,12 +65,9 @@ static int host_init(b2q_ctx* ctx) {
     B2Q_CHECK_CUDA(cudaStreamCreateWithFlags(&hs->h2d, cudaStreamNonBlocking));
     B2Q_CHECK_CUDA(cudaStreamCreateWithFlags(&hs->comp, cudaStreamNonBlocking));
     B2Q_CHECK_CUDA(cudaStreamCreateWithFlags(&hs->d2h, cudaStreamNonBlocking));
-    for (HostStage& s : hs->set) {
-        B2Q_CHECK_CUDA(cudaMalloc(&s.aux, sizeof(float) * B2Q_MAX_GROUPS));
-        B2Q_CHECK_CUDA(cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
-        B2Q_CHECK_CUDA(cudaEventCreateWithFlags(&s.comp_done, cudaEventDisableTiming));
-        B2Q_CHECK_CUDA(cudaEventCreateWithFlags(&s.d2h_done, cudaEventDisableTiming));
-    }
+    B2Q_CHECK_CUDA(cudaMalloc(&hs->aux, sizeof(float) * B2Q_MAX_GROUPS * B2Q_HOST_AUX_SLOTS));
+    for (int i = 0; i < B2Q_HOST_AUX_SLOTS; ++i)
+        B2Q_CHECK_CUDA(cudaEventCreateWithFlags(&hs->aux_done[i], cudaEventDisableTiming));
     return 0;
 }
 
@@ -57,35 +75,80 @@ static int host_sync_all(HostState* hs) {
     B2Q_CHECK_CUDA(cudaStreamSynchronize(hs->h2d));
     B2Q_CHECK_CUDA(cudaStreamSynchronize(hs->comp));
     B2Q_CHECK_CUDA(cudaStreamSynchronize(hs->d2h));
+    for (HostSeg& s : hs->inflight) hs->events.push_back(s.done);
+    hs->inflight.clear();
+    hs->head = 0;
     return 0;
 }
 
-// Next staging set with room for n elements (and a third buffer if need_c); the h2d stream is made to wait until the
-// set's previous occupant has been copied out.
-static int take_stage(b2q_ctx* ctx, int64_t n, bool need_c, HostStage** out) {
+// Reserve n elements of every ring buffer for one call; the h2d stream waits for the calls being overwritten.
+static int take_stage(b2q_ctx* ctx, int64_t n64, bool need_c, HostStage* out) {
     int rc = host_init(ctx);
     if (rc) return rc;
     HostState* hs = host_state(ctx);
-    if ((size_t)n > hs->cap || (need_c && !hs->have_c)) {
+    const size_t n = ((size_t)n64 + 63) & ~(size_t)63;   // 256-byte granules keep every segment 256-bit aligned
+    if (3 * n > hs->cap || (need_c && !hs->c)) {
         rc = host_sync_all(hs);
         if (rc) return rc;
-        size_t cap = (size_t)n > hs->cap ? (size_t)n : hs->cap;
-        for (HostStage& s : hs->set) {
-            if (cap > hs->cap) {
-                cudaFree(s.a); cudaFree(s.b); cudaFree(s.c);
-                s.a = s.b = s.c = nullptr;
-                B2Q_CHECK_CUDA(cudaMalloc(&s.a, sizeof(float) * cap));
-                B2Q_CHECK_CUDA(cudaMalloc(&s.b, sizeof(float) * cap));
-            }
-            if ((need_c || hs->have_c) && !s.c) B2Q_CHECK_CUDA(cudaMalloc(&s.c, sizeof(float) * cap));
+        size_t cap = hs->cap;
+        if (3 * n > cap) cap = 3 * n;
+        if (cap < (size_t)B2Q_HOST_MIN_RING) cap = (size_t)B2Q_HOST_MIN_RING;
+        if (cap != hs->cap) {
+            cudaFree(hs->a); cudaFree(hs->b); cudaFree(hs->c);
+            hs->a = hs->b = hs->c = nullptr;
+            B2Q_CHECK_CUDA(cudaMalloc(&hs->a, sizeof(float) * cap));
+            B2Q_CHECK_CUDA(cudaMalloc(&hs->b, sizeof(float) * cap));
+            hs->cap = cap;
         }
-        hs->cap = cap;
-        hs->have_c = hs->have_c || need_c;
+        if (need_c && !hs->c) B2Q_CHECK_CUDA(cudaMalloc(&hs->c, sizeof(float) * hs->cap));
     }
-    HostStage& s = hs->set[hs->next++ % B2Q_HOST_SETS];
-    if (s.used) B2Q_CHECK_CUDA(cudaStreamWaitEvent(hs->h2d, s.d2h_done, 0));
-    s.used = true;
-    *out = &s;
+    if (hs->head + n > hs->cap) {   // wrap: whatever still lives in [head, cap) must drain first
+        while (!hs->inflight.empty() && hs->inflight.front().off >= hs->head) {
+            B2Q_CHECK_CUDA(cudaStreamWaitEvent(hs->h2d, hs->inflight.front().done, 0));
+            hs->events.push_back(hs->inflight.front().done);
+            hs->inflight.pop_front();
+        }
+        hs->head = 0;
+    }
+    const size_t lo = hs->head, hi = hs->head + n;
+    while (!hs->inflight.empty()) {
+        const HostSeg& f = hs->inflight.front();
+        if (f.off >= hi || f.off + f.len <= lo) break;   // oldest live segment does not overlap: nothing else can
+        B2Q_CHECK_CUDA(cudaStreamWaitEvent(hs->h2d, f.done, 0));
+        hs->events.push_back(f.done);
+        hs->inflight.pop_front();
+    }
+    HostSeg seg;
+    seg.off = lo;
+    seg.len = n;
+    rc = new_event(hs, &seg.done);
+    if (rc) return rc;
+    hs->inflight.push_back(seg);
+    hs->head = hi;
+    const unsigned slot = hs->calls++ % B2Q_HOST_AUX_SLOTS;
+    if (hs->aux_used[slot]) B2Q_CHECK_CUDA(cudaStreamWaitEvent(hs->h2d, hs->aux_done[slot], 0));
+    hs->aux_used[slot] = true;
+    out->a = hs->a + lo;
+    out->b = hs->b + lo;
+    out->c = hs->c ? hs->c + lo : nullptr;
+    out->aux = hs->aux + (size_t)slot * B2Q_MAX_GROUPS;
+    out->d2h_done = seg.done;
+    out->comp_done = hs->aux_done[slot];   // doubles as the aux slot's release marker (recorded last, on d2h)
+    rc = new_event(hs, &out->h2d_done);
+    return rc;
+}
+
+// h2d -> compute dependency, returns the event to the pool (a recorded-and-waited event may be reused at once)
+static int chain(HostState* hs, cudaEvent_t e, cudaStream_t from, cudaStream_t to) {
+    B2Q_CHECK_CUDA(cudaEventRecord(e, from));
+    B2Q_CHECK_CUDA(cudaStreamWaitEvent(to, e, 0));
+    return 0;
+}
+
+static int finish(HostState* hs, HostStage& s) {
+    B2Q_CHECK_CUDA(cudaEventRecord(s.d2h_done, hs->d2h));
+    B2Q_CHECK_CUDA(cudaEventRecord(s.comp_done, hs->d2h));
+    hs->events.push_back(s.h2d_done);
     return 0;
 }
 
@@ -95,12 +158,10 @@ int b2q_host_release(b2q_ctx* ctx) {
     if (hs->h2d) { cudaStreamSynchronize(hs->h2d); cudaStreamDestroy(hs->h2d); }
     if (hs->comp) { cudaStreamSynchronize(hs->comp); cudaStreamDestroy(hs->comp); }
     if (hs->d2h) { cudaStreamSynchronize(hs->d2h); cudaStreamDestroy(hs->d2h); }
-    for (HostStage& s : hs->set) {
-        cudaFree(s.a); cudaFree(s.b); cudaFree(s.c); cudaFree(s.aux);
-        if (s.h2d_done) cudaEventDestroy(s.h2d_done);
-        if (s.comp_done) cudaEventDestroy(s.comp_done);
-        if (s.d2h_done) cudaEventDestroy(s.d2h_done);
-    }
+    cudaFree(hs->a); cudaFree(hs->b); cudaFree(hs->c); cudaFree(hs->aux);
+    for (HostSeg& s : hs->inflight) cudaEventDestroy(s.done);
+    for (cudaEvent_t e : hs->events) cudaEventDestroy(e);
+    for (cudaEvent_t e : hs->aux_done) if (e) cudaEventDestroy(e);
     delete hs;
     ctx->host_state = nullptr;
     return 0;
@@ -122,64 +183,64 @@ int b2q_minmax_quant_fwd_host_f32(b2q_ctx* ctx, int variant, const float* host_x
     const int64_t n = rows * cols;
     const int64_t naux = (per_channel && is_weight) ? rows : 1;
     B2Q_REQUIRE(naux <= B2Q_MAX_GROUPS, "too many channels");
-    HostStage* s;
+    HostStage s;
     int rc = take_stage(ctx, n, false, &s);
     if (rc) return rc;
     HostState* hs = host_state(ctx);
-    B2Q_CHECK_CUDA(cudaMemcpyAsync(s->aux, host_aux, sizeof(float) * naux, cudaMemcpyHostToDevice, hs->h2d));
-    B2Q_CHECK_CUDA(cudaMemcpyAsync(s->a, host_x, sizeof(float) * n, cudaMemcpyHostToDevice, hs->h2d));
-    B2Q_CHECK_CUDA(cudaEventRecord(s->h2d_done, hs->h2d));
-    B2Q_CHECK_CUDA(cudaStreamWaitEvent(hs->comp, s->h2d_done, 0));
-    rc = b2q_minmax_quant_fwd_f32(ctx, variant, s->a, s->b, s->aux, rows, cols, is_weight, per_channel, is_train, init,
+    B2Q_CHECK_CUDA(cudaMemcpyAsync(s.aux, host_aux, sizeof(float) * naux, cudaMemcpyHostToDevice, hs->h2d));
+    B2Q_CHECK_CUDA(cudaMemcpyAsync(s.a, host_x, sizeof(float) * n, cudaMemcpyHostToDevice, hs->h2d));
+    if ((rc = chain(hs, s.h2d_done, hs->h2d, hs->comp))) return rc;
+    rc = b2q_minmax_quant_fwd_f32(ctx, variant, s.a, s.b, s.aux, rows, cols, is_weight, per_channel, is_train, init,
                                   ema_decay, one_minus_decay, B2Q_REQ_WRITE, hs->comp);
     if (rc) return rc;
-    B2Q_CHECK_CUDA(cudaEventRecord(s->comp_done, hs->comp));
-    B2Q_CHECK_CUDA(cudaStreamWaitEvent(hs->d2h, s->comp_done, 0));
-    B2Q_CHECK_CUDA(cudaMemcpyAsync(host_y, s->b, sizeof(float) * n, cudaMemcpyDeviceToHost, hs->d2h));
-    B2Q_CHECK_CUDA(cudaMemcpyAsync(host_aux, s->aux, sizeof(float) * naux, cudaMemcpyDeviceToHost, hs->d2h));
-    B2Q_CHECK_CUDA(cudaEventRecord(s->d2h_done, hs->d2h));
-    return 0;
+    cudaEvent_t e;
+    if ((rc = new_event(hs, &e))) return rc;
+    if ((rc = chain(hs, e, hs->comp, hs->d2h))) return rc;
+    hs->events.push_back(e);
+    B2Q_CHECK_CUDA(cudaMemcpyAsync(host_y, s.b, sizeof(float) * n, cudaMemcpyDeviceToHost, hs->d2h));
+    B2Q_CHECK_CUDA(cudaMemcpyAsync(host_aux, s.aux, sizeof(float) * naux, cudaMemcpyDeviceToHost, hs->d2h));
+    return finish(hs, s);
 }
 
 int b2q_ste_bwd_host_f32(b2q_ctx* ctx, const float* host_dy, float* host_dx, int64_t n) {
     B2Q_CTX(ctx);
     B2Q_REQUIRE(host_dy && host_dx && n >= 1, "bad argument");
-    HostStage* s;
+    HostStage s;
     int rc = take_stage(ctx, n, false, &s);
     if (rc) return rc;
     HostState* hs = host_state(ctx);
-    B2Q_CHECK_CUDA(cudaMemcpyAsync(s->a, host_dy, sizeof(float) * n, cudaMemcpyHostToDevice, hs->h2d));
-    B2Q_CHECK_CUDA(cudaEventRecord(s->h2d_done, hs->h2d));
-    B2Q_CHECK_CUDA(cudaStreamWaitEvent(hs->comp, s->h2d_done, 0));
-    rc = b2q_ste_bwd_f32(ctx, s->a, s->b, n, B2Q_REQ_WRITE, hs->comp);
+    B2Q_CHECK_CUDA(cudaMemcpyAsync(s.a, host_dy, sizeof(float) * n, cudaMemcpyHostToDevice, hs->h2d));
+    if ((rc = chain(hs, s.h2d_done, hs->h2d, hs->comp))) return rc;
+    rc = b2q_ste_bwd_f32(ctx, s.a, s.b, n, B2Q_REQ_WRITE, hs->comp);
     if (rc) return rc;
-    B2Q_CHECK_CUDA(cudaEventRecord(s->comp_done, hs->comp));
-    B2Q_CHECK_CUDA(cudaStreamWaitEvent(hs->d2h, s->comp_done, 0));
-    B2Q_CHECK_CUDA(cudaMemcpyAsync(host_dx, s->b, sizeof(float) * n, cudaMemcpyDeviceToHost, hs->d2h));
-    B2Q_CHECK_CUDA(cudaEventRecord(s->d2h_done, hs->d2h));
-    return 0;
+    cudaEvent_t e;
+    if ((rc = new_event(hs, &e))) return rc;
+    if ((rc = chain(hs, e, hs->comp, hs->d2h))) return rc;
+    hs->events.push_back(e);
+    B2Q_CHECK_CUDA(cudaMemcpyAsync(host_dx, s.b, sizeof(float) * n, cudaMemcpyDeviceToHost, hs->d2h));
+    return finish(hs, s);
 }
 
 int b2q_clipgrad_bwd_host_f32(b2q_ctx* ctx, const float* host_x, const float* host_dy, float* host_dx,
                               const float* host_aux, int64_t n) {
     B2Q_CTX(ctx);
     B2Q_REQUIRE(host_x && host_dy && host_dx && host_aux && n >= 1, "bad argument");
-    HostStage* s;
+    HostStage s;
     int rc = take_stage(ctx, n, true, &s);
     if (rc) return rc;
     HostState* hs = host_state(ctx);
-    B2Q_CHECK_CUDA(cudaMemcpyAsync(s->aux, host_aux, sizeof(float), cudaMemcpyHostToDevice, hs->h2d));
-    B2Q_CHECK_CUDA(cudaMemcpyAsync(s->a, host_x, sizeof(float) * n, cudaMemcpyHostToDevice, hs->h2d));
-    B2Q_CHECK_CUDA(cudaMemcpyAsync(s->b, host_dy, sizeof(float) * n, cudaMemcpyHostToDevice, hs->h2d));
-    B2Q_CHECK_CUDA(cudaEventRecord(s->h2d_done, hs->h2d));
-    B2Q_CHECK_CUDA(cudaStreamWaitEvent(hs->comp, s->h2d_done, 0));
-    rc = b2q_clipgrad_bwd_f32(ctx, s->a, s->b, s->c, s->aux, n, hs->comp);
+    B2Q_CHECK_CUDA(cudaMemcpyAsync(s.aux, host_aux, sizeof(float), cudaMemcpyHostToDevice, hs->h2d));
+    B2Q_CHECK_CUDA(cudaMemcpyAsync(s.a, host_x, sizeof(float) * n, cudaMemcpyHostToDevice, hs->h2d));
+    B2Q_CHECK_CUDA(cudaMemcpyAsync(s.b, host_dy, sizeof(float) * n, cudaMemcpyHostToDevice, hs->h2d));
+    if ((rc = chain(hs, s.h2d_done, hs->h2d, hs->comp))) return rc;
+    rc = b2q_clipgrad_bwd_f32(ctx, s.a, s.b, s.c, s.aux, n, hs->comp);
     if (rc) return rc;
-    B2Q_CHECK_CUDA(cudaEventRecord(s->comp_done, hs->comp));
-    B2Q_CHECK_CUDA(cudaStreamWaitEvent(hs->d2h, s->comp_done, 0));
-    B2Q_CHECK_CUDA(cudaMemcpyAsync(host_dx, s->c, sizeof(float) * n, cudaMemcpyDeviceToHost, hs->d2h));
-    B2Q_CHECK_CUDA(cudaEventRecord(s->d2h_done, hs->d2h));
-    return 0;
+    cudaEvent_t e;
+    if ((rc = new_event(hs, &e))) return rc;
+    if ((rc = chain(hs, e, hs->comp, hs->d2h))) return rc;
+    hs->events.push_back(e);
+    B2Q_CHECK_CUDA(cudaMemcpyAsync(host_dx, s.c, sizeof(float) * n, cudaMemcpyDeviceToHost, hs->d2h));
+    return finish(hs, s);
 }
 
 }  // extern "C"

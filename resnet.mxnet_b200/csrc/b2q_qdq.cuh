@@ -13,6 +13,9 @@
 #ifndef B2Q_QDQ_STPOL
 #define B2Q_QDQ_STPOL 0   // y: plain store -- the convolution reads it next, let it live in L2
 #endif
+#ifndef B2Q_STREAM_BYTES
+#define B2Q_STREAM_BYTES (96ll << 20)   // outputs larger than this cannot stay in L2 anyway: store them evict_first
+#endif
 #ifndef B2Q_BWD_UNROLL
 #define B2Q_BWD_UNROLL 2
 #endif
@@ -131,29 +134,28 @@ qdq_flat_hot_kernel(const float* __restrict__ x, float* __restrict__ y, FlatSpli
                     DeferredUpdate d, int clip_with_fresh) {
     float T, Tc;
     if (DEFERRED) {
-        // combine the reduction's partials (every block, same fixed order), derive thresholds in registers
-        __shared__ double smem[32];
-        __shared__ float s_thr[2];
-        double acc = 0.0;
-        float m = 0.f;
-        for (int i = threadIdx.x; i < d.n_partials; i += blockDim.x) {
-            const double p = d.partial[i];
-            if (d.is_max) m = fmaxf(m, (float)p); else acc += p;
+        float stat;
+        if (d.is_max) {
+            // one epoch-tagged word, read by every thread (broadcast L2 hit): no shared memory, no barrier
+            stat = __uint_as_float((unsigned int)(*d.max64 & 0xffffffffull));
+        } else {
+            // sums: every block combines the double partials in the same fixed order
+            __shared__ double smem[32];
+            __shared__ float s_stat;
+            double acc = 0.0;
+            for (int i = threadIdx.x; i < d.n_partials; i += blockDim.x) acc += d.partial[i];
+            const double tot = block_reduce<false>(acc, smem);
+            if (threadIdx.x == 0) s_stat = __fdiv_rn((float)tot, d.count);
+            __syncthreads();
+            stat = s_stat;
         }
-        const double tot = d.is_max ? block_reduce<true>((double)m, smem) : block_reduce<false>(acc, smem);
-        if (threadIdx.x == 0) {
-            const float stat = d.is_max ? (float)tot : __fdiv_rn((float)tot, d.count);
-            const float a_old = d.u.aux ? d.aux_old[0] : 0.f;
-            float fresh, next;
-            compute_update(d.u.mode, d.u.p0, d.u.p1, a_old, stat, fresh, next);
-            const float after = d.u.write_aux ? next : a_old;
-            s_thr[0] = d.u.use_aux_as_scale ? after : fresh;
-            s_thr[1] = clip_with_fresh ? fresh : s_thr[0];
-            if (blockIdx.x == 0 && d.u.write_aux && d.u.aux) d.u.aux[0] = next;
-        }
-        __syncthreads();
-        T = s_thr[0];
-        Tc = s_thr[1];
+        const float a_old = d.u.aux ? d.aux_old[0] : 0.f;
+        float fresh, next;
+        compute_update(d.u.mode, d.u.p0, d.u.p1, a_old, stat, fresh, next);
+        const float after = d.u.write_aux ? next : a_old;
+        T = d.u.use_aux_as_scale ? after : fresh;
+        Tc = clip_with_fresh ? fresh : T;
+        if (blockIdx.x == 0 && threadIdx.x == 0 && d.u.write_aux && d.u.aux) d.u.aux[0] = next;
     } else {
         T = a.thr ? __ldg(a.thr) : a.thr_imm;
         Tc = a.clip_thr ? __ldg(a.clip_thr) : (a.thr ? T : a.clip_imm);
@@ -414,12 +416,12 @@ static inline bool same_misalignment(const void* a, const void* b) {
             if (hot) {
                 const int64_t grid = b2q_flat_grid(ctx, sp.n8, B2Q_QDQ_UNROLL);
                 DeferredUpdate none = {};
-                if (a.clip_mode == B2Q_CLIP_SYM)
-                    qdq_flat_hot_kernel<true, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, B2Q_QDQ_STPOL, false>
-                        <<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, y, sp, a, ctx->reverse, none, 0);
-                else
-                    qdq_flat_hot_kernel<false, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, B2Q_QDQ_STPOL, false>
-                        <<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, y, sp, a, ctx->reverse, none, 0);
+                const bool stream_out = n * 4 > B2Q_STREAM_BYTES;
+#define B2Q_HOT(C, S) qdq_flat_hot_kernel<C, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, S, false> \
+                          <<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, y, sp, a, ctx->reverse, none, 0)
+                if (a.clip_mode == B2Q_CLIP_SYM) { if (stream_out) B2Q_HOT(true, 1); else B2Q_HOT(true, B2Q_QDQ_STPOL); }
+                else { if (stream_out) B2Q_HOT(false, 1); else B2Q_HOT(false, B2Q_QDQ_STPOL); }
+#undef B2Q_HOT
             } else {
                 const int64_t grid = b2q_flat_grid(ctx, sp.n8, 2);
                 qdq_flat_generic_kernel<2><<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, y, sp, a);
@@ -451,10 +453,12 @@ template <bool IS_MAX>
     FlatSplit sp = b2q_flat_split(x, n);
     if (!same_misalignment(x, y) || sp.head > B2Q_THREADS) return 0;
     int np = 0;
-    int rc = launch_reduce_deferred<IS_MAX>(ctx, slot, x, n, u, st, &np);
+    unsigned int epoch = 0;
+    int rc = launch_reduce_deferred<IS_MAX>(ctx, slot, x, n, u, st, &np, &epoch);
     if (rc || np == 0) return rc;
     DeferredUpdate d;
     d.partial = slot->partial;
+    d.max64 = &slot->max64;
     d.aux_old = slot->scale;
     d.n_partials = np;
     d.is_max = IS_MAX ? 1 : 0;
@@ -464,12 +468,12 @@ template <bool IS_MAX>
     const int64_t grid = b2q_flat_grid(ctx, sp.n8, B2Q_QDQ_UNROLL);
     {
         b2q_timed_launch tl(ctx, B2Q_KIND_QDQ_HOT, 8.0 * (double)n, st);
-        if (clip_mode == B2Q_CLIP_SYM)
-            qdq_flat_hot_kernel<true, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, B2Q_QDQ_STPOL, true>
-                <<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, y, sp, a, ctx->reverse, d, clip_with_fresh);
-        else
-            qdq_flat_hot_kernel<false, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, B2Q_QDQ_STPOL, true>
-                <<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, y, sp, a, ctx->reverse, d, clip_with_fresh);
+        const bool stream_out = n * 4 > B2Q_STREAM_BYTES;
+#define B2Q_HOT(C, S) qdq_flat_hot_kernel<C, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, S, true> \
+                          <<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, y, sp, a, ctx->reverse, d, clip_with_fresh)
+        if (clip_mode == B2Q_CLIP_SYM) { if (stream_out) B2Q_HOT(true, 1); else B2Q_HOT(true, B2Q_QDQ_STPOL); }
+        else { if (stream_out) B2Q_HOT(false, 1); else B2Q_HOT(false, B2Q_QDQ_STPOL); }
+#undef B2Q_HOT
         B2Q_LAUNCH_CHECK(ctx);
     }
     *done = 1;
@@ -487,7 +491,10 @@ static int launch_bwd_mask(b2q_ctx* ctx, const float* x, const float* dy, float*
         if (ok && sp.head <= B2Q_THREADS) {
             const int64_t grid = b2q_flat_grid(ctx, sp.n8, B2Q_BWD_UNROLL);
             b2q_timed_launch tl(ctx, MASK == 0 ? B2Q_KIND_BWD_STE : B2Q_KIND_BWD_MASK, (MASK == 0 ? 8.0 : 12.0) * (double)n, st);
+            const bool stream_out = n * 4 > B2Q_STREAM_BYTES;
             if (add) bwd_flat_kernel<MASK, true, B2Q_BWD_UNROLL, B2Q_BWD_LDPOL, B2Q_BWD_STPOL>
+                    <<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, dy, dx, sp, thr, thr_imm);
+            else if (stream_out) bwd_flat_kernel<MASK, false, B2Q_BWD_UNROLL, B2Q_BWD_LDPOL, 1>
                     <<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, dy, dx, sp, thr, thr_imm);
             else bwd_flat_kernel<MASK, false, B2Q_BWD_UNROLL, B2Q_BWD_LDPOL, B2Q_BWD_STPOL>
                     <<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, dy, dx, sp, thr, thr_imm);

@@ -28,6 +28,7 @@ static std::vector<float*> g_x, g_y;
 static b2q_slot* g_slot;
 static float* g_thr;
 static FILE* g_out;
+static unsigned int g_epoch = 0;
 
 template <class F>
 static float time_launches(F launch, int reps) {
@@ -55,7 +56,7 @@ static void report(const char* kernel, int64_t n, int unroll, int ldpol, int stp
 
 template <int U, int L, bool FIN>
 static void sweep_reduce(int64_t n, int nbuf, int reps) {
-    for (int bps : {2, 3, 4, 6, 8}) {
+    for (int bps : {3, 4, 8, 16, 32}) {
         UpdateArgs u = {};
         u.mode = B2Q_UPD_EMA; u.write_aux = 1; u.use_aux_as_scale = 1; u.p0 = 0.99f; u.p1 = 0.01f; u.aux = g_thr;
         float ms = time_launches([&](int i) {
@@ -63,7 +64,7 @@ static void sweep_reduce(int64_t n, int nbuf, int reps) {
             FlatSplit sp = b2q_flat_split(x, n);
             const int64_t tile = (int64_t)B2Q_THREADS * U;
             int64_t grid = std::min<int64_t>((sp.n8 + tile - 1) / tile, (int64_t)g_sms * bps);
-            reduce_flat_kernel<true, U, L, FIN><<<(unsigned)grid, B2Q_THREADS>>>(x, sp, g_slot, u, (float)n);
+            reduce_flat_kernel<true, U, L, FIN><<<(unsigned)grid, B2Q_THREADS>>>(x, sp, g_slot, u, (float)n, ++g_epoch);
         }, reps);
         report(FIN ? "reduce" : "reduce_nofin", n, U, L, 0, bps, 4.0, ms);
     }
@@ -71,7 +72,7 @@ static void sweep_reduce(int64_t n, int nbuf, int reps) {
 
 template <int U, int L, int S>
 static void sweep_qdq(int64_t n, int nbuf, int reps) {
-    for (int bps : {4, 5, 8, 16, 24, 32, 64}) {
+    for (int bps : {8, 16, 32, 64, 128, 256, 100000}) {
         QdqArgs a = {g_thr, nullptr, 0.f, 0.f, 127.f, 1, nullptr, B2Q_CLIP_SYM, 1, B2Q_REQ_WRITE};
         DeferredUpdate none = {};
         float ms = time_launches([&](int i) {
@@ -100,14 +101,14 @@ static void sweep_pair(int64_t n, int nbuf, int reps, int rbps, int qbps, int re
         int64_t qgrid = std::min<int64_t>((sp.n8 + B2Q_THREADS * 2 - 1) / (B2Q_THREADS * 2), (int64_t)g_sms * qbps);
         QdqArgs a = {g_thr, nullptr, 0.f, 0.f, 127.f, 1, nullptr, B2Q_CLIP_SYM, 1, B2Q_REQ_WRITE};
         if (DEFER) {
-            reduce_flat_kernel<true, 4, 0, false><<<(unsigned)rgrid, B2Q_THREADS>>>(x, sp, g_slot, u, (float)n);
+            reduce_flat_kernel<true, 4, 0, false><<<(unsigned)rgrid, B2Q_THREADS>>>(x, sp, g_slot, u, (float)n, ++g_epoch);
             DeferredUpdate d;
-            d.partial = g_slot->partial; d.aux_old = g_slot->scale; d.n_partials = (int)rgrid; d.is_max = 1;
+            d.partial = g_slot->partial; d.max64 = &g_slot->max64; d.aux_old = g_slot->scale; d.n_partials = (int)rgrid; d.is_max = 1;
             d.count = (float)n; d.u = u;
             qdq_flat_hot_kernel<true, 2, 2, 0, true><<<(unsigned)qgrid, B2Q_THREADS>>>(x, y, sp, a, reverse, d, 0);
         } else {
             DeferredUpdate none = {};
-            reduce_flat_kernel<true, 4, 0, true><<<(unsigned)rgrid, B2Q_THREADS>>>(x, sp, g_slot, u, (float)n);
+            reduce_flat_kernel<true, 4, 0, true><<<(unsigned)rgrid, B2Q_THREADS>>>(x, sp, g_slot, u, (float)n, 0u);
             qdq_flat_hot_kernel<true, 2, 2, 0, false><<<(unsigned)qgrid, B2Q_THREADS>>>(x, y, sp, a, reverse, none, 0);
         }
     }, reps);
@@ -118,7 +119,7 @@ static void sweep_pair(int64_t n, int nbuf, int reps, int rbps, int qbps, int re
 
 template <int U, int L, int S>
 static void sweep_copy(int64_t n, int nbuf, int reps) {
-    for (int bps : {4, 5, 8, 16, 24, 32, 64}) {
+    for (int bps : {8, 16, 32, 64, 128, 256, 100000}) {
         float ms = time_launches([&](int i) {
             const float* x = g_x[i % nbuf];
             float* y = g_y[i % nbuf];
@@ -168,12 +169,12 @@ int main(int argc, char** argv) {
         sweep_reduce<2, 0, false>(n, nbuf, reps);
         sweep_qdq<1, 2, 0>(n, nbuf, reps); sweep_qdq<2, 2, 0>(n, nbuf, reps); sweep_qdq<2, 2, 1>(n, nbuf, reps);
         sweep_copy<1, 2, 0>(n, nbuf, reps); sweep_copy<2, 2, 0>(n, nbuf, reps); sweep_copy<2, 2, 1>(n, nbuf, reps);
-        for (int qbps : {8, 16, 32})
+        for (int qbps : {16, 64, 256})
             for (int rev : {0, 1}) {
                 sweep_pair<false>(n, nbuf, reps, 4, qbps, rev);
                 sweep_pair<true>(n, nbuf, reps, 4, qbps, rev);
             }
-        sweep_pair<true>(n, nbuf, reps, 2, 16, 1); sweep_pair<true>(n, nbuf, reps, 8, 16, 1);
+        sweep_pair<true>(n, nbuf, reps, 8, 64, 1); sweep_pair<true>(n, nbuf, reps, 16, 64, 1);
         g_x = bx; g_y = by;
     }
     fclose(g_out);

@@ -284,8 +284,17 @@ def main():
     nodes = build_nodes(torch, node_list, "Quantization_int8_V2", device, seed=5 + rank)
 
     bucket = None
-    if world > 1:   # data parallel: thresholds allreduce(max) per activation node, weight grads allreduce(sum)
+    exchange = "none"
+    if world > 1:   # data parallel: thresholds max over ranks per activation node, weight grads allreduce(sum)
+        exchange = "nccl allreduce(max) per activation node"
         attach_threshold_sync([nd["op"] for nd in nodes])
+        if os.environ.get("B2Q_EXCHANGE", "peer") == "peer":
+            try:   # fused peer-memory exchange (NVLink): no NCCL call on the forward critical path
+                from b200quant.dist import attach_peer_exchange
+                attach_peer_exchange([nd["op"] for nd in nodes], device)
+                exchange = "fused peer-memory kernels (b2q_peer_minmax_quant_fwd_f32)"
+            except Exception as e:  # pragma: no cover
+                exchange += " (peer path unavailable: %s)" % (str(e).splitlines()[0][:100],)
         wn = [nd for nd in nodes if nd["kind"] == "weight"]
         bucket = GradBucket([nd["shape"] for nd in wn], device)
         for nd, view in zip(wn, bucket.views):
@@ -410,7 +419,7 @@ def main():
                                    "per-GPU batch %d" % (args.workload, len(nodes), sm["act_nodes"], sm["weight_nodes"],
                                                          batch),
                        "elements_per_step": total_elems, "alg_bytes_per_step": 20 * total_elems,
-                       "parallelism": "dp%d" % world, "l2": "inputs larger than L2 (10.9 GB touched once per step)",
+                       "parallelism": "dp%d" % world, "threshold_exchange": exchange, "l2": "inputs larger than L2 (10.9 GB touched once per step)",
                        "mode": mode},
             "ms_per_step_by_mode": timings,
             "hbm_frac_whole_step": 20.0 * total_elems / (ms / args.steps / 1e3) / 1e9 / peak_gbs,

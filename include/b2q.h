@@ -209,6 +209,26 @@ int b2q_multi_plan_destroy(b2q_ctx* ctx, b2q_multi_plan* plan);
 int b2q_multi_weight_quant_fwd_f32(b2q_ctx* ctx, b2q_multi_plan* plan, int variant, int is_train, void* stream);
 int b2q_multi_weight_ste_bwd_f32(b2q_ctx* ctx, b2q_multi_plan* plan, void* stream);
 
+/* ---- cross-rank threshold exchange over peer memory (NVLink / NVSwitch), fused into the forward kernels ----
+ * Data-parallel training needs allreduce(max) of every activation node's statistic before its threshold update
+ * (BASELINE.json north_star).  Instead of reduce kernel -> ncclAllReduce(4 bytes) -> update kernel -> QDQ kernel,
+ * b2q_peer_minmax_quant_fwd_f32 runs two kernels: the reduction's last block stores (sequence, max|x|) into every
+ * rank's mailbox with 8-byte P2P stores, and the QDQ sweep polls its own mailbox until all `world` entries of that
+ * sequence number are present, takes their max, applies the EMA / first-batch update in registers and sweeps.
+ * Semantics = Quantization_int8 / ClipGrad_Quantization_int8 activation forward in training mode
+ * (symbol/quant_ops.py:32-40, symbol/clip_grad_quantization_int8.py:37-51) with max|x| taken over all ranks.
+ * mailboxes[r] = rank r's mailbox as mapped on THIS device (own: b2q_peer_mailbox_create; peers: the 64-byte CUDA
+ * IPC handle exchanged out of band and opened with b2q_peer_mailbox_open).  All ranks must issue the same sequence
+ * of calls with sequence = 1, 2, 3, ...; a peer that never arrives makes the kernel trap after ~2 s.            */
+int b2q_peer_mailbox_bytes(void);
+int b2q_peer_mailbox_create(b2q_ctx* ctx, void** mailbox, void* ipc_handle_out /* 64 bytes */);
+int b2q_peer_mailbox_open(b2q_ctx* ctx, const void* ipc_handle /* 64 bytes */, void** peer_ptr);
+int b2q_peer_mailbox_close(b2q_ctx* ctx, void* peer_ptr);
+int b2q_peer_mailbox_destroy(b2q_ctx* ctx, void* mailbox);
+int b2q_peer_minmax_quant_fwd_f32(b2q_ctx* ctx, int variant, const float* x, float* y, float* aux, int64_t n,
+                                  int init, float ema_decay, float one_minus_decay, void* const* mailboxes,
+                                  int rank, int world, uint32_t sequence, void* stream);
+
 /* ---- host-buffer path: the call a framework whose tensors live in HOST memory makes (bench.py "e2e") --
  * Same semantics as the device entry points but x / y / aux are HOST pointers (pinned for full speed).
  * Each call stages its tensor through one of two device staging sets on that set's own stream

@@ -57,6 +57,12 @@ _CTX_FUNCS = {
     "b2q_ste_bwd_host_f32": [_P, _P, _L],
     "b2q_clipgrad_bwd_host_f32": [_P, _P, _P, _P, _L],
     "b2q_host_sync": [],
+    "b2q_peer_mailbox_create": [ctypes.POINTER(ctypes.c_void_p), _P],
+    "b2q_peer_mailbox_open": [_P, ctypes.POINTER(ctypes.c_void_p)],
+    "b2q_peer_mailbox_close": [_P],
+    "b2q_peer_mailbox_destroy": [_P],
+    "b2q_peer_minmax_quant_fwd_f32": [_I, _P, _P, _P, _L, _I, _F, _F, ctypes.POINTER(ctypes.c_void_p), _I, _I,
+                                      ctypes.c_uint32, _P],
     "b2q_multi_plan_create": [_P, _I, ctypes.POINTER(ctypes.c_void_p)],
     "b2q_multi_plan_destroy": [_P],
     "b2q_multi_weight_quant_fwd_f32": [_P, _I, _I, _P],
@@ -71,6 +77,7 @@ class WeightDesc(ctypes.Structure):
                 ("per_channel", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 _PLAIN_FUNCS = {
     "b2q_abi_version": ([], _I),
+    "b2q_peer_mailbox_bytes": ([], _I),
     "b2q_last_error": ([], ctypes.c_char_p),
     "b2q_create": ([_I, ctypes.POINTER(ctypes.c_void_p)], _I),
     "b2q_launch_count": ([ctypes.c_void_p], _L),

@@ -81,7 +81,8 @@ int b2q_set_option(b2q_ctx* ctx, const char* key, int value) {
     int* p = option_slot(ctx, key);
     B2Q_REQUIRE(p != nullptr, "unknown option");
     if (p == &ctx->blocks_per_sm || p == &ctx->reduce_blocks_per_sm)
-        B2Q_REQUIRE(value >= 1 && value <= 64, "blocks_per_sm out of range");
+        B2Q_REQUIRE(value >= 1 && value <= 65536, "blocks_per_sm out of range");
+    if (p == &ctx->reduce_blocks_per_sm) B2Q_REQUIRE(value <= B2Q_MAX_PIECES / 256, "too many reduction blocks");
     *p = value;
     return 0;
 }

@@ -46,10 +46,13 @@ struct b2q_ctx {
     unsigned int slot_epoch[B2Q_NSLOTS] = {};   // per-slot use counter: tags deferred max reductions (b2q_slot::max64)
     long long launches = 0;
     // run-time knobs (never change results)
-    int blocks_per_sm = 64;          // flat QDQ / backward sweeps: grid = SMs x this (sweep: many short blocks win)
-    int reduce_blocks_per_sm = 4;    // flat reductions
+    int blocks_per_sm = 4096;        // flat QDQ / backward sweeps: grid = min(tiles, SMs x this); the sweep shows one
+                                     // 16 KB tile per block (no grid-stride loop) is fastest: dynamic balance over SMs
+    int reduce_blocks_per_sm = 4;    // flat reductions that finalise in their last block (partials are re-read)
+    int reduce_deferred_blocks_per_sm = 16;   // flat reductions with deferred update (one atomicMax per block)
     int deferred = 1;                // consumer-side threshold update in the fused whole-tensor forward
-    int reverse = 1;
+    int reverse = 1;                 // QDQ sweep walks descending addresses when the tensor exceeds reverse_min_bytes
+    long long reverse_min_bytes = 96ll << 20;
     int fast_div = 1;
     int timing = 0;
     std::vector<b2q_timing_rec> recs;

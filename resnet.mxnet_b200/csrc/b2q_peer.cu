@@ -1,2 +1,255 @@
-// placeholder translation unit (peer-memory threshold exchange: see DESIGN.md "next")
+// Cross-rank activation-threshold exchange over peer memory (NVLink / NVSwitch), fused into the two kernels of the
+// forward pass.  Replaces  [reduce kernel] -> ncclAllReduce(max, 4 bytes) -> [update kernel] -> [QDQ kernel]
+// (3 launches + a latency-bound collective on the forward critical path of every activation node) by
+//
+//   kernel 1  reduce_peer_kernel   local max|x|; its last block stores (sequence << 32 | float bits) into slot
+//                                  [sequence % 64][rank] of EVERY rank's mailbox with 8-byte system-scope stores
+//                                  (P2P over NVLink for peers), and snapshots the old aux
+//   kernel 2  the QDQ sweep        each block polls its OWN (local) mailbox until all `world` entries of the slot carry
+//                                  this sequence number, takes the max over ranks (exact, order independent), applies
+//                                  the EMA / first-batch update in registers and sweeps; block 0 writes the new aux
+//
+// Every rank launches the same sequence of calls (data parallel), so rank A's sweep only ever waits for kernels that
+// rank B has already enqueued or will enqueue without depending on A's later work: progress is guaranteed as long as
+// all ranks run on different GPUs.  A slot is reused after 64 calls; no rank can be more than one call ahead because
+// each call needs every rank's value.  The poll is bounded: after ~2 s it traps (CUDA error) instead of hanging.
+#include <cstring>
+
 #include "b2q_common.cuh"
+#include "b2q_qdq.cuh"
+#include "b2q_reduce.cuh"
+
+#define B2Q_CTX(ctx)                               \
+    B2Q_REQUIRE((ctx) != nullptr, "null context"); \
+    B2Q_CHECK_CUDA(cudaSetDevice((ctx)->device))
+
+#define B2Q_PEER_MAX_RANKS 16
+#define B2Q_PEER_SLOTS 64
+#define B2Q_PEER_BYTES (B2Q_PEER_SLOTS * B2Q_PEER_MAX_RANKS * 8)
+
+struct PeerBoxes {
+    unsigned long long* box[B2Q_PEER_MAX_RANKS];
+    int rank, world;
+    unsigned int seq;
+};
+
+__device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// kernel 1: whole-tensor max|x|, last block publishes to every rank's mailbox
+template <int UNROLL>
+__global__ void __launch_bounds__(B2Q_THREADS)
+reduce_peer_kernel(const float* __restrict__ x, FlatSplit sp, b2q_slot* slot, const float* aux, PeerBoxes pb) {
+    __shared__ double smem[32];
+    __shared__ unsigned int s_ticket;
+    float mx = 0.f;
+    double unused = 0.0;
+    const float* xb = x + sp.head;
+    const int64_t tile = (int64_t)B2Q_THREADS * UNROLL;
+    const int64_t ntiles = (sp.n8 + tile - 1) / tile;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t base = t * tile + threadIdx.x;
+        f8 v[UNROLL];
+#pragma unroll
+        for (int k = 0; k < UNROLL; ++k) {
+            const int64_t i = base + (int64_t)k * B2Q_THREADS;
+            if (i < sp.n8) v[k] = ld_f8<0>(xb + 8 * i);
+            else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[k].v[j] = 0.f;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < UNROLL; ++k) acc8<true>(unused, mx, v[k]);
+    }
+    if (blockIdx.x == 0) {
+        if ((int64_t)threadIdx.x < sp.head) mx = fmaxf(mx, fabsf(x[threadIdx.x]));
+        if ((int64_t)threadIdx.x < sp.tail) mx = fmaxf(mx, fabsf(x[sp.head + 8 * sp.n8 + threadIdx.x]));
+    }
+    const float r = (float)block_reduce<true>((double)mx, smem);
+    if (threadIdx.x == 0) {
+        slot->partial[blockIdx.x] = (double)r;
+        __threadfence();
+        s_ticket = atomicAdd(&slot->ticket, 1u);
+    }
+    __syncthreads();
+    if (s_ticket != gridDim.x - 1) return;
+    __threadfence();
+    float m = 0.f;
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) m = fmaxf(m, (float)__ldcg(&slot->partial[i]));
+    const float tot = (float)block_reduce<true>((double)m, smem);
+    __shared__ float s_tot;
+    if (threadIdx.x == 0) {
+        s_tot = tot;
+        slot->scale[0] = aux[0];   // snapshot of the old threshold for the sweep
+        slot->ticket = 0;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < pb.world) {   // one lane per destination rank: 8-byte P2P store
+        const unsigned long long word = ((unsigned long long)pb.seq << 32) | __float_as_uint(s_tot);
+        st_sys_u64(pb.box[threadIdx.x] + (size_t)(pb.seq % B2Q_PEER_SLOTS) * B2Q_PEER_MAX_RANKS + pb.rank, word);
+    }
+    __threadfence_system();
+}
+
+// kernel 2: QDQ sweep whose prologue gathers every rank's statistic from the local mailbox
+template <bool CLIP_SYM, int UNROLL, int LDPOL, int STPOL>
+__global__ void __launch_bounds__(B2Q_THREADS)
+qdq_peer_kernel(const float* __restrict__ x, float* __restrict__ y, FlatSplit sp, const unsigned long long* mybox,
+                int world, unsigned int seq, const float* aux_old, UpdateArgs u, float qlevel, int fast, int reverse) {
+    __shared__ float s_stat;
+    if (threadIdx.x < 32) {
+        float v = 0.f;
+        if ((int)threadIdx.x < world) {
+            const unsigned long long* p = mybox + (size_t)(seq % B2Q_PEER_SLOTS) * B2Q_PEER_MAX_RANKS + threadIdx.x;
+            unsigned long long w = ld_sys_u64(p);
+            unsigned int spins = 0;
+            while ((unsigned int)(w >> 32) != seq) {
+                __nanosleep(64);
+                w = ld_sys_u64(p);
+                if (++spins > (1u << 21)) __trap();   // a peer never arrived: fail loudly instead of hanging
+            }
+            v = __uint_as_float((unsigned int)(w & 0xffffffffull));
+        }
+        v = warp_max(v);
+        if (threadIdx.x == 0) s_stat = v;
+    }
+    __syncthreads();
+    const float a_old = aux_old[0];
+    float fresh, next;
+    compute_update(u.mode, u.p0, u.p1, a_old, s_stat, fresh, next);
+    const float T = next;
+    if (blockIdx.x == 0 && threadIdx.x == 0) u.aux[0] = next;
+    const QScale s = make_qscale(T, qlevel, fast != 0 && !(CLIP_SYM && !(T >= 0.f)));
+    const float* xb = x + sp.head;
+    float* yb = y + sp.head;
+    const int64_t tile = (int64_t)B2Q_THREADS * UNROLL;
+    const int64_t ntiles = (sp.n8 + tile - 1) / tile;
+    for (int64_t tt = blockIdx.x; tt < ntiles; tt += gridDim.x) {
+        const int64_t t = reverse ? (ntiles - 1 - tt) : tt;
+        const int64_t base = t * tile + threadIdx.x;
+        f8 v[UNROLL];
+#pragma unroll
+        for (int k = 0; k < UNROLL; ++k) {
+            const int64_t i = base + (int64_t)k * B2Q_THREADS;
+            if (i < sp.n8) v[k] = ld_f8<LDPOL>(xb + 8 * i);
+        }
+#pragma unroll
+        for (int k = 0; k < UNROLL; ++k) {
+            const int64_t i = base + (int64_t)k * B2Q_THREADS;
+            if (i < sp.n8) {
+                f8 o;
+                qdq8<CLIP_SYM>(v[k], o, T, s);
+                st_f8<STPOL>(yb + 8 * i, o);
+            }
+        }
+    }
+    if (blockIdx.x == 0) {
+        const int64_t tid = threadIdx.x;
+        int64_t idx = -1;
+        if (tid < sp.head) idx = tid;
+        else if (tid - sp.head < sp.tail) idx = sp.head + 8 * sp.n8 + (tid - sp.head);
+        if (idx >= 0) {
+            const float c = CLIP_SYM ? mx_clip(x[idx], -T, T) : x[idx];
+            y[idx] = __fmul_rn(quant_code(c, s), s.q);
+        }
+    }
+}
+
+extern "C" {
+
+int b2q_peer_mailbox_bytes(void) { return B2Q_PEER_BYTES; }
+
+int b2q_peer_mailbox_create(b2q_ctx* ctx, void** mailbox, void* ipc_handle_out) {
+    B2Q_CTX(ctx);
+    B2Q_REQUIRE(mailbox && ipc_handle_out, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void* p = nullptr;
+    B2Q_CHECK_CUDA(cudaMalloc(&p, B2Q_PEER_BYTES));
+    B2Q_CHECK_CUDA(cudaMemset(p, 0, B2Q_PEER_BYTES));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        b2q_set_error(std::string("cudaIpcGetMemHandle failed: ") + cudaGetErrorString(e));
+        return 1;
+    }
+    memcpy(ipc_handle_out, &h, sizeof(h));
+    *mailbox = p;
+    return 0;
+}
+
+int b2q_peer_mailbox_open(b2q_ctx* ctx, const void* ipc_handle, void** peer_ptr) {
+    B2Q_CTX(ctx);
+    B2Q_REQUIRE(ipc_handle && peer_ptr, "null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle, sizeof(h));
+    B2Q_CHECK_CUDA(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+int b2q_peer_mailbox_close(b2q_ctx* ctx, void* peer_ptr) {
+    B2Q_CTX(ctx);
+    if (peer_ptr) B2Q_CHECK_CUDA(cudaIpcCloseMemHandle(peer_ptr));
+    return 0;
+}
+
+int b2q_peer_mailbox_destroy(b2q_ctx* ctx, void* mailbox) {
+    B2Q_CTX(ctx);
+    if (mailbox) B2Q_CHECK_CUDA(cudaFree(mailbox));
+    return 0;
+}
+
+int b2q_peer_minmax_quant_fwd_f32(b2q_ctx* ctx, int variant, const float* x, float* y, float* aux, int64_t n, int init,
+                                  float ema_decay, float one_minus_decay, void* const* mailboxes, int rank, int world,
+                                  uint32_t sequence, void* stream) {
+    B2Q_CTX(ctx);
+    B2Q_REQUIRE(x && y && aux && mailboxes && n >= 1, "bad argument");
+    B2Q_REQUIRE(variant == 0 || variant == 1, "variant must be 0 or 1");
+    B2Q_REQUIRE(world >= 1 && world <= B2Q_PEER_MAX_RANKS && rank >= 0 && rank < world, "bad rank / world");
+    B2Q_REQUIRE(sequence != 0, "sequence numbers start at 1 (0 marks an empty mailbox entry)");
+    cudaStream_t st = (cudaStream_t)stream;
+    FlatSplit sp = b2q_flat_split(x, n);
+    B2Q_REQUIRE(same_misalignment(x, y) && sp.head <= B2Q_THREADS, "peer path needs equally aligned float32 buffers");
+    PeerBoxes pb;
+    memset(&pb, 0, sizeof(pb));
+    for (int r = 0; r < world; ++r) {
+        B2Q_REQUIRE(mailboxes[r] != nullptr, "null mailbox pointer");
+        pb.box[r] = (unsigned long long*)mailboxes[r];
+    }
+    pb.rank = rank; pb.world = world; pb.seq = sequence;
+    b2q_slot* slot = b2q_take_slot(ctx);
+    {
+        const int64_t grid = b2q_flat_grid(ctx, sp.n8, B2Q_REDUCE_UNROLL, ctx->reduce_blocks_per_sm);
+        b2q_timed_launch tl(ctx, B2Q_KIND_REDUCE_FLAT, 4.0 * (double)n, st);
+        reduce_peer_kernel<B2Q_REDUCE_UNROLL><<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, sp, slot, aux, pb);
+        B2Q_LAUNCH_CHECK(ctx);
+    }
+    UpdateArgs u;
+    memset(&u, 0, sizeof(u));
+    u.mode = (variant == 1 && init) ? B2Q_UPD_STORE : B2Q_UPD_EMA;   // clip_grad...py:42-46 / quant_ops.py:37
+    u.write_aux = 1; u.use_aux_as_scale = 1; u.p0 = ema_decay; u.p1 = one_minus_decay; u.aux = aux;
+    {
+        const int64_t grid = b2q_flat_grid(ctx, sp.n8, B2Q_QDQ_UNROLL);
+        const unsigned long long* mybox = (const unsigned long long*)mailboxes[rank];
+        const int rev = (ctx->reverse && n * 4 > ctx->reverse_min_bytes) ? 1 : 0;
+        b2q_timed_launch tl(ctx, B2Q_KIND_QDQ_HOT, 8.0 * (double)n, st);
+        if (variant == 1)
+            qdq_peer_kernel<true, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, B2Q_QDQ_STPOL><<<(unsigned)grid, B2Q_THREADS, 0, st>>>(
+                x, y, sp, mybox, world, sequence, slot->scale, u, 127.f, ctx->fast_div, rev);
+        else
+            qdq_peer_kernel<false, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, B2Q_QDQ_STPOL><<<(unsigned)grid, B2Q_THREADS, 0, st>>>(
+                x, y, sp, mybox, world, sequence, slot->scale, u, 127.f, ctx->fast_div, rev);
+        B2Q_LAUNCH_CHECK(ctx);
+    }
+    return 0;
+}
+
+}  // extern "C"

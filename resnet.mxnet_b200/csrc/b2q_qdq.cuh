@@ -417,8 +417,9 @@ static inline bool same_misalignment(const void* a, const void* b) {
                 const int64_t grid = b2q_flat_grid(ctx, sp.n8, B2Q_QDQ_UNROLL);
                 DeferredUpdate none = {};
                 const bool stream_out = n * 4 > B2Q_STREAM_BYTES;
+                const int rev = (ctx->reverse && n * 4 > ctx->reverse_min_bytes) ? 1 : 0;
 #define B2Q_HOT(C, S) qdq_flat_hot_kernel<C, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, S, false> \
-                          <<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, y, sp, a, ctx->reverse, none, 0)
+                          <<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, y, sp, a, rev, none, 0)
                 if (a.clip_mode == B2Q_CLIP_SYM) { if (stream_out) B2Q_HOT(true, 1); else B2Q_HOT(true, B2Q_QDQ_STPOL); }
                 else { if (stream_out) B2Q_HOT(false, 1); else B2Q_HOT(false, B2Q_QDQ_STPOL); }
 #undef B2Q_HOT
@@ -469,8 +470,9 @@ template <bool IS_MAX>
     {
         b2q_timed_launch tl(ctx, B2Q_KIND_QDQ_HOT, 8.0 * (double)n, st);
         const bool stream_out = n * 4 > B2Q_STREAM_BYTES;
+        const int rev = (ctx->reverse && n * 4 > ctx->reverse_min_bytes) ? 1 : 0;
 #define B2Q_HOT(C, S) qdq_flat_hot_kernel<C, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, S, true> \
-                          <<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, y, sp, a, ctx->reverse, d, clip_with_fresh)
+                          <<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, y, sp, a, rev, d, clip_with_fresh)
         if (clip_mode == B2Q_CLIP_SYM) { if (stream_out) B2Q_HOT(true, 1); else B2Q_HOT(true, B2Q_QDQ_STPOL); }
         else { if (stream_out) B2Q_HOT(false, 1); else B2Q_HOT(false, B2Q_QDQ_STPOL); }
 #undef B2Q_HOT

@@ -263,7 +263,8 @@ static inline int64_t b2q_flat_grid(const b2q_ctx* ctx, int64_t n8, int unroll, 
     int64_t grid = (int64_t)ctx->num_sms * (bps > 0 ? bps : ctx->blocks_per_sm);
     if (grid > ntiles) grid = ntiles;
     if (grid < 1) grid = 1;
-    if (grid > B2Q_MAX_PIECES) grid = B2Q_MAX_PIECES;
+    if (bps > 0 && grid > B2Q_MAX_PIECES) grid = B2Q_MAX_PIECES;   // reductions keep one partial per block
+    if (grid > 0x7fffffff) grid = 0x7fffffff;
     return grid;
 }
 
@@ -278,7 +279,8 @@ static int launch_reduce_deferred(b2q_ctx* ctx, b2q_slot* slot, const float* x, 
     *epoch_out = epoch;
     FlatSplit sp = b2q_flat_split(x, n);
     if (sp.head > B2Q_THREADS) return 0;
-    const int64_t grid = b2q_flat_grid(ctx, sp.n8, B2Q_REDUCE_UNROLL, ctx->reduce_blocks_per_sm);
+    const int64_t grid = b2q_flat_grid(ctx, sp.n8, B2Q_REDUCE_UNROLL,
+                                       IS_MAX ? ctx->reduce_deferred_blocks_per_sm : ctx->reduce_blocks_per_sm);
     b2q_timed_launch tl(ctx, B2Q_KIND_REDUCE_FLAT, 4.0 * (double)n, st);
     reduce_flat_kernel<IS_MAX, B2Q_REDUCE_UNROLL, B2Q_REDUCE_LDPOL, false>
         <<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, sp, slot, u, (float)n, epoch);

@@ -52,3 +52,71 @@ class GradBucket(object):
             if average:
                 self.flat.div_(dist.get_world_size(group))
         return self.flat
+
+
+class PeerThresholdExchange(object):
+    """Threshold exchange over peer memory, fused into the forward kernels (b2q_peer_minmax_quant_fwd_f32): no NCCL
+    call on the forward critical path.  Each rank allocates a mailbox, the 64-byte CUDA IPC handles are exchanged
+    once through torch.distributed, and every activation node then runs [reduce + publish] -> [poll + update + QDQ].
+    Single node only (CUDA IPC); all ranks must call the nodes in the same order."""
+
+    def __init__(self, device, group=None):
+        import ctypes
+        from . import _lib
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.device = torch.device(device)
+        self.ctx = _lib.context(self.device.index)
+        self.sequence = 0
+        own = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        self.ctx.call("b2q_peer_mailbox_create", ctypes.byref(own), ctypes.cast(handle, ctypes.c_void_p))
+        self._own = own
+        handles = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        else:
+            handles[0] = bytes(handle.raw)
+        self._boxes = (ctypes.c_void_p * self.world)()
+        self._opened = []
+        for r in range(self.world):
+            if r == self.rank:
+                self._boxes[r] = own.value
+            else:
+                p = ctypes.c_void_p()
+                buf = ctypes.create_string_buffer(handles[r], 64)
+                self.ctx.call("b2q_peer_mailbox_open", ctypes.cast(buf, ctypes.c_void_p), ctypes.byref(p))
+                self._boxes[r] = p.value
+                self._opened.append(p)
+        if self.world > 1:
+            dist.barrier(group=group)
+
+    def quantize(self, variant, x, y, aux, init, ema_decay):
+        """Activation forward (training) of Quantization_int8_V2 (variant 0) / ClipGrad (variant 1) with the
+        statistic maximised over all ranks."""
+        import numpy as np
+        from .dlpack import as_buffer, current_stream
+        xb, yb, ab = as_buffer(x), as_buffer(y, write=True), as_buffer(aux, write=True)
+        self.sequence += 1
+        self.ctx.call("b2q_peer_minmax_quant_fwd_f32", int(variant), xb.ptr, yb.ptr, ab.ptr, xb.numel, int(bool(init)),
+                      float(np.float32(ema_decay)), float(np.float32(1 - ema_decay)), self._boxes, self.rank, self.world,
+                      self.sequence, current_stream(xb))
+
+    def close(self):
+        for p in self._opened:
+            self.ctx.call("b2q_peer_mailbox_close", p)
+        self._opened = []
+        if self._own is not None:
+            self.ctx.call("b2q_peer_mailbox_destroy", self._own)
+            self._own = None
+
+
+def attach_peer_exchange(ops, device, group=None):
+    """Route every activation minmax node in ``ops`` through the fused peer-memory exchange."""
+    ex = PeerThresholdExchange(device, group)
+    for op in ops:
+        if not getattr(op, "is_weight", True) and hasattr(op, "VARIANT"):
+            op.peer = ex
+            op.sync = None
+    return ex

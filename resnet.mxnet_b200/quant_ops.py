@@ -29,13 +29,16 @@ class Quantization_int8(CustomOp):
         self.ema_decay = ema_decay
         self.QUANT_LEVEL = 127
         self.init = True
-        self.sync = None     # optional cross-rank threshold exchange (b200quant.dist.ThresholdSync)
+        self.sync = None     # optional cross-rank threshold exchange through NCCL (b200quant.dist.ThresholdSync)
+        self.peer = None     # optional fused peer-memory exchange (b200quant.dist.PeerThresholdExchange)
         self._stat = None
 
     def _quantize(self, is_train, req, x, y, aux, first):
         """One fused call; or, when a cross-rank sync is attached to a training activation node:
         reduce -> allreduce(max) -> update + QDQ, so every rank applies the same threshold."""
-        if self.sync is not None and is_train and not self.is_weight:
+        if self.peer is not None and is_train and not self.is_weight and req in ("write", "inplace"):
+            self.peer.quantize(self.VARIANT, x, y, aux, first, self.ema_decay)
+        elif self.sync is not None and is_train and not self.is_weight:
             if self._stat is None:
                 import torch
                 self._stat = torch.empty(1, dtype=torch.float32, device=x.device)

@@ -1,0 +1,82 @@
+"""Multi-GPU parity check, run under torchrun (one process per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tests/multi_gpu_check.py
+
+Every rank quantises its own shard; thresholds are exchanged (a) with NCCL allreduce(max) and (b) with the fused
+peer-memory kernels.  Rank r checks, bit for bit, against the NumPy oracle fed the max over ranks: aux after every
+step and its own quantised output.  Exit code 0 = all good."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+F = np.float32
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import b200quant
+    from b200quant.dist import ThresholdSync, attach_peer_exchange
+    from oracle import quant_oracle as qo
+
+    def bits(a, b):
+        return np.array_equal(np.ascontiguousarray(a, dtype=F).view(np.uint32), np.ascontiguousarray(b, dtype=F).view(np.uint32))
+
+    failures = 0
+    for mode in ("nccl", "peer"):
+        for op_type, variant in (("Quantization_int8_V2", 0), ("ClipGrad_Quantization_int8", 1)):
+            op = b200quant.get_prop(op_type)(quant_mode="minmax", is_weight="False").create_operator(None, None, None)
+            ex = None
+            if mode == "nccl":
+                op.sync = ThresholdSync()
+            else:
+                ex = attach_peer_exchange([op], torch.device("cuda", local))
+            aux = torch.ones(1, device="cuda")
+            aux_ref = np.ones(1, F)
+            init = True
+            for step in range(4):
+                rng = np.random.default_rng(1000 * step + 5 + rank)
+                shape = (4, 16, 28, 28) if step % 2 == 0 else (3, 7, 5)
+                x = (rng.standard_normal(shape) * (1.0 + rank + 0.5 * step)).astype(F)
+                xd = torch.from_numpy(x).cuda()
+                yd = torch.zeros_like(xd)
+                op.forward(True, ["write"], [xd], [yd], [aux])
+                # oracle: statistic = max over ranks of the per-rank absmax
+                m = torch.tensor([float(np.abs(x).max())], device="cuda")
+                dist.all_reduce(m, op=dist.ReduceOp.MAX)
+                stat = F(m.item())
+                if variant == 1 and init:
+                    aux_ref[...] = stat
+                else:
+                    aux_ref[...] = qo.mx_add(qo.mx_mul(aux_ref, F(0.99)), qo.mx_mul(stat, F(1 - 0.99)))
+                init = False
+                q = qo.mx_div(aux_ref, F(127))
+                src = qo.mx_clip(x, -float(aux_ref[0]), float(aux_ref[0])) if variant == 1 else x
+                want, _ = qo.qdq(src, q)
+                ok = bits(aux.cpu().numpy(), aux_ref) and bits(yd.cpu().numpy(), want)
+                if not ok:
+                    failures += 1
+                    print("rank %d FAIL mode=%s op=%s step=%d aux=%r want=%r" % (rank, mode, op_type, step,
+                                                                                 aux.cpu().numpy(), aux_ref), flush=True)
+            if ex is not None:
+                torch.cuda.synchronize()
+                dist.barrier()
+                ex.close()
+    t = torch.tensor([failures], device="cuda")
+    dist.all_reduce(t)
+    if rank == 0:
+        print("multi_gpu_check: world=%d failures=%d" % (world, int(t.item())), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    return 1 if int(t.item()) else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -95,17 +95,25 @@ class ClockSampler(threading.Thread):
 # ---------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------
-def build_nodes(torch, nodes, op_type, device, host=False, seed=5):
-    """Allocate every node's tensors (inputs resident before the timed region) and create its operator through
-    the registered Prop with string attributes, as MXNet would."""
+def make_op(op_type, is_w):
+    """Operator through its registered Prop with string attributes, as MXNet would create it."""
     import b200quant
+    if op_type == "GDRQ_PY":   # config/quant_attrs.py:38-63 with nbits 8 (int8)
+        attrs = dict(nbits="8", group_size="-1", is_weight=str(is_w), lamda="0.001", delay_quant="0",
+                     fix_alpha="False", ktimes="3")
+    else:
+        attrs = dict(quant_mode="minmax", is_weight=str(is_w), is_weight_perchannel="False", delay_quant="0",
+                     ema_decay="0.99")
+    return b200quant.get_prop(op_type)(**attrs).create_operator(None, None, None)
+
+
+def build_nodes(torch, nodes, op_type, device, host=False, seed=5):
+    """Allocate every node's tensors (inputs resident before the timed region) and create its operator."""
     g = torch.Generator(device=device).manual_seed(seed)
     out = []
     for name, kind, shape in nodes:
         is_w = kind == "weight"
-        prop = b200quant.get_prop(op_type)(quant_mode="minmax", is_weight=str(is_w), is_weight_perchannel="False",
-                                           delay_quant="0", ema_decay="0.99")
-        op = prop.create_operator(None, None, None)
+        op = make_op(op_type, is_w)
         if is_w:
             fan_in = 1
             for s in shape[1:]:
@@ -249,12 +257,32 @@ def main_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": co.num_threads(), "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
     return 0
+
+
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Libraries (NCCL's version banner, torchrun notices) print to fd 1; the driver wants exactly one JSON line
+    there.  Everything written to stdout from now on goes to stderr; emit() writes the JSON to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
     args = parse()
+    claim_stdout()
     if args.impl == "reference":
         return main_reference(args)
 
@@ -281,7 +309,14 @@ def main():
     sm = summary(node_list)
     total_elems = sm["act_elems"] + sm["weight_elems"]
     ctx = _lib.context(local)
-    nodes = build_nodes(torch, node_list, "Quantization_int8_V2", device, seed=5 + rank)
+    if op_type == "GDRQ_Fold_BN":
+        raise SystemExit("the fold-BN workload is a parity case (tests/test_gpu_configs.py), not a bench line")
+    nodes = build_nodes(torch, node_list, op_type, device, seed=5 + rank)
+    minmax = op_type in ("Quantization_int8_V2", "ClipGrad_Quantization_int8")
+    # algorithmic bytes per element: forward 12 (4 reduce + 8 sweep); backward 8 (STE copy) or 12 (masked, activations
+    # of the clip-grad / GDRQ operators)
+    bwd_act = 8 if op_type == "Quantization_int8_V2" else 12
+    alg_bytes_step = 12 * total_elems + bwd_act * sm["act_elems"] + 8 * sm["weight_elems"]
 
     bucket = None
     exchange = "none"
@@ -309,8 +344,10 @@ def main():
     from b200quant.multi import WeightGroup
     wnodes = [nd for nd in nodes if nd["kind"] == "weight"]
     anodes = [nd for nd in nodes if nd["kind"] == "act"]
-    group = WeightGroup([nd["op"] for nd in wnodes], [nd["x"] for nd in wnodes], [nd["y"] for nd in wnodes],
-                        [nd["aux"] for nd in wnodes], [nd["dy"] for nd in wnodes], [nd["dx"] for nd in wnodes])
+    group = None
+    if minmax:
+        group = WeightGroup([nd["op"] for nd in wnodes], [nd["x"] for nd in wnodes], [nd["y"] for nd in wnodes],
+                            [nd["aux"] for nd in wnodes], [nd["dy"] for nd in wnodes], [nd["dx"] for nd in wnodes])
 
     def step_multi():
         group.forward(True)
@@ -337,19 +374,22 @@ def main():
     ms = ms_eager
     timings = {mode: ms_eager / args.steps}
 
-    for _ in range(3):
-        step_multi()
-    l0 = ctx.launch_count()
-    ms_multi = time_steps(torch, dist, step_multi, args.steps, world)
-    timings["eager, weight nodes batched (WeightGroup)"] = ms_multi / args.steps
-    if ms_multi < ms:
-        ms, mode, launches = ms_multi, "eager, weight nodes batched (WeightGroup)", ctx.launch_count() - l0
+    if group is not None:
+        for _ in range(3):
+            step_multi()
+        l0 = ctx.launch_count()
+        ms_multi = time_steps(torch, dist, step_multi, args.steps, world)
+        timings["eager, weight nodes batched (WeightGroup)"] = ms_multi / args.steps
+        if ms_multi < ms:
+            ms, mode, launches = ms_multi, "eager, weight nodes batched (WeightGroup)", ctx.launch_count() - l0
 
     # ---- the same steps replayed from a CUDA graph (single GPU; the graph holds our kernels only) ----
     ms_graph = None
     if world == 1 and not args.no_graph:
         for label, fn_ in (("cuda_graph, one CustomOp call per node", step),
                            ("cuda_graph, weight nodes batched (WeightGroup)", step_multi)):
+            if fn_ is step_multi and group is None:
+                continue
             try:
                 graph = torch.cuda.CUDAGraph()
                 s = torch.cuda.Stream()
@@ -412,21 +452,22 @@ def main():
                 "alg_bytes_per_launch": (dom.get("alg_bytes_total", 0) / dom["launches"]) if dom else None,
                 "avg_launch_ms": (dom.get("ms_total", 0) / dom["launches"]) if dom else None}
 
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+    metric = METRIC if args.workload == "resnet50_int8" else args.workload + "_quant_path_images_per_sec"
+    line = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%s quant path: fwd+bwd of all %d Quantization_int8_V2 nodes (%d act + %d weight), "
-                                   "per-GPU batch %d" % (args.workload, len(nodes), sm["act_nodes"], sm["weight_nodes"],
-                                                         batch),
-                       "elements_per_step": total_elems, "alg_bytes_per_step": 20 * total_elems,
+            "config": {"workload": "%s quant path: fwd+bwd of all %d %s nodes (%d act + %d weight), "
+                                   "per-GPU batch %d" % (args.workload, len(nodes), op_type, sm["act_nodes"],
+                                                         sm["weight_nodes"], batch),
+                       "elements_per_step": total_elems, "alg_bytes_per_step": alg_bytes_step,
                        "parallelism": "dp%d" % world, "threshold_exchange": exchange, "l2": "inputs larger than L2 (10.9 GB touched once per step)",
                        "mode": mode},
             "ms_per_step_by_mode": timings,
-            "hbm_frac_whole_step": 20.0 * total_elems / (ms / args.steps / 1e3) / 1e9 / peak_gbs,
+            "hbm_frac_whole_step": alg_bytes_step / (ms / args.steps / 1e3) / 1e9 / peak_gbs,
             "roofline": roofline, "kernels": kernels, "clocks": clocks, "gpu_launches": launches}
 
     # ---- e2e: host buffers through the host C ABI (rank-local; N ranks run it concurrently) ----
-    if not args.no_e2e:
+    if not args.no_e2e and op_type == "Quantization_int8_V2":
         hstep, b_in, b_out = host_step_factory(torch, nodes, ctx)
         hstep()
         if world > 1:
@@ -445,11 +486,11 @@ def main():
                        "d2h_bytes_per_step": b_out, "steps": args.e2e_steps, "ms_per_step": dt / args.e2e_steps * 1e3,
                        "path": "CustomOp.forward/backward with pinned HOST tensors -> b2q_*_host_f32"}
 
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and op_type == "Quantization_int8_V2":
         line["cpu_baseline"] = cpu_baseline(total_elems, batch)
 
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

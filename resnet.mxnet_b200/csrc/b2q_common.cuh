@@ -16,7 +16,8 @@
 // order, applies the threshold update and resets the ticket, so a slot is reusable without a memset.
 struct b2q_slot {
     unsigned int ticket;
-    unsigned int pad;
+    unsigned int epoch;           // device-side use counter of max64 (advanced by the consumer kernel, so a CUDA graph
+                                  // that replays the pair keeps producing fresh tags)
     unsigned long long max64;     // (epoch << 32 | float bits) for the deferred max reduction: atomicMax, never reset
     float scale[B2Q_MAX_GROUPS];  // threshold T the following QDQ kernel scales with (when it is not aux)
     float clip[B2Q_MAX_GROUPS];   // threshold the following QDQ kernel clips with (when it differs)
@@ -43,7 +44,6 @@ struct b2q_ctx {
     int num_sms = 0;
     b2q_slot* slots = nullptr;      // device
     unsigned int next_slot = 0;
-    unsigned int slot_epoch[B2Q_NSLOTS] = {};   // per-slot use counter: tags deferred max reductions (b2q_slot::max64)
     long long launches = 0;
     // run-time knobs (never change results)
     int blocks_per_sm = 4096;        // flat QDQ / backward sweeps: grid = min(tiles, SMs x this); the sweep shows one
@@ -251,6 +251,7 @@ __device__ __forceinline__ void apply_update(const UpdateArgs& u, int g, float s
 struct DeferredUpdate {
     const double* partial;   // sums: [n_partials] written by reduce_flat_kernel<false, .., FINALIZE=false>
     const unsigned long long* max64;   // max: epoch-tagged atomicMax word written by reduce_flat_kernel<true, ..>
+    unsigned int* epoch;     // slot->epoch: the sweep's block 0 stores the consumed tag here
     const float* aux_old;    // snapshot of aux[0] taken by the reduction kernel
     int n_partials;
     int is_max;

@@ -6,8 +6,9 @@
 // A plan is built once (weight pointers are stable across steps): a device table of tensors and a device table of
 // work items.  Item kinds: RANGE = a slice of <= 8192 elements of one group (whole tensor, or one long row);
 // ROWS = up to 64 consecutive short rows of a per-channel tensor, one warp per row (depthwise 3x3: 9 elements).
-// max is combined with atomicMax on the bit pattern of non-negative floats: exact and order-independent.
-// Two statistic buffers alternate between calls; the sweep kernel clears the one the next call will use.
+// max is combined with atomicMax on (epoch << 32 | bit pattern of the non-negative float): exact, order-independent and
+// never in need of a reset, because the epoch lives on the device and is advanced by the sweep kernel that consumes
+// the statistics -- a CUDA graph replaying the two launches keeps working on fresh tags.
 #include <cstring>
 #include <vector>
 
@@ -46,8 +47,8 @@ struct b2q_multi_plan {
     int n_tensors, n_items, n_groups;
     MtTensor* d_tensors;
     MtItem* d_items;
-    unsigned int* d_stat[2];
-    unsigned parity;
+    unsigned long long* d_stat;
+    unsigned int* d_epoch;
     long long elements;
     int has_grad;
 };
@@ -57,8 +58,10 @@ __device__ __forceinline__ const float* mt_group_base(const MtTensor& t, int gro
 }
 
 __global__ void __launch_bounds__(B2Q_THREADS)
-mt_absmax_kernel(const MtTensor* __restrict__ tensors, const MtItem* __restrict__ items, unsigned int* __restrict__ stat) {
+mt_absmax_kernel(const MtTensor* __restrict__ tensors, const MtItem* __restrict__ items,
+                 unsigned long long* __restrict__ stat, const unsigned int* __restrict__ epoch) {
     __shared__ double smem[32];
+    const unsigned long long tag = (unsigned long long)(*epoch + 1u) << 32;
     const MtItem it = items[blockIdx.x];
     const MtTensor t = tensors[it.tensor];
     if (it.kind == 0) {
@@ -76,7 +79,7 @@ mt_absmax_kernel(const MtTensor* __restrict__ tensors, const MtItem* __restrict_
             for (long long i = it.a + threadIdx.x; i < it.b; i += blockDim.x) m = fmaxf(m, fabsf(base[i]));
         }
         const float r = (float)block_reduce<true>((double)m, smem);
-        if (threadIdx.x == 0) atomicMax(stat + t.gbase + it.group, __float_as_uint(r));
+        if (threadIdx.x == 0) atomicMax(stat + t.gbase + it.group, tag | __float_as_uint(r));
     } else {
         const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
         for (long long row = it.a + wid; row < it.b; row += nw) {
@@ -84,19 +87,20 @@ mt_absmax_kernel(const MtTensor* __restrict__ tensors, const MtItem* __restrict_
             float m = 0.f;
             for (long long c = lane; c < t.cols; c += 32) m = fmaxf(m, fabsf(p[c]));
             m = warp_max(m);
-            if (lane == 0) stat[t.gbase + row] = __float_as_uint(m);
+            if (lane == 0) stat[t.gbase + row] = tag | __float_as_uint(m);
         }
     }
 }
 
 __global__ void __launch_bounds__(B2Q_THREADS)
-mt_qdq_kernel(const MtTensor* __restrict__ tensors, const MtItem* __restrict__ items, const unsigned int* __restrict__ stat,
-              unsigned int* __restrict__ next_stat, int n_groups, int from_stat, int write_aux, int fast) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_groups; i += gridDim.x * blockDim.x) next_stat[i] = 0u;
+mt_qdq_kernel(const MtTensor* __restrict__ tensors, const MtItem* __restrict__ items,
+              const unsigned long long* __restrict__ stat, unsigned int* __restrict__ epoch, int from_stat, int write_aux,
+              int fast) {
+    if (from_stat && blockIdx.x == 0 && threadIdx.x == 0) *epoch = (unsigned int)(stat[0] >> 32);   // consume the tag
     const MtItem it = items[blockIdx.x];
     const MtTensor t = tensors[it.tensor];
     if (it.kind == 0) {
-        const float T = from_stat ? __uint_as_float(stat[t.gbase + it.group]) : t.aux[it.group];
+        const float T = from_stat ? __uint_as_float((unsigned int)(stat[t.gbase + it.group] & 0xffffffffull)) : t.aux[it.group];
         const QScale s = make_qscale(T, 127.f, fast != 0);
         if (write_aux && it.first && threadIdx.x == 0) t.aux[it.group] = T;
         const long long off = (t.per_channel ? (long long)it.group * t.cols : 0);
@@ -121,7 +125,7 @@ mt_qdq_kernel(const MtTensor* __restrict__ tensors, const MtItem* __restrict__ i
     } else {
         const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
         for (long long row = it.a + wid; row < it.b; row += nw) {
-            const float T = from_stat ? __uint_as_float(stat[t.gbase + row]) : t.aux[row];
+            const float T = from_stat ? __uint_as_float((unsigned int)(stat[t.gbase + row] & 0xffffffffull)) : t.aux[row];
             const QScale s = make_qscale(T, 127.f, fast != 0);
             if (write_aux && lane == 0) t.aux[row] = T;
             const float* p = t.x + row * t.cols;
@@ -194,14 +198,14 @@ int b2q_multi_plan_create(b2q_ctx* ctx, const b2q_weight_desc* descs, int count,
     p->has_grad = has_grad;
     cudaError_t e = cudaMalloc(&p->d_tensors, sizeof(MtTensor) * tensors.size());
     if (e == cudaSuccess) e = cudaMalloc(&p->d_items, sizeof(MtItem) * items.size());
-    if (e == cudaSuccess) e = cudaMalloc(&p->d_stat[0], sizeof(unsigned int) * gbase);
-    if (e == cudaSuccess) e = cudaMalloc(&p->d_stat[1], sizeof(unsigned int) * gbase);
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_stat, sizeof(unsigned long long) * gbase);
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_epoch, sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMemcpy(p->d_tensors, tensors.data(), sizeof(MtTensor) * tensors.size(), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(p->d_items, items.data(), sizeof(MtItem) * items.size(), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemset(p->d_stat[0], 0, sizeof(unsigned int) * gbase);
-    if (e == cudaSuccess) e = cudaMemset(p->d_stat[1], 0, sizeof(unsigned int) * gbase);
+    if (e == cudaSuccess) e = cudaMemset(p->d_stat, 0, sizeof(unsigned long long) * gbase);
+    if (e == cudaSuccess) e = cudaMemset(p->d_epoch, 0, sizeof(unsigned int));
     if (e != cudaSuccess) {
-        cudaFree(p->d_tensors); cudaFree(p->d_items); cudaFree(p->d_stat[0]); cudaFree(p->d_stat[1]);
+        cudaFree(p->d_tensors); cudaFree(p->d_items); cudaFree(p->d_stat); cudaFree(p->d_epoch);
         delete p;
         b2q_set_error(std::string("multi plan allocation failed: ") + cudaGetErrorString(e));
         return 1;
@@ -213,7 +217,7 @@ int b2q_multi_plan_create(b2q_ctx* ctx, const b2q_weight_desc* descs, int count,
 int b2q_multi_plan_destroy(b2q_ctx* ctx, b2q_multi_plan* p) {
     if (!p) return 0;
     if (ctx) cudaSetDevice(ctx->device);
-    cudaFree(p->d_tensors); cudaFree(p->d_items); cudaFree(p->d_stat[0]); cudaFree(p->d_stat[1]);
+    cudaFree(p->d_tensors); cudaFree(p->d_items); cudaFree(p->d_stat); cudaFree(p->d_epoch);
     delete p;
     return 0;
 }
@@ -226,20 +230,17 @@ int b2q_multi_weight_quant_fwd_f32(b2q_ctx* ctx, b2q_multi_plan* p, int variant,
     // quant_ops.py:17-31 reduces always and stores aux when training; clip_grad...py:19-36 reduces only when
     // training and otherwise quantises from the stored aux
     const int do_reduce = (variant == 0 || is_train) ? 1 : 0;
-    unsigned int* cur = p->d_stat[p->parity & 1];
-    unsigned int* nxt = p->d_stat[(p->parity + 1) & 1];
     if (do_reduce) {
         b2q_timed_launch tl(ctx, B2Q_KIND_OTHER, 4.0 * (double)p->elements, st);
-        mt_absmax_kernel<<<(unsigned)p->n_items, B2Q_THREADS, 0, st>>>(p->d_tensors, p->d_items, cur);
+        mt_absmax_kernel<<<(unsigned)p->n_items, B2Q_THREADS, 0, st>>>(p->d_tensors, p->d_items, p->d_stat, p->d_epoch);
         B2Q_LAUNCH_CHECK(ctx);
     }
     {
         b2q_timed_launch tl(ctx, B2Q_KIND_OTHER, 8.0 * (double)p->elements, st);
-        mt_qdq_kernel<<<(unsigned)p->n_items, B2Q_THREADS, 0, st>>>(p->d_tensors, p->d_items, cur, nxt, p->n_groups,
+        mt_qdq_kernel<<<(unsigned)p->n_items, B2Q_THREADS, 0, st>>>(p->d_tensors, p->d_items, p->d_stat, p->d_epoch,
                                                                     do_reduce, is_train ? 1 : 0, ctx->fast_div);
         B2Q_LAUNCH_CHECK(ctx);
     }
-    if (do_reduce) p->parity++;   // otherwise `cur` was not touched and is still all zero
     return 0;
 }
 

@@ -25,12 +25,13 @@
 
 #define B2Q_PEER_MAX_RANKS 16
 #define B2Q_PEER_SLOTS 64
-#define B2Q_PEER_BYTES (B2Q_PEER_SLOTS * B2Q_PEER_MAX_RANKS * 8)
+#define B2Q_PEER_BOX_BYTES (B2Q_PEER_SLOTS * B2Q_PEER_MAX_RANKS * 8)
+#define B2Q_PEER_BYTES (B2Q_PEER_BOX_BYTES + 256)   // + device-side sequence counters (so CUDA graphs can replay)
 
 struct PeerBoxes {
     unsigned long long* box[B2Q_PEER_MAX_RANKS];
     int rank, world;
-    unsigned int seq;
+    unsigned int* counters;   // own mailbox + B2Q_PEER_BOX_BYTES: [0] calls so far, [1] sequence of the call in flight
 };
 
 __device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
@@ -86,15 +87,21 @@ reduce_peer_kernel(const float* __restrict__ x, FlatSplit sp, b2q_slot* slot, co
     for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) m = fmaxf(m, (float)__ldcg(&slot->partial[i]));
     const float tot = (float)block_reduce<true>((double)m, smem);
     __shared__ float s_tot;
+    __shared__ unsigned int s_seq;
     if (threadIdx.x == 0) {
         s_tot = tot;
         slot->scale[0] = aux[0];   // snapshot of the old threshold for the sweep
         slot->ticket = 0;
+        // the sequence number lives on the device (every rank issues the same calls, so the counters stay in step);
+        // a CUDA graph that replays this kernel therefore publishes fresh numbers every time
+        s_seq = pb.counters[0] + 1u;
+        pb.counters[0] = s_seq;
+        pb.counters[1] = s_seq;
     }
     __syncthreads();
     if ((int)threadIdx.x < pb.world) {   // one lane per destination rank: 8-byte P2P store
-        const unsigned long long word = ((unsigned long long)pb.seq << 32) | __float_as_uint(s_tot);
-        st_sys_u64(pb.box[threadIdx.x] + (size_t)(pb.seq % B2Q_PEER_SLOTS) * B2Q_PEER_MAX_RANKS + pb.rank, word);
+        const unsigned long long word = ((unsigned long long)s_seq << 32) | __float_as_uint(s_tot);
+        st_sys_u64(pb.box[threadIdx.x] + (size_t)(s_seq % B2Q_PEER_SLOTS) * B2Q_PEER_MAX_RANKS + pb.rank, word);
     }
     __threadfence_system();
 }
@@ -103,9 +110,11 @@ reduce_peer_kernel(const float* __restrict__ x, FlatSplit sp, b2q_slot* slot, co
 template <bool CLIP_SYM, int UNROLL, int LDPOL, int STPOL>
 __global__ void __launch_bounds__(B2Q_THREADS)
 qdq_peer_kernel(const float* __restrict__ x, float* __restrict__ y, FlatSplit sp, const unsigned long long* mybox,
-                int world, unsigned int seq, const float* aux_old, UpdateArgs u, float qlevel, int fast, int reverse) {
+                int world, const unsigned int* counters, const float* aux_old, UpdateArgs u, float qlevel, int fast,
+                int reverse) {
     __shared__ float s_stat;
     if (threadIdx.x < 32) {
+        const unsigned int seq = counters[1];   // written by this call's reduction kernel (same stream)
         float v = 0.f;
         if ((int)threadIdx.x < world) {
             const unsigned long long* p = mybox + (size_t)(seq % B2Q_PEER_SLOTS) * B2Q_PEER_MAX_RANKS + threadIdx.x;
@@ -214,7 +223,7 @@ int b2q_peer_minmax_quant_fwd_f32(b2q_ctx* ctx, int variant, const float* x, flo
     B2Q_REQUIRE(x && y && aux && mailboxes && n >= 1, "bad argument");
     B2Q_REQUIRE(variant == 0 || variant == 1, "variant must be 0 or 1");
     B2Q_REQUIRE(world >= 1 && world <= B2Q_PEER_MAX_RANKS && rank >= 0 && rank < world, "bad rank / world");
-    B2Q_REQUIRE(sequence != 0, "sequence numbers start at 1 (0 marks an empty mailbox entry)");
+    (void)sequence;   // kept in the ABI for logging; the authoritative counter is on the device
     cudaStream_t st = (cudaStream_t)stream;
     FlatSplit sp = b2q_flat_split(x, n);
     B2Q_REQUIRE(same_misalignment(x, y) && sp.head <= B2Q_THREADS, "peer path needs equally aligned float32 buffers");
@@ -224,7 +233,8 @@ int b2q_peer_minmax_quant_fwd_f32(b2q_ctx* ctx, int variant, const float* x, flo
         B2Q_REQUIRE(mailboxes[r] != nullptr, "null mailbox pointer");
         pb.box[r] = (unsigned long long*)mailboxes[r];
     }
-    pb.rank = rank; pb.world = world; pb.seq = sequence;
+    pb.rank = rank; pb.world = world;
+    pb.counters = (unsigned int*)((char*)mailboxes[rank] + B2Q_PEER_BOX_BYTES);
     b2q_slot* slot = b2q_take_slot(ctx);
     {
         const int64_t grid = b2q_flat_grid(ctx, sp.n8, B2Q_REDUCE_UNROLL, ctx->reduce_blocks_per_sm);
@@ -243,10 +253,10 @@ int b2q_peer_minmax_quant_fwd_f32(b2q_ctx* ctx, int variant, const float* x, flo
         b2q_timed_launch tl(ctx, B2Q_KIND_QDQ_HOT, 8.0 * (double)n, st);
         if (variant == 1)
             qdq_peer_kernel<true, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, B2Q_QDQ_STPOL><<<(unsigned)grid, B2Q_THREADS, 0, st>>>(
-                x, y, sp, mybox, world, sequence, slot->scale, u, 127.f, ctx->fast_div, rev);
+                x, y, sp, mybox, world, pb.counters, slot->scale, u, 127.f, ctx->fast_div, rev);
         else
             qdq_peer_kernel<false, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, B2Q_QDQ_STPOL><<<(unsigned)grid, B2Q_THREADS, 0, st>>>(
-                x, y, sp, mybox, world, sequence, slot->scale, u, 127.f, ctx->fast_div, rev);
+                x, y, sp, mybox, world, pb.counters, slot->scale, u, 127.f, ctx->fast_div, rev);
         B2Q_LAUNCH_CHECK(ctx);
     }
     return 0;

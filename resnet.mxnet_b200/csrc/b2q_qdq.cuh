@@ -137,7 +137,9 @@ qdq_flat_hot_kernel(const float* __restrict__ x, float* __restrict__ y, FlatSpli
         float stat;
         if (d.is_max) {
             // one epoch-tagged word, read by every thread (broadcast L2 hit): no shared memory, no barrier
-            stat = __uint_as_float((unsigned int)(*d.max64 & 0xffffffffull));
+            const unsigned long long word = *d.max64;
+            stat = __uint_as_float((unsigned int)(word & 0xffffffffull));
+            if (blockIdx.x == 0 && threadIdx.x == 0) *d.epoch = (unsigned int)(word >> 32);   // consume the tag
         } else {
             // sums: every block combines the double partials in the same fixed order
             __shared__ double smem[32];
@@ -454,12 +456,12 @@ template <bool IS_MAX>
     FlatSplit sp = b2q_flat_split(x, n);
     if (!same_misalignment(x, y) || sp.head > B2Q_THREADS) return 0;
     int np = 0;
-    unsigned int epoch = 0;
-    int rc = launch_reduce_deferred<IS_MAX>(ctx, slot, x, n, u, st, &np, &epoch);
+    int rc = launch_reduce_deferred<IS_MAX>(ctx, slot, x, n, u, st, &np);
     if (rc || np == 0) return rc;
     DeferredUpdate d;
     d.partial = slot->partial;
     d.max64 = &slot->max64;
+    d.epoch = &slot->epoch;
     d.aux_old = slot->scale;
     d.n_partials = np;
     d.is_max = IS_MAX ? 1 : 0;

@@ -59,8 +59,7 @@ __device__ __forceinline__ void acc8(double& a, float& m, const f8& r) {
 // ------------------------------------------------------------------------------------------------
 template <bool IS_MAX, int UNROLL, int LDPOL, bool FINALIZE>
 __global__ void __launch_bounds__(B2Q_THREADS)
-reduce_flat_kernel(const float* __restrict__ x, FlatSplit sp, b2q_slot* slot, UpdateArgs u, float count,
-                   unsigned int epoch) {
+reduce_flat_kernel(const float* __restrict__ x, FlatSplit sp, b2q_slot* slot, UpdateArgs u, float count) {
     __shared__ double smem[32];
     __shared__ unsigned int s_ticket;
     double acc = 0.0;
@@ -91,8 +90,13 @@ reduce_flat_kernel(const float* __restrict__ x, FlatSplit sp, b2q_slot* slot, Up
     if (!FINALIZE) {
         // deferred update: the consumer kernel combines the partials (see DeferredUpdate)
         if (threadIdx.x == 0) {
-            if (IS_MAX) atomicMax(&slot->max64, ((unsigned long long)epoch << 32) | __float_as_uint((float)r));
-            else slot->partial[blockIdx.x] = r;
+            if (IS_MAX) {
+                // tag = slot->epoch + 1: strictly newer than anything the word holds, so no reset is ever needed
+                const unsigned long long tag = (unsigned long long)(slot->epoch + 1u) << 32;
+                atomicMax(&slot->max64, tag | __float_as_uint((float)r));
+            } else {
+                slot->partial[blockIdx.x] = r;
+            }
             if (blockIdx.x == 0 && u.aux) slot->scale[0] = u.aux[0];   // snapshot of the old threshold
         }
         return;
@@ -272,18 +276,15 @@ static inline int64_t b2q_flat_grid(const b2q_ctx* ctx, int64_t n8, int unroll, 
 // partials through *n_partials (0: tensor not eligible, caller must use launch_reduce).
 template <bool IS_MAX>
 static int launch_reduce_deferred(b2q_ctx* ctx, b2q_slot* slot, const float* x, int64_t n, UpdateArgs u,
-                                  cudaStream_t st, int* n_partials, unsigned int* epoch_out) {
+                                  cudaStream_t st, int* n_partials) {
     *n_partials = 0;
-    // strictly increasing per slot, so a newer launch always wins the atomicMax over whatever the slot held before
-    const unsigned int epoch = __atomic_add_fetch(&ctx->slot_epoch[slot - ctx->slots], 1u, __ATOMIC_RELAXED);
-    *epoch_out = epoch;
     FlatSplit sp = b2q_flat_split(x, n);
     if (sp.head > B2Q_THREADS) return 0;
     const int64_t grid = b2q_flat_grid(ctx, sp.n8, B2Q_REDUCE_UNROLL,
                                        IS_MAX ? ctx->reduce_deferred_blocks_per_sm : ctx->reduce_blocks_per_sm);
     b2q_timed_launch tl(ctx, B2Q_KIND_REDUCE_FLAT, 4.0 * (double)n, st);
     reduce_flat_kernel<IS_MAX, B2Q_REDUCE_UNROLL, B2Q_REDUCE_LDPOL, false>
-        <<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, sp, slot, u, (float)n, epoch);
+        <<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, sp, slot, u, (float)n);
     B2Q_LAUNCH_CHECK(ctx);
     *n_partials = (int)grid;
     return 0;
@@ -301,7 +302,7 @@ static int launch_reduce(b2q_ctx* ctx, b2q_slot* slot, const float* x, int64_t o
             const int64_t grid = b2q_flat_grid(ctx, sp.n8, B2Q_REDUCE_UNROLL, ctx->reduce_blocks_per_sm);
             b2q_timed_launch tl(ctx, B2Q_KIND_REDUCE_FLAT, 4.0 * (double)n, st);
             reduce_flat_kernel<IS_MAX, B2Q_REDUCE_UNROLL, B2Q_REDUCE_LDPOL, true>
-                <<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, sp, slot, u, (float)n, 0u);
+                <<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, sp, slot, u, (float)n);
             B2Q_LAUNCH_CHECK(ctx);
             return 0;
         }

@@ -64,7 +64,7 @@ static void sweep_reduce(int64_t n, int nbuf, int reps) {
             FlatSplit sp = b2q_flat_split(x, n);
             const int64_t tile = (int64_t)B2Q_THREADS * U;
             int64_t grid = std::min<int64_t>((sp.n8 + tile - 1) / tile, (int64_t)g_sms * bps);
-            reduce_flat_kernel<true, U, L, FIN><<<(unsigned)grid, B2Q_THREADS>>>(x, sp, g_slot, u, (float)n, ++g_epoch);
+            reduce_flat_kernel<true, U, L, FIN><<<(unsigned)grid, B2Q_THREADS>>>(x, sp, g_slot, u, (float)n);
         }, reps);
         report(FIN ? "reduce" : "reduce_nofin", n, U, L, 0, bps, 4.0, ms);
     }
@@ -101,14 +101,14 @@ static void sweep_pair(int64_t n, int nbuf, int reps, int rbps, int qbps, int re
         int64_t qgrid = std::min<int64_t>((sp.n8 + B2Q_THREADS * 2 - 1) / (B2Q_THREADS * 2), (int64_t)g_sms * qbps);
         QdqArgs a = {g_thr, nullptr, 0.f, 0.f, 127.f, 1, nullptr, B2Q_CLIP_SYM, 1, B2Q_REQ_WRITE};
         if (DEFER) {
-            reduce_flat_kernel<true, 4, 0, false><<<(unsigned)rgrid, B2Q_THREADS>>>(x, sp, g_slot, u, (float)n, ++g_epoch);
+            reduce_flat_kernel<true, 4, 0, false><<<(unsigned)rgrid, B2Q_THREADS>>>(x, sp, g_slot, u, (float)n);
             DeferredUpdate d;
-            d.partial = g_slot->partial; d.max64 = &g_slot->max64; d.aux_old = g_slot->scale; d.n_partials = (int)rgrid; d.is_max = 1;
+            d.partial = g_slot->partial; d.max64 = &g_slot->max64; d.epoch = &g_slot->epoch; d.aux_old = g_slot->scale; d.n_partials = (int)rgrid; d.is_max = 1;
             d.count = (float)n; d.u = u;
             qdq_flat_hot_kernel<true, 2, 2, 0, true><<<(unsigned)qgrid, B2Q_THREADS>>>(x, y, sp, a, reverse, d, 0);
         } else {
             DeferredUpdate none = {};
-            reduce_flat_kernel<true, 4, 0, true><<<(unsigned)rgrid, B2Q_THREADS>>>(x, sp, g_slot, u, (float)n, 0u);
+            reduce_flat_kernel<true, 4, 0, true><<<(unsigned)rgrid, B2Q_THREADS>>>(x, sp, g_slot, u, (float)n);
             qdq_flat_hot_kernel<true, 2, 2, 0, false><<<(unsigned)qgrid, B2Q_THREADS>>>(x, y, sp, a, reverse, none, 0);
         }
     }, reps);

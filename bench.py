@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--profile", action="store_true",
+                    help="profiling aid: only the per-node eager step (warm-up + timed), nothing else")
     return ap.parse_args()
 
 
@@ -374,6 +376,9 @@ def main():
     ms = ms_eager
     timings = {mode: ms_eager / args.steps}
 
+    if args.profile:
+        group = None
+        args.no_graph = args.no_e2e = args.no_cpu = True
     if group is not None:
         for _ in range(3):
             step_multi()
@@ -385,7 +390,8 @@ def main():
 
     # ---- the same steps replayed from a CUDA graph (single GPU; the graph holds our kernels only) ----
     ms_graph = None
-    if world == 1 and not args.no_graph:
+    graph_ok = world == 1 or os.environ.get("B2Q_GRAPH_MULTI", "1") == "1"   # NCCL collectives are capturable
+    if graph_ok and not args.no_graph:
         for label, fn_ in (("cuda_graph, one CustomOp call per node", step),
                            ("cuda_graph, weight nodes batched (WeightGroup)", step_multi)):
             if fn_ is step_multi and group is None:
@@ -426,7 +432,7 @@ def main():
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     ctx.set_option("timing", 1)
     ctx.timing_read(0, reset=True)
-    for _ in range(min(args.steps, 5)):
+    for _ in range(0 if args.profile else min(args.steps, 5)):
         step()
     torch.cuda.synchronize()
     kinds = {1: "reduce_flat (max|x| + EMA update)", 2: "qdq_flat_hot (QDQ sweep)", 3: "bwd_flat (STE copy)",

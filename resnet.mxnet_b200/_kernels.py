@@ -4,6 +4,8 @@ anything exporting DLPack), views them zero-copy and enqueues CUDA kernels on th
 Host (CPU) arrays are accepted by the operators that have a host-buffer entry point (the "e2e" path of
 bench.py): they are staged through device memory by the library; nothing is ever computed on the CPU.
 """
+import functools
+
 import numpy as np
 
 from . import _lib
@@ -21,16 +23,18 @@ def _req(r):
         raise ValueError("unknown req %r (expected one of %s)" % (r, sorted(REQ)))
 
 
+@functools.lru_cache(maxsize=256)
 def _f32(v):
     """Python double -> float32 the way MXNet applies scalar operands."""
     return float(np.float32(v))
 
 
 def _same_place(*bufs):
-    dev = {(b.on_device, b.device_id if b.on_device else 0) for b in bufs}
-    if len(dev) != 1:
-        raise ValueError("all tensors of one operator call must live on the same device")
-    return bufs[0].on_device, bufs[0].device_id
+    first = bufs[0]
+    for b in bufs:
+        if b.on_device != first.on_device or (b.on_device and b.device_id != first.device_id):
+            raise ValueError("all tensors of one operator call must live on the same device")
+    return first.on_device, first.device_id
 
 
 def _rows_cols(shape):

@@ -135,9 +135,10 @@ class Context(object):
         if rc != 0:
             raise B2QError("b2q_create(device=%d) failed: %s" % (self.device, last_error()))
         self.handle = h
+        self._fn = {name: getattr(self.lib, name) for name in _CTX_FUNCS}
 
     def call(self, name, *args):
-        rc = getattr(self.lib, name)(self.handle, *args)
+        rc = self._fn[name](self.handle, *args)
         if rc != 0:
             raise B2QError("%s failed (%d): %s" % (name, rc, last_error()))
 

@@ -107,5 +107,12 @@ def current_stream(buf):
     """CUDA stream to launch on for ``buf``'s device: torch's current stream when torch owns the memory,
     the legacy default stream (0) otherwise (MXNet: the shim synchronises)."""
     if torch is not None and isinstance(buf.keep, torch.Tensor) and buf.on_device:
-        return torch.cuda.current_stream(buf.device_id).cuda_stream
+        return _raw_stream(buf.device_id)
     return 0
+
+
+def _raw_stream(device_id):
+    try:
+        return torch._C._cuda_getCurrentRawStream(device_id)
+    except AttributeError:  # pragma: no cover - older torch
+        return torch.cuda.current_stream(device_id).cuda_stream

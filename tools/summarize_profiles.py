@@ -54,7 +54,7 @@ def launches(tag):
             f.write("%d,%s,%s,%s,%.3f\n" % (i, short(r["Kernel Name"]), r["Grid Size"].replace(",", " "),
                                             r["Block Size"].replace(",", " "), float(r["Metric Value"].replace(",", "")) / 1e3))
     tot = sum(v[1] for k, v in agg.items() if "at::" not in k)
-    md = ["# %s: ncu launch list of `bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-graph`" % tag, "",
+    md = ["# %s: ncu launch list of `bench.py --steps 2 --warmup 3 --profile`" % tag, "",
           "`ncu --metrics gpu__time_duration.sum --clock-control none` (cold-cache, serialised: shares, not absolutes).",
           "", "| kernel | launches | total us | share of our kernels | avg us |", "|---|---|---|---|---|"]
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):

@@ -445,16 +445,21 @@ def main():
                              "achieved_gbs": kbytes / kms / 1e6, "frac_of_peak": kbytes / kms / 1e6 / peak_gbs}
     ctx.timing_read(0, reset=True)
     ctx.set_option("timing", 0)
-    traffic = None
+    traffic, traffic_note = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_dominant_kernel.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            tj = json.load(f)
+        traffic = tj.get("dram_bytes_per_launch")
+        traffic_note = {"source": tj.get("source"), "launch_alg_bytes": tj.get("alg_bytes_of_this_launch"),
+                        "launch_duration_us": tj.get("duration_us"),
+                        "note": "ncu dram__bytes_read+write of one captured launch (a 256x64x56x56 activation); compare "
+                                "with launch_alg_bytes, not with the average alg_bytes_per_launch"}
     except Exception:
         pass
     dom = kernels.get(kinds[2], {})
     roofline = {"bound": "hbm", "kernel": "qdq_flat_hot_kernel", "achieved": dom.get("achieved_gbs"),
                 "peak": peak_gbs, "unit": "GB/s", "frac": dom.get("frac_of_peak"), "traffic": traffic,
-                "peak_source": peak_src,
+                "peak_source": peak_src, "traffic_detail": traffic_note,
                 "alg_bytes_per_launch": (dom.get("alg_bytes_total", 0) / dom["launches"]) if dom else None,
                 "avg_launch_ms": (dom.get("ms_total", 0) / dom["launches"]) if dom else None}
 

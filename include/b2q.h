@@ -121,8 +121,10 @@ int b2q_mask_bwd_f32(b2q_ctx* ctx, const float* x, const float* dy, float* dx, i
  * ClipGrad_Quantization_int8.forward, non-delay branch symbol/clip_grad_quantization_int8.py:19-51
  * variant 0 = Quantization_int8_V2, 1 = ClipGrad_Quantization_int8.
  * aux: minmax state [1] or [rows] (per-channel weight).  rows*cols = numel.  init: ClipGrad first-batch flag.
- * stat_out (may be NULL): if non-NULL the function ONLY reduces (max|x| -> stat_out[groups]) and returns,
- * so the caller can allreduce(max) across ranks and finish with b2q_minmax_quant_finish_f32.          */
+ * Whole-tensor case = two launches: a reduction that publishes max|x| with one tagged atomicMax per block, and a
+ * QDQ sweep whose blocks derive the (EMA-updated) threshold in registers and whose block 0 writes aux.
+ * For data-parallel training b2q_minmax_quant_stat_f32 only reduces (max|x| -> stat_out[groups]) so the caller can
+ * allreduce(max) across ranks and finish with b2q_minmax_quant_finish_f32 (or see b2q_peer_* below).    */
 int b2q_minmax_quant_fwd_f32(b2q_ctx* ctx, int variant, const float* x, float* y, float* aux,
                              int64_t rows, int64_t cols, int is_weight, int per_channel, int is_train,
                              int init, float ema_decay, float one_minus_decay, int req, void* stream);
@@ -219,7 +221,8 @@ int b2q_multi_weight_ste_bwd_f32(b2q_ctx* ctx, b2q_multi_plan* plan, void* strea
  * (symbol/quant_ops.py:32-40, symbol/clip_grad_quantization_int8.py:37-51) with max|x| taken over all ranks.
  * mailboxes[r] = rank r's mailbox as mapped on THIS device (own: b2q_peer_mailbox_create; peers: the 64-byte CUDA
  * IPC handle exchanged out of band and opened with b2q_peer_mailbox_open).  All ranks must issue the same sequence
- * of calls with sequence = 1, 2, 3, ...; a peer that never arrives makes the kernel trap after ~2 s.            */
+ * of calls; the sequence number itself is kept on the device (so a CUDA graph can replay the pair), the `sequence`
+ * argument is informational.  A peer that never arrives makes the kernel trap after ~2 s instead of hanging.   */
 int b2q_peer_mailbox_bytes(void);
 int b2q_peer_mailbox_create(b2q_ctx* ctx, void** mailbox, void* ipc_handle_out /* 64 bytes */);
 int b2q_peer_mailbox_open(b2q_ctx* ctx, const void* ipc_handle /* 64 bytes */, void** peer_ptr);

@@ -297,7 +297,10 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (the quantization operators have no CPU fallback)")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        # a short collective timeout: if one rank dies, the others abort instead of waiting 10 minutes
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local),
+                                timeout=datetime.timedelta(seconds=int(os.environ.get("B2Q_NCCL_TIMEOUT", "180"))))
     device = torch.device("cuda", local)
 
     import b200quant  # noqa: F401
@@ -337,8 +340,11 @@ def main():
         for nd, view in zip(wn, bucket.views):
             nd["dx"] = view
 
-    def step():
+    def step_local():
         run_step(nodes)
+
+    def step():
+        step_local()
         if bucket is not None:
             bucket.allreduce()
 
@@ -351,13 +357,16 @@ def main():
         group = WeightGroup([nd["op"] for nd in wnodes], [nd["x"] for nd in wnodes], [nd["y"] for nd in wnodes],
                             [nd["aux"] for nd in wnodes], [nd["dy"] for nd in wnodes], [nd["dx"] for nd in wnodes])
 
-    def step_multi():
+    def step_multi_local():
         group.forward(True)
         for nd in anodes:
             nd["op"].forward(True, ["write"], [nd["x"]], [nd["y"]], [nd["aux"]])
         for nd in reversed(anodes):
             nd["op"].backward(["write"], [nd["dy"]], [nd["x"]], [nd["y"]], [nd["dx"]], [nd["aux"]])
         group.backward()
+
+    def step_multi():
+        step_multi_local()
         if bucket is not None:
             bucket.allreduce()
 
@@ -390,27 +399,46 @@ def main():
 
     # ---- the same steps replayed from a CUDA graph (single GPU; the graph holds our kernels only) ----
     ms_graph = None
-    graph_ok = world == 1 or os.environ.get("B2Q_GRAPH_MULTI", "1") == "1"   # NCCL collectives are capturable
+    # multi-GPU: only our own kernels are captured (the peer-memory exchange needs no NCCL call); the single gradient
+    # allreduce stays an eager NCCL call after each replay.  With the NCCL threshold exchange nothing is captured.
+    graph_ok = world == 1 or (exchange.startswith("fused peer") and os.environ.get("B2Q_GRAPH_MULTI", "1") == "1")
     if graph_ok and not args.no_graph:
-        for label, fn_ in (("cuda_graph, one CustomOp call per node", step),
-                           ("cuda_graph, weight nodes batched (WeightGroup)", step_multi)):
-            if fn_ is step_multi and group is None:
+        for label, fn_ in (("cuda_graph, one CustomOp call per node", step_local),
+                           ("cuda_graph, weight nodes batched (WeightGroup)", step_multi_local)):
+            if fn_ is step_multi_local and group is None:
                 continue
             try:
-                graph = torch.cuda.CUDAGraph()
-                s = torch.cuda.Stream()
-                s.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(s):
-                    fn_()
-                    torch.cuda.synchronize()
-                    l0 = ctx.launch_count()
-                    with torch.cuda.graph(graph, stream=s):
+                graph, err = None, None
+                try:
+                    graph = torch.cuda.CUDAGraph()
+                    s = torch.cuda.Stream()
+                    s.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(s):
                         fn_()
-                    captured = ctx.launch_count() - l0
-                torch.cuda.current_stream().wait_stream(s)
-                for _ in range(3):
+                        torch.cuda.synchronize()
+                        l0 = ctx.launch_count()
+                        with torch.cuda.graph(graph, stream=s):
+                            fn_()
+                        captured = ctx.launch_count() - l0
+                    torch.cuda.current_stream().wait_stream(s)
+                except Exception as e:  # pragma: no cover
+                    graph, err = None, e
+                if world > 1:   # every rank must take the same path, or the peer exchange would wait forever
+                    okflag = torch.tensor([0 if graph is None else 1], device="cuda")
+                    dist.all_reduce(okflag, op=dist.ReduceOp.MIN)
+                    if int(okflag.item()) == 0 and graph is not None:
+                        graph, err = None, RuntimeError("capture failed on another rank")
+                if graph is None:
+                    raise err
+
+                def replay(graph=graph):
                     graph.replay()
-                t = time_steps(torch, dist, graph.replay, args.steps, world)
+                    if bucket is not None:
+                        bucket.allreduce()
+
+                for _ in range(3):
+                    replay()
+                t = time_steps(torch, dist, replay, args.steps, world)
                 timings[label] = t / args.steps
                 if label.endswith("per node"):
                     ms_graph = t

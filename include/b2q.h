@@ -222,7 +222,7 @@ int b2q_multi_weight_ste_bwd_f32(b2q_ctx* ctx, b2q_multi_plan* plan, void* strea
  * mailboxes[r] = rank r's mailbox as mapped on THIS device (own: b2q_peer_mailbox_create; peers: the 64-byte CUDA
  * IPC handle exchanged out of band and opened with b2q_peer_mailbox_open).  All ranks must issue the same sequence
  * of calls; the sequence number itself is kept on the device (so a CUDA graph can replay the pair), the `sequence`
- * argument is informational.  A peer that never arrives makes the kernel trap after ~2 s instead of hanging.   */
+ * argument is informational.  A peer that never arrives makes the kernel trap after ~20 s instead of hanging.   */
 int b2q_peer_mailbox_bytes(void);
 int b2q_peer_mailbox_create(b2q_ctx* ctx, void** mailbox, void* ipc_handle_out /* 64 bytes */);
 int b2q_peer_mailbox_open(b2q_ctx* ctx, const void* ipc_handle /* 64 bytes */, void** peer_ptr);

@@ -12,7 +12,7 @@
 // Every rank launches the same sequence of calls (data parallel), so rank A's sweep only ever waits for kernels that
 // rank B has already enqueued or will enqueue without depending on A's later work: progress is guaranteed as long as
 // all ranks run on different GPUs.  A slot is reused after 64 calls; no rank can be more than one call ahead because
-// each call needs every rank's value.  The poll is bounded: after ~2 s it traps (CUDA error) instead of hanging.
+// each call needs every rank's value.  The poll is bounded: after ~20 s it traps (CUDA error) instead of hanging.
 #include <cstring>
 
 #include "b2q_common.cuh"
@@ -123,7 +123,7 @@ qdq_peer_kernel(const float* __restrict__ x, float* __restrict__ y, FlatSplit sp
             while ((unsigned int)(w >> 32) != seq) {
                 __nanosleep(64);
                 w = ld_sys_u64(p);
-                if (++spins > (1u << 21)) __trap();   // a peer never arrived: fail loudly instead of hanging
+                if (++spins > (1u << 24)) __trap();   // a peer never arrived: fail loudly instead of hanging
             }
             v = __uint_as_float((unsigned int)(w & 0xffffffffull));
         }

@@ -3,11 +3,11 @@
 N=${1:-2}
 mkdir -p gpurun_out
 RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
-timeout 300 $RUN --master-port 29511 tests/multi_gpu_check.py > gpurun_out/multi_check_$N.log 2>&1
+timeout 150 $RUN --master-port 29511 tests/multi_gpu_check.py > gpurun_out/multi_check_$N.log 2>&1
 echo "multi_check rc=$?" >> gpurun_out/multi_check_$N.log
-B2Q_EXCHANGE=nccl timeout 600 $RUN --master-port 29512 bench.py --gpus $N --steps 10 --warmup 3 --no-cpu --e2e-steps 2 \
+B2Q_EXCHANGE=nccl timeout 200 $RUN --master-port 29512 bench.py --gpus $N --steps 10 --warmup 3 --no-cpu --e2e-steps 2 \
     > gpurun_out/bench_${N}gpu_nccl.json 2> gpurun_out/bench_${N}gpu_nccl.err
-B2Q_EXCHANGE=peer timeout 600 $RUN --master-port 29513 bench.py --gpus $N --steps 10 --warmup 3 --no-cpu --e2e-steps 2 \
+B2Q_EXCHANGE=peer timeout 200 $RUN --master-port 29513 bench.py --gpus $N --steps 10 --warmup 3 --no-cpu --e2e-steps 2 \
     > gpurun_out/bench_${N}gpu_peer.json 2> gpurun_out/bench_${N}gpu_peer.err
 tail -3 gpurun_out/multi_check_$N.log
 for f in gpurun_out/bench_${N}gpu_nccl gpurun_out/bench_${N}gpu_peer; do

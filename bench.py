@@ -357,18 +357,36 @@ def main():
         group = WeightGroup([nd["op"] for nd in wnodes], [nd["x"] for nd in wnodes], [nd["y"] for nd in wnodes],
                             [nd["aux"] for nd in wnodes], [nd["dy"] for nd in wnodes], [nd["dx"] for nd in wnodes])
 
-    def step_multi_local():
+    # The weight gradients are complete after group.backward(); their allreduce(sum) then runs on a side stream while
+    # the activation backward sweeps continue (standard overlap of gradient communication with the backward pass).
+    side = torch.cuda.Stream() if bucket is not None else None
+
+    def part1():   # forward of everything + weight backward
         group.forward(True)
         for nd in anodes:
             nd["op"].forward(True, ["write"], [nd["x"]], [nd["y"]], [nd["aux"]])
-        for nd in reversed(anodes):
-            nd["op"].backward(["write"], [nd["dy"]], [nd["x"]], [nd["y"]], [nd["dx"]], [nd["aux"]])
         group.backward()
 
-    def step_multi():
-        step_multi_local()
+    def part2():   # activation backward
+        for nd in reversed(anodes):
+            nd["op"].backward(["write"], [nd["dy"]], [nd["x"]], [nd["y"]], [nd["dx"]], [nd["aux"]])
+
+    def overlapped(p1, p2):
+        p1()
         if bucket is not None:
-            bucket.allreduce()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                bucket.allreduce()
+        p2()
+        if bucket is not None:
+            torch.cuda.current_stream().wait_stream(side)
+
+    def step_multi_local():
+        part1()
+        part2()
+
+    def step_multi():
+        overlapped(part1, part2)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -407,20 +425,27 @@ def main():
                            ("cuda_graph, weight nodes batched (WeightGroup)", step_multi_local)):
             if fn_ is step_multi_local and group is None:
                 continue
+            parts = [fn_] if (bucket is None or fn_ is step_local) else [part1, part2]
             try:
                 graph, err = None, None
                 try:
-                    graph = torch.cuda.CUDAGraph()
+                    graphs = []
+                    captured = 0
                     s = torch.cuda.Stream()
                     s.wait_stream(torch.cuda.current_stream())
                     with torch.cuda.stream(s):
-                        fn_()
+                        for part in parts:
+                            part()
                         torch.cuda.synchronize()
-                        l0 = ctx.launch_count()
-                        with torch.cuda.graph(graph, stream=s):
-                            fn_()
-                        captured = ctx.launch_count() - l0
+                        for part in parts:
+                            g_ = torch.cuda.CUDAGraph()
+                            l0 = ctx.launch_count()
+                            with torch.cuda.graph(g_, stream=s):
+                                part()
+                            captured += ctx.launch_count() - l0
+                            graphs.append(g_)
                     torch.cuda.current_stream().wait_stream(s)
+                    graph = graphs
                 except Exception as e:  # pragma: no cover
                     graph, err = None, e
                 if world > 1:   # every rank must take the same path, or the peer exchange would wait forever
@@ -431,10 +456,13 @@ def main():
                 if graph is None:
                     raise err
 
-                def replay(graph=graph):
-                    graph.replay()
-                    if bucket is not None:
-                        bucket.allreduce()
+                def replay(graphs=graph):
+                    if len(graphs) == 2:
+                        overlapped(graphs[0].replay, graphs[1].replay)
+                    else:
+                        graphs[0].replay()
+                        if bucket is not None:
+                            bucket.allreduce()
 
                 for _ in range(3):
                     replay()

@@ -260,6 +260,14 @@ int b2q_minmax_quant_fwd_f32(b2q_ctx* ctx, int variant, const float* x, float* y
                                                  st, &done);
             if (rc || done) return rc;
         }
+        if (groups > 1) {   // per-channel weight: one warp per row does reduce + update + sweep in one launch
+            UpdateArgs ur = u;
+            ur.scale_out = nullptr;
+            QdqArgs ar = {nullptr, nullptr, 0.f, 0.f, 127.f, ctx->fast_div, nullptr, B2Q_CLIP_NONE, 1, eff_req};
+            int done = 0;
+            int rc = launch_rows_fused<true>(ctx, x, y, groups, inner, kNoPrescale, kNoBias, ur, ar, 0, st, &done);
+            if (rc || done) return rc;
+        }
         int rc = launch_reduce<true>(ctx, slot, x, outer, groups, inner, kNoPrescale, u, st);
         if (rc) return rc;
     }
@@ -328,6 +336,12 @@ int b2q_gdrq_fwd_f32(b2q_ctx* ctx, const float* x, float* y, float* alpha, int64
         if (groups == 1 && do_round && (req == B2Q_REQ_WRITE || req == B2Q_REQ_INPLACE)) {
             int done = 0;
             int rc = launch_fused_flat_fwd<false>(ctx, slot, x, y, outer * inner, u, qlevel, B2Q_CLIP_SYM, 0, st, &done);
+            if (rc || done) return rc;
+        }
+        if (groups > 1 && outer == 1) {   // grouped weight: warp per group, one launch
+            QdqArgs ar = {nullptr, nullptr, 0.f, 0.f, qlevel, ctx->fast_div, nullptr, B2Q_CLIP_WHERE_LE, do_round, req};
+            int done = 0;
+            int rc = launch_rows_fused<false>(ctx, x, y, groups, inner, kNoPrescale, kNoBias, u, ar, 0, st, &done);
             if (rc || done) return rc;
         }
         int rc = launch_reduce<false>(ctx, slot, x, outer, groups, inner, kNoPrescale, u, st);
@@ -409,6 +423,12 @@ int b2q_foldbn_weight_fwd_f32(b2q_ctx* ctx, const float* w, float* w_q, float* b
     u.write_aux = is_train ? 1 : 0;
     u.use_aux_as_scale = 0;
     u.aux = aux_weight;
+    if (per_channel) {   // warp per out-channel: prescale, 2*mean|w'|, clip, QDQ and the folded bias in one launch
+        QdqArgs ar = {nullptr, nullptr, 0.f, 0.f, 127.f, ctx->fast_div, nullptr, B2Q_CLIP_SYM, 1, B2Q_REQ_WRITE};
+        int done = 0;
+        int rc = launch_rows_fused<false>(ctx, w, w_q, cout, cols, ps, fb, u, ar, 0, st, &done);
+        if (rc || done) return rc;
+    }
     u.scale_out = slot->scale;
     int rc = launch_reduce<false>(ctx, slot, w, outer, groups, cols, ps, u, st);
     if (rc) return rc;

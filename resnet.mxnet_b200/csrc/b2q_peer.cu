@@ -107,7 +107,7 @@ reduce_peer_kernel(const float* __restrict__ x, FlatSplit sp, b2q_slot* slot, co
 }
 
 // kernel 2: QDQ sweep whose prologue gathers every rank's statistic from the local mailbox
-template <bool CLIP_SYM, int UNROLL, int LDPOL, int STPOL>
+template <int CLIP, int UNROLL, int LDPOL, int STPOL>
 __global__ void __launch_bounds__(B2Q_THREADS)
 qdq_peer_kernel(const float* __restrict__ x, float* __restrict__ y, FlatSplit sp, const unsigned long long* mybox,
                 int world, const unsigned int* counters, const float* aux_old, UpdateArgs u, float qlevel, int fast,
@@ -136,7 +136,7 @@ qdq_peer_kernel(const float* __restrict__ x, float* __restrict__ y, FlatSplit sp
     compute_update(u.mode, u.p0, u.p1, a_old, s_stat, fresh, next);
     const float T = next;
     if (blockIdx.x == 0 && threadIdx.x == 0) u.aux[0] = next;
-    const QScale s = make_qscale(T, qlevel, fast != 0 && !(CLIP_SYM && !(T >= 0.f)));
+    const QScale s = make_qscale(T, qlevel, fast != 0 && !(CLIP != B2Q_CLIP_NONE && !(T >= 0.f)));
     const float* xb = x + sp.head;
     float* yb = y + sp.head;
     const int64_t tile = (int64_t)B2Q_THREADS * UNROLL;
@@ -155,7 +155,7 @@ qdq_peer_kernel(const float* __restrict__ x, float* __restrict__ y, FlatSplit sp
             const int64_t i = base + (int64_t)k * B2Q_THREADS;
             if (i < sp.n8) {
                 f8 o;
-                qdq8<CLIP_SYM>(v[k], o, T, s);
+                qdq8<CLIP>(v[k], o, T, s);
                 st_f8<STPOL>(yb + 8 * i, o);
             }
         }
@@ -166,8 +166,7 @@ qdq_peer_kernel(const float* __restrict__ x, float* __restrict__ y, FlatSplit sp
         if (tid < sp.head) idx = tid;
         else if (tid - sp.head < sp.tail) idx = sp.head + 8 * sp.n8 + (tid - sp.head);
         if (idx >= 0) {
-            const float c = CLIP_SYM ? mx_clip(x[idx], -T, T) : x[idx];
-            y[idx] = __fmul_rn(quant_code(c, s), s.q);
+            y[idx] = __fmul_rn(quant_code_exact(clip_value(CLIP, x[idx], T), s.q), s.q);
         }
     }
 }
@@ -252,10 +251,10 @@ int b2q_peer_minmax_quant_fwd_f32(b2q_ctx* ctx, int variant, const float* x, flo
         const int rev = (ctx->reverse && n * 4 > ctx->reverse_min_bytes) ? 1 : 0;
         b2q_timed_launch tl(ctx, B2Q_KIND_QDQ_HOT, 8.0 * (double)n, st);
         if (variant == 1)
-            qdq_peer_kernel<true, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, B2Q_QDQ_STPOL><<<(unsigned)grid, B2Q_THREADS, 0, st>>>(
+            qdq_peer_kernel<B2Q_CLIP_SYM, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, B2Q_QDQ_STPOL><<<(unsigned)grid, B2Q_THREADS, 0, st>>>(
                 x, y, sp, mybox, world, pb.counters, slot->scale, u, 127.f, ctx->fast_div, rev);
         else
-            qdq_peer_kernel<false, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, B2Q_QDQ_STPOL><<<(unsigned)grid, B2Q_THREADS, 0, st>>>(
+            qdq_peer_kernel<B2Q_CLIP_NONE, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, B2Q_QDQ_STPOL><<<(unsigned)grid, B2Q_THREADS, 0, st>>>(
                 x, y, sp, mybox, world, pb.counters, slot->scale, u, 127.f, ctx->fast_div, rev);
         B2Q_LAUNCH_CHECK(ctx);
     }

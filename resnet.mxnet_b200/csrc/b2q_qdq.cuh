@@ -70,26 +70,6 @@ __device__ __forceinline__ float quant_code(float x, const QScale& s) {
     return c;
 }
 
-// Eight elements at once: one divergence point per 256-bit word instead of one per element.
-// CLIP_SYM uses min/max on the fast path, which equals mx.nd.clip for T >= 0 and non-NaN x; the caller
-// disables the fast path (r = NaN) when T < 0, and NaN inputs fail the safety test by themselves.
-template <bool CLIP_SYM>
-__device__ __forceinline__ void qdq8(const f8& in, f8& out, float Tc, const QScale& s) {
-    bool safe = true;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const float c = CLIP_SYM ? fminf(fmaxf(in.v[j], -Tc), Tc) : in.v[j];
-        out.v[j] = __fmul_rn(quant_code_try(c, s.r, safe), s.q);
-    }
-    if (!safe) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float c = CLIP_SYM ? mx_clip(in.v[j], -Tc, Tc) : in.v[j];
-            out.v[j] = __fmul_rn(quant_code_exact(c, s.q), s.q);
-        }
-    }
-}
-
 __device__ __forceinline__ float clip_value(int clip, float x, float T) {
     switch (clip) {
         case B2Q_CLIP_SYM: return mx_clip(x, -T, T);
@@ -98,6 +78,29 @@ __device__ __forceinline__ float clip_value(int clip, float x, float T) {
         case B2Q_CLIP_PACT: return (x < T) ? x : T;
         case B2Q_CLIP_WHERE_LT: return (fabsf(x) < T) ? x : __fmul_rn(T, mx_sign(x));
         default: return x;
+    }
+}
+
+// Clip on the fast path: min/max forms that equal the reference's comparison-based clips for non-NaN inputs and a
+// non-negative threshold (NaN inputs fail the safety test and are redone exactly; the caller disables the fast path
+// when the threshold is negative).
+template <int CLIP>
+__device__ __forceinline__ float clip_fast(float x, float T) {
+    if (CLIP == B2Q_CLIP_SYM || CLIP == B2Q_CLIP_WHERE_LE || CLIP == B2Q_CLIP_WHERE_LT) return fminf(fmaxf(x, -T), T);
+    if (CLIP == B2Q_CLIP_ZERO_T) return fminf(fmaxf(x, 0.f), T);
+    if (CLIP == B2Q_CLIP_PACT) return fminf(x, T);
+    return x;
+}
+
+// Eight elements at once: one divergence point per 256-bit word instead of one per element.
+template <int CLIP>
+__device__ __forceinline__ void qdq8(const f8& in, f8& out, float Tc, const QScale& s) {
+    bool safe = true;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) out.v[j] = __fmul_rn(quant_code_try(clip_fast<CLIP>(in.v[j], Tc), s.r, safe), s.q);
+    if (!safe) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) out.v[j] = __fmul_rn(quant_code_exact(clip_value(CLIP, in.v[j], Tc), s.q), s.q);
     }
 }
 
@@ -128,7 +131,7 @@ __device__ __forceinline__ float qdq_generic(const QdqArgs& a, float x, float Tc
 // tail of x is still in the 126 MB L2.  x is loaded evict-first (last use); y is stored plainly because the
 // convolution reads it next.
 // ------------------------------------------------------------------------------------------------
-template <bool CLIP_SYM, int UNROLL, int LDPOL, int STPOL, bool DEFERRED>
+template <int CLIP, int UNROLL, int LDPOL, int STPOL, bool DEFERRED>
 __global__ void __launch_bounds__(B2Q_THREADS)
 qdq_flat_hot_kernel(const float* __restrict__ x, float* __restrict__ y, FlatSplit sp, QdqArgs a, int reverse,
                     DeferredUpdate d, int clip_with_fresh) {
@@ -162,7 +165,8 @@ qdq_flat_hot_kernel(const float* __restrict__ x, float* __restrict__ y, FlatSpli
         T = a.thr ? __ldg(a.thr) : a.thr_imm;
         Tc = a.clip_thr ? __ldg(a.clip_thr) : (a.thr ? T : a.clip_imm);
     }
-    const QScale s = make_qscale(T, a.qlevel, a.fast != 0 && !(CLIP_SYM && !(Tc >= 0.f)));
+    const bool needs_pos = (CLIP != B2Q_CLIP_NONE && CLIP != B2Q_CLIP_PACT);
+    const QScale s = make_qscale(T, a.qlevel, a.fast != 0 && !(needs_pos && !(Tc >= 0.f)));
     const float* xb = x + sp.head;
     float* yb = y + sp.head;
     const int64_t tile = (int64_t)B2Q_THREADS * UNROLL;
@@ -181,7 +185,7 @@ qdq_flat_hot_kernel(const float* __restrict__ x, float* __restrict__ y, FlatSpli
             const int64_t i = base + (int64_t)k * B2Q_THREADS;
             if (i < sp.n8) {
                 f8 o;
-                qdq8<CLIP_SYM>(v[k], o, Tc, s);
+                qdq8<CLIP>(v[k], o, Tc, s);
                 st_f8<STPOL>(yb + 8 * i, o);
             }
         }
@@ -192,8 +196,7 @@ qdq_flat_hot_kernel(const float* __restrict__ x, float* __restrict__ y, FlatSpli
         if (tid < sp.head) idx = tid;
         else if (tid - sp.head < sp.tail) idx = sp.head + 8 * sp.n8 + (tid - sp.head);
         if (idx >= 0) {
-            const float c = CLIP_SYM ? mx_clip(x[idx], -Tc, Tc) : x[idx];
-            y[idx] = __fmul_rn(quant_code(c, s), s.q);
+            y[idx] = __fmul_rn(quant_code_exact(clip_value(CLIP, x[idx], Tc), s.q), s.q);
         }
     }
 }
@@ -282,24 +285,36 @@ qdq_seg_kernel(const float* __restrict__ x, float* __restrict__ y, SegPlan pl, P
         if (VEC == 4) {
             const float4* x4 = reinterpret_cast<const float4*>(xb);
             float4* y4 = reinterpret_cast<float4*>(yb);
-            for (int64_t i = (pc.i0 >> 2) + threadIdx.x; i < (pc.i1 >> 2); i += blockDim.x) {
-                float4 v = x4[i];
-                if (ps.gamma) { v.x = __fmul_rn(v.x, f); v.y = __fmul_rn(v.y, f); v.z = __fmul_rn(v.z, f); v.w = __fmul_rn(v.w, f); }
-                float4 r;
-                float cx, cy, cz, cw;
-                r.x = qdq_generic(a, v.x, Tc, qs, cx);
-                r.y = qdq_generic(a, v.y, Tc, qs, cy);
-                r.z = qdq_generic(a, v.z, Tc, qs, cz);
-                r.w = qdq_generic(a, v.w, Tc, qs, cw);
-                if (add) {
-                    const float4 old = y4[i];
-                    r.x = __fadd_rn(old.x, r.x); r.y = __fadd_rn(old.y, r.y);
-                    r.z = __fadd_rn(old.z, r.z); r.w = __fadd_rn(old.w, r.w);
+            const int64_t end = pc.i1 >> 2;
+            for (int64_t i0 = (pc.i0 >> 2) + threadIdx.x; i0 < end; i0 += 4 * (int64_t)blockDim.x) {
+                float4 vv[4];   // four independent 128-bit loads in flight per thread
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int64_t j = i0 + (int64_t)k * blockDim.x;
+                    if (j < end) vv[k] = x4[j];
                 }
-                y4[i] = r;
-                if (cb) {
-                    cb[4 * i + 0] = code_to_i32(cx); cb[4 * i + 1] = code_to_i32(cy);
-                    cb[4 * i + 2] = code_to_i32(cz); cb[4 * i + 3] = code_to_i32(cw);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int64_t i = i0 + (int64_t)k * blockDim.x;
+                    if (i >= end) break;
+                    float4 v = vv[k];
+                    if (ps.gamma) { v.x = __fmul_rn(v.x, f); v.y = __fmul_rn(v.y, f); v.z = __fmul_rn(v.z, f); v.w = __fmul_rn(v.w, f); }
+                    float4 r;
+                    float cx, cy, cz, cw;
+                    r.x = qdq_generic(a, v.x, Tc, qs, cx);
+                    r.y = qdq_generic(a, v.y, Tc, qs, cy);
+                    r.z = qdq_generic(a, v.z, Tc, qs, cz);
+                    r.w = qdq_generic(a, v.w, Tc, qs, cw);
+                    if (add) {
+                        const float4 old = y4[i];
+                        r.x = __fadd_rn(old.x, r.x); r.y = __fadd_rn(old.y, r.y);
+                        r.z = __fadd_rn(old.z, r.z); r.w = __fadd_rn(old.w, r.w);
+                    }
+                    y4[i] = r;
+                    if (cb) {
+                        cb[4 * i + 0] = code_to_i32(cx); cb[4 * i + 1] = code_to_i32(cy);
+                        cb[4 * i + 2] = code_to_i32(cz); cb[4 * i + 3] = code_to_i32(cw);
+                    }
                 }
             }
         } else {
@@ -314,6 +329,103 @@ qdq_seg_kernel(const float* __restrict__ x, float* __restrict__ y, SegPlan pl, P
             }
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row-fused weight path (K2 / K9): one WARP per row (out-channel or GDRQ group), ONE kernel.
+// pass 1: statistic of the row (max|w| or sum|w|, optional fold-BN prescale) -> warp shuffle tree (fixed order);
+// threshold update in registers (lane 0 writes aux); pass 2: clip + QDQ of the same row, which is still in L1.
+// Replaces reduce + (ticket / last block) + sweep for per-channel weights: depthwise 3x3 rows have 9 elements.
+// ------------------------------------------------------------------------------------------------
+#define B2Q_ROWS_FUSED_MAX_INNER 16384
+
+template <bool IS_MAX>
+__global__ void __launch_bounds__(B2Q_THREADS)
+rows_fused_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t rows, int64_t inner, Prescale ps,
+                  FoldBias fb, UpdateArgs u, QdqArgs a, int clip_with_fresh) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int64_t row = (int64_t)blockIdx.x * nw + wid;
+    if (row >= rows) return;
+    const float* xb = x + row * inner;
+    float* yb = y + row * inner;
+    const float f = ps.gamma ? prescale_factor(ps, row) : 1.f;
+    const bool vec = ((((uintptr_t)xb) & 15) == 0) && ((((uintptr_t)yb) & 15) == 0) && ((inner & 3) == 0);
+    double acc = 0.0;
+    float m = 0.f;
+    if (vec) {
+        const float4* x4 = reinterpret_cast<const float4*>(xb);
+        for (int64_t i = lane; i < (inner >> 2); i += 32) {
+            float4 v = x4[i];
+            if (ps.gamma) { v.x = __fmul_rn(v.x, f); v.y = __fmul_rn(v.y, f); v.z = __fmul_rn(v.z, f); v.w = __fmul_rn(v.w, f); }
+            acc1<IS_MAX>(acc, m, v.x); acc1<IS_MAX>(acc, m, v.y); acc1<IS_MAX>(acc, m, v.z); acc1<IS_MAX>(acc, m, v.w);
+        }
+    } else {
+        for (int64_t i = lane; i < inner; i += 32) {
+            float v = xb[i];
+            if (ps.gamma) v = __fmul_rn(v, f);
+            acc1<IS_MAX>(acc, m, v);
+        }
+    }
+    float stat;
+    if (IS_MAX) stat = warp_max(m);
+    else stat = __fdiv_rn((float)warp_sum(acc), (float)inner);
+    const float a_old = u.aux ? u.aux[row] : 0.f;
+    float fresh, next;
+    compute_update(u.mode, u.p0, u.p1, a_old, stat, fresh, next);
+    __syncwarp();
+    if (lane == 0 && u.write_aux && u.aux) u.aux[row] = next;
+    const float after = u.write_aux ? next : a_old;
+    const float T = u.use_aux_as_scale ? after : fresh;
+    const float Tc = clip_with_fresh ? fresh : T;
+    if (fb.bias && lane == 0) {
+        const float den = __fsqrt_rn(__fadd_rn(ps.var[row], ps.eps));
+        fb.bias[row] = __fsub_rn(fb.beta[row], __fdiv_rn(__fmul_rn(fb.mean[row], ps.gamma[row]), den));
+    }
+    if (a.req == B2Q_REQ_NULL) return;
+    const QScale qs = make_qscale(T, a.qlevel, a.fast != 0);
+    const bool add = (a.req == B2Q_REQ_ADD);
+    if (vec) {
+        const float4* x4 = reinterpret_cast<const float4*>(xb);
+        float4* y4 = reinterpret_cast<float4*>(yb);
+        for (int64_t i = lane; i < (inner >> 2); i += 32) {
+            float4 v = x4[i];
+            if (ps.gamma) { v.x = __fmul_rn(v.x, f); v.y = __fmul_rn(v.y, f); v.z = __fmul_rn(v.z, f); v.w = __fmul_rn(v.w, f); }
+            float4 r;
+            float c;
+            r.x = qdq_generic(a, v.x, Tc, qs, c); r.y = qdq_generic(a, v.y, Tc, qs, c);
+            r.z = qdq_generic(a, v.z, Tc, qs, c); r.w = qdq_generic(a, v.w, Tc, qs, c);
+            if (add) {
+                const float4 old = y4[i];
+                r.x = __fadd_rn(old.x, r.x); r.y = __fadd_rn(old.y, r.y); r.z = __fadd_rn(old.z, r.z); r.w = __fadd_rn(old.w, r.w);
+            }
+            y4[i] = r;
+        }
+    } else {
+        for (int64_t i = lane; i < inner; i += 32) {
+            float v = xb[i];
+            if (ps.gamma) v = __fmul_rn(v, f);
+            float c;
+            float r = qdq_generic(a, v, Tc, qs, c);
+            if (add) r = __fadd_rn(yb[i], r);
+            yb[i] = r;
+        }
+    }
+}
+
+// Eligible: weights viewed as (1, rows, inner) with short rows.  *done = 0 -> caller uses reduce + sweep.
+template <bool IS_MAX>
+[[maybe_unused]] static int launch_rows_fused(b2q_ctx* ctx, const float* x, float* y, int64_t rows, int64_t inner,
+                                              Prescale ps, FoldBias fb, UpdateArgs u, QdqArgs a, int clip_with_fresh,
+                                              cudaStream_t st, int* done) {
+    *done = 0;
+    if (inner > B2Q_ROWS_FUSED_MAX_INNER || rows < 2 || a.codes != nullptr || u.stat_out != nullptr) return 0;
+    const int nw = B2Q_THREADS / 32;
+    const unsigned grid = (unsigned)((rows + nw - 1) / nw);
+    b2q_timed_launch tl(ctx, B2Q_KIND_OTHER, 8.0 * (double)(rows * inner), st);
+    rows_fused_kernel<IS_MAX><<<grid, B2Q_THREADS, 0, st>>>(x, y, rows, inner, ps, fb, u, a, clip_with_fresh);
+    B2Q_LAUNCH_CHECK(ctx);
+    *done = 1;
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -387,6 +499,36 @@ bwd_seg_kernel(const float* __restrict__ x, const float* __restrict__ dy, float*
     const float T = thr ? __ldg(thr + pc.g) : thr_imm;
     for (int64_t o = pc.o0; o < pc.o1; ++o) {
         const int64_t off = (o * pl.groups + pc.g) * pl.inner;
+        if (pl.vec == 4) {
+            const float4* x4 = reinterpret_cast<const float4*>(x + off);
+            const float4* g4 = reinterpret_cast<const float4*>(dy + off);
+            float4* o4 = reinterpret_cast<float4*>(dx + off);
+            const int64_t end = pc.i1 >> 2;
+            for (int64_t i0 = (pc.i0 >> 2) + threadIdx.x; i0 < end; i0 += 2 * (int64_t)blockDim.x) {
+                float4 xv[2], gv[2];
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const int64_t j = i0 + (int64_t)k * blockDim.x;
+                    if (j < end) { gv[k] = g4[j]; if (MASK != 0) xv[k] = x4[j]; }
+                }
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const int64_t j = i0 + (int64_t)k * blockDim.x;
+                    if (j >= end) break;
+                    float4 r = gv[k];
+                    if (MASK != 0) {
+                        r.x = mask_grad<MASK>(xv[k].x, gv[k].x, T); r.y = mask_grad<MASK>(xv[k].y, gv[k].y, T);
+                        r.z = mask_grad<MASK>(xv[k].z, gv[k].z, T); r.w = mask_grad<MASK>(xv[k].w, gv[k].w, T);
+                    }
+                    if (ADD) {
+                        const float4 old = o4[j];
+                        r.x = __fadd_rn(old.x, r.x); r.y = __fadd_rn(old.y, r.y); r.z = __fadd_rn(old.z, r.z); r.w = __fadd_rn(old.w, r.w);
+                    }
+                    o4[j] = r;
+                }
+            }
+            continue;
+        }
         for (int64_t i = pc.i0 + threadIdx.x; i < pc.i1; i += blockDim.x) {
             float r = (MASK != 0) ? mask_grad<MASK>(x[off + i], dy[off + i], T) : dy[off + i];
             if (ADD) r = __fadd_rn(dx[off + i], r);
@@ -412,8 +554,7 @@ static inline bool same_misalignment(const void* a, const void* b) {
         FlatSplit sp = b2q_flat_split(x, n);
         bool ok = same_misalignment(x, y) && (!a.codes || ((((uintptr_t)x >> 2) & 7) == (((uintptr_t)a.codes >> 2) & 7)));
         if (ok && sp.head <= B2Q_THREADS) {
-            const bool hot = a.do_round && a.req != B2Q_REQ_ADD && !a.codes &&
-                             (a.clip_mode == B2Q_CLIP_NONE || a.clip_mode == B2Q_CLIP_SYM);
+            const bool hot = a.do_round && a.req != B2Q_REQ_ADD && !a.codes;
             b2q_timed_launch tl(ctx, hot ? B2Q_KIND_QDQ_HOT : B2Q_KIND_OTHER, 8.0 * (double)n, st);
             if (hot) {
                 const int64_t grid = b2q_flat_grid(ctx, sp.n8, B2Q_QDQ_UNROLL);
@@ -422,8 +563,16 @@ static inline bool same_misalignment(const void* a, const void* b) {
                 const int rev = (ctx->reverse && n * 4 > ctx->reverse_min_bytes) ? 1 : 0;
 #define B2Q_HOT(C, S) qdq_flat_hot_kernel<C, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, S, false> \
                           <<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, y, sp, a, rev, none, 0)
-                if (a.clip_mode == B2Q_CLIP_SYM) { if (stream_out) B2Q_HOT(true, 1); else B2Q_HOT(true, B2Q_QDQ_STPOL); }
-                else { if (stream_out) B2Q_HOT(false, 1); else B2Q_HOT(false, B2Q_QDQ_STPOL); }
+#define B2Q_HOT_S(C) do { if (stream_out) B2Q_HOT(C, 1); else B2Q_HOT(C, B2Q_QDQ_STPOL); } while (0)
+                switch (a.clip_mode) {
+                    case B2Q_CLIP_SYM: B2Q_HOT_S(B2Q_CLIP_SYM); break;
+                    case B2Q_CLIP_WHERE_LE: B2Q_HOT_S(B2Q_CLIP_WHERE_LE); break;
+                    case B2Q_CLIP_ZERO_T: B2Q_HOT_S(B2Q_CLIP_ZERO_T); break;
+                    case B2Q_CLIP_PACT: B2Q_HOT_S(B2Q_CLIP_PACT); break;
+                    case B2Q_CLIP_WHERE_LT: B2Q_HOT_S(B2Q_CLIP_WHERE_LT); break;
+                    default: B2Q_HOT_S(B2Q_CLIP_NONE); break;
+                }
+#undef B2Q_HOT_S
 #undef B2Q_HOT
             } else {
                 const int64_t grid = b2q_flat_grid(ctx, sp.n8, 2);
@@ -434,7 +583,7 @@ static inline bool same_misalignment(const void* a, const void* b) {
         }
         outer = 1; inner = n;  // mutually misaligned buffers: scalar segmented path
     }
-    SegPlan pl = b2q_seg_plan(x, y, outer, groups, inner, ctx->num_sms * 8);
+    SegPlan pl = b2q_seg_plan(x, y, outer, groups, inner, ctx->num_sms * 16);
     const unsigned grid = (unsigned)(groups * pl.S * pl.P);
     b2q_timed_launch tl(ctx, B2Q_KIND_OTHER, 8.0 * (double)n, st);
     if (pl.vec == 4) qdq_seg_kernel<4><<<grid, 128, 0, st>>>(x, y, pl, ps, fb, a);
@@ -451,6 +600,9 @@ template <bool IS_MAX>
                                                   UpdateArgs u, float qlevel, int clip_mode, int clip_with_fresh,
                                                   cudaStream_t st, int* done) {
     *done = 0;
+    // Sums keep the last-block finalisation: a deferred sum would make every one-tile block of the sweep re-combine
+    // hundreds of double partials; the max needs only one tagged word.
+    if (!IS_MAX) return 0;
     if (!ctx->deferred || !(clip_mode == B2Q_CLIP_NONE || clip_mode == B2Q_CLIP_SYM)) return 0;
     if (u.stat_out != nullptr) return 0;
     FlatSplit sp = b2q_flat_split(x, n);
@@ -475,8 +627,8 @@ template <bool IS_MAX>
         const int rev = (ctx->reverse && n * 4 > ctx->reverse_min_bytes) ? 1 : 0;
 #define B2Q_HOT(C, S) qdq_flat_hot_kernel<C, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, S, true> \
                           <<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, y, sp, a, rev, d, clip_with_fresh)
-        if (clip_mode == B2Q_CLIP_SYM) { if (stream_out) B2Q_HOT(true, 1); else B2Q_HOT(true, B2Q_QDQ_STPOL); }
-        else { if (stream_out) B2Q_HOT(false, 1); else B2Q_HOT(false, B2Q_QDQ_STPOL); }
+        if (clip_mode == B2Q_CLIP_SYM) { if (stream_out) B2Q_HOT(B2Q_CLIP_SYM, 1); else B2Q_HOT(B2Q_CLIP_SYM, B2Q_QDQ_STPOL); }
+        else { if (stream_out) B2Q_HOT(B2Q_CLIP_NONE, 1); else B2Q_HOT(B2Q_CLIP_NONE, B2Q_QDQ_STPOL); }
 #undef B2Q_HOT
         B2Q_LAUNCH_CHECK(ctx);
     }
@@ -508,7 +660,8 @@ static int launch_bwd_mask(b2q_ctx* ctx, const float* x, const float* dy, float*
         outer = 1; inner = n;
     }
     B2Q_REQUIRE(thr != nullptr || groups == 1, "grouped mask needs a device threshold vector");
-    SegPlan pl = b2q_seg_plan(nullptr, nullptr, outer, groups, inner, ctx->num_sms * 8);
+    SegPlan pl = b2q_seg_plan(dy, dx, outer, groups, inner, ctx->num_sms * 16);
+    if (MASK != 0 && (((uintptr_t)x) & 15)) pl.vec = 1;
     const unsigned grid = (unsigned)(groups * pl.S * pl.P);
     if (add) bwd_seg_kernel<MASK, true><<<grid, 128, 0, st>>>(x, dy, dx, pl, thr, thr_imm);
     else bwd_seg_kernel<MASK, false><<<grid, 128, 0, st>>>(x, dy, dx, pl, thr, thr_imm);

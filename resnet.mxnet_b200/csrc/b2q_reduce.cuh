@@ -150,7 +150,7 @@ static inline SegPlan b2q_seg_plan(const void* x, const void* y, int64_t outer, 
     int64_t S = outer < want ? outer : want;
     if (S < 1) S = 1;
     int64_t wantP = (want + S - 1) / S;
-    int64_t min_part = 2048;  // do not cut rows into pieces smaller than this many elements
+    int64_t min_part = 4096;  // do not cut rows into pieces smaller than this many elements
     int64_t maxP = (inner + min_part - 1) / min_part;
     int64_t P = wantP < maxP ? wantP : maxP;
     if (P < 1) P = 1;
@@ -209,11 +209,20 @@ reduce_seg_kernel(const float* __restrict__ x, SegPlan pl, Prescale ps, b2q_slot
         const float f = ps.gamma ? prescale_factor(ps, row) : 1.f;
         if (VEC == 4) {
             const float4* b4 = reinterpret_cast<const float4*>(base);
-            for (int64_t i = (pc.i0 >> 2) + threadIdx.x; i < (pc.i1 >> 2); i += blockDim.x) {
-                float4 v = b4[i];
-                if (ps.gamma) { v.x = __fmul_rn(v.x, f); v.y = __fmul_rn(v.y, f); v.z = __fmul_rn(v.z, f); v.w = __fmul_rn(v.w, f); }
-                acc1<IS_MAX>(acc, mx, v.x); acc1<IS_MAX>(acc, mx, v.y);
-                acc1<IS_MAX>(acc, mx, v.z); acc1<IS_MAX>(acc, mx, v.w);
+            const int64_t end = pc.i1 >> 2;
+            for (int64_t i = (pc.i0 >> 2) + threadIdx.x; i < end; i += 4 * (int64_t)blockDim.x) {
+                float4 v[4];   // four independent 128-bit loads in flight per thread
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int64_t j = i + (int64_t)k * blockDim.x;
+                    v[k] = (j < end) ? b4[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (ps.gamma) { v[k].x = __fmul_rn(v[k].x, f); v[k].y = __fmul_rn(v[k].y, f); v[k].z = __fmul_rn(v[k].z, f); v[k].w = __fmul_rn(v[k].w, f); }
+                    acc1<IS_MAX>(acc, mx, v[k].x); acc1<IS_MAX>(acc, mx, v[k].y);
+                    acc1<IS_MAX>(acc, mx, v[k].z); acc1<IS_MAX>(acc, mx, v[k].w);
+                }
             }
         } else {
             for (int64_t i = pc.i0 + threadIdx.x; i < pc.i1; i += blockDim.x) {
@@ -224,6 +233,12 @@ reduce_seg_kernel(const float* __restrict__ x, SegPlan pl, Prescale ps, b2q_slot
         }
     }
     double r = block_reduce<IS_MAX>(IS_MAX ? (double)mx : acc, smem);
+    const int SP = pl.S * pl.P;
+    const float count = (float)(pl.outer * pl.inner);  // elements per group (float32(N) like MXNet's mean)
+    if (SP == 1) {   // one piece per group: this block owns the whole group, nothing to combine
+        if (threadIdx.x == 0) apply_update(u, (int)pc.g, IS_MAX ? (float)r : __fdiv_rn((float)r, count));
+        return;
+    }
     if (threadIdx.x == 0) {
         slot->partial[blockIdx.x] = r;
         __threadfence();
@@ -232,20 +247,28 @@ reduce_seg_kernel(const float* __restrict__ x, SegPlan pl, Prescale ps, b2q_slot
     __syncthreads();
     if (s_ticket != gridDim.x - 1) return;
     __threadfence();
-    const int SP = pl.S * pl.P;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const float count = (float)(pl.outer * pl.inner);  // elements per group (float32(N) like MXNet's mean)
-    for (int64_t gg = wid; gg < pl.groups; gg += nw) {
-        double a = 0.0;
-        float m = 0.f;
-        for (int l = lane; l < SP; l += 32) {
-            double q = __ldcg(&slot->partial[gg * SP + l]);
-            if (IS_MAX) m = fmaxf(m, (float)q); else a += q;
+    if (pl.groups >= 64) {
+        // many groups: one thread per group walks its SP partials in order (fixed order => deterministic)
+        for (int64_t gg = threadIdx.x; gg < pl.groups; gg += blockDim.x) {
+            double a = 0.0;
+            float m = 0.f;
+            for (int l = 0; l < SP; ++l) {
+                const double q = __ldcg(&slot->partial[gg * SP + l]);
+                if (IS_MAX) m = fmaxf(m, (float)q); else a += q;
+            }
+            apply_update(u, (int)gg, IS_MAX ? m : __fdiv_rn((float)a, count));
         }
-        if (IS_MAX) m = warp_max(m); else a = warp_sum(a);
-        if (lane == 0) {
-            float stat = IS_MAX ? m : __fdiv_rn((float)a, count);
-            apply_update(u, (int)gg, stat);
+    } else {
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        for (int64_t gg = wid; gg < pl.groups; gg += nw) {
+            double a = 0.0;
+            float m = 0.f;
+            for (int l = lane; l < SP; l += 32) {
+                double q = __ldcg(&slot->partial[gg * SP + l]);
+                if (IS_MAX) m = fmaxf(m, (float)q); else a += q;
+            }
+            if (IS_MAX) m = warp_max(m); else a = warp_sum(a);
+            if (lane == 0) apply_update(u, (int)gg, IS_MAX ? m : __fdiv_rn((float)a, count));
         }
     }
     __syncthreads();
@@ -308,7 +331,7 @@ static int launch_reduce(b2q_ctx* ctx, b2q_slot* slot, const float* x, int64_t o
         }
         outer = 1; inner = n;  // not even float-aligned: scalar segmented path
     }
-    SegPlan pl = b2q_seg_plan(x, nullptr, outer, groups, inner, ctx->num_sms * 8);
+    SegPlan pl = b2q_seg_plan(x, nullptr, outer, groups, inner, ctx->num_sms * 16);
     const unsigned grid = (unsigned)(groups * pl.S * pl.P);
     b2q_timed_launch tl(ctx, B2Q_KIND_OTHER, 4.0 * (double)n, st);
     if (pl.vec == 4) reduce_seg_kernel<IS_MAX, 4><<<grid, 128, 0, st>>>(x, pl, ps, slot, u);

@@ -25,9 +25,16 @@ __device__ __forceinline__ void put_scalar(float* dst, float v, int req) {
 
 // ------------------------------------------------------------------------------------------------
 // Generic flat "elementwise + up to 3 sums + 1 max" kernel.  Op provides
-//   __device__ void setup();  __device__ void apply(int64_t i, double* s, float& m);
-//   __device__ void finalize(const double* s, float m);      (last block, thread 0)
+//   __device__ void setup();
+//   __device__ EwIn load(int64_t i) const;                      (all global loads of element i)
+//   __device__ void apply(int64_t i, const EwIn& in, double* s, float& m);
+//   __device__ void finalize(const double* s, float m);         (last block, thread 0)
+// Loads of four elements are issued before any of them is consumed (memory-level parallelism).
 // ------------------------------------------------------------------------------------------------
+struct EwIn {
+    float a, b;
+};
+
 template <class Op>
 __global__ void __launch_bounds__(B2Q_THREADS) ew_kernel(Op op, int64_t n, b2q_slot* slot) {
     __shared__ double smem[32];
@@ -35,8 +42,20 @@ __global__ void __launch_bounds__(B2Q_THREADS) ew_kernel(Op op, int64_t n, b2q_s
     op.setup();
     double s[3] = {0.0, 0.0, 0.0};
     float m = 0.f;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) op.apply(i, s, m);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x * 4 + threadIdx.x; base < n; base += stride) {
+        EwIn in[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int64_t i = base + (int64_t)k * blockDim.x;
+            if (i < n) in[k] = op.load(i);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int64_t i = base + (int64_t)k * blockDim.x;
+            if (i < n) op.apply(i, in[k], s, m);
+        }
+    }
     if (!Op::REDUCES) return;
     double r[4];
     r[0] = block_reduce<false>(s[0], smem);
@@ -74,7 +93,7 @@ template <class Op>
 static int launch_ew(b2q_ctx* ctx, Op op, int64_t n, cudaStream_t st) {
     B2Q_REQUIRE(n >= 1, "empty tensor");
     int64_t grid = (n + B2Q_THREADS * 4 - 1) / (B2Q_THREADS * 4);
-    int64_t cap = (int64_t)ctx->num_sms * 8;
+    int64_t cap = Op::REDUCES ? (int64_t)ctx->num_sms * 16 : (int64_t)0x7fffffff;   // reducing ops keep 4 partials per block
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
     ew_kernel<Op><<<(unsigned)grid, B2Q_THREADS, 0, st>>>(op, n, b2q_take_slot(ctx));
@@ -89,9 +108,10 @@ struct WnqFwd {
     static const bool REDUCES = false;
     const float* x; float* y; const float* m; int64_t cols; int per_channel; float L; int add;
     __device__ void setup() {}
-    __device__ void apply(int64_t i, double*, float&) {
+    __device__ EwIn load(int64_t i) const { return {x[i], 0.f}; }
+    __device__ void apply(int64_t i, const EwIn& in, double*, float&) {
         const float mm = m[per_channel ? i / cols : 0];
-        const float normed = __fdiv_rn(x[i], mm);                                  // WNQ.py:62
+        const float normed = __fdiv_rn(in.a, mm);                                  // WNQ.py:62
         const float code = roundf(__fmul_rn(normed, L));
         put(y, i, __fmul_rn(__fdiv_rn(code, L), mm), add);                         // :63
     }
@@ -140,11 +160,12 @@ struct WnqBwdApply {
     static const bool REDUCES = false;
     const float* x; const float* dy; float* dx; const float* m; const float* mgrad; int64_t cols; int per_channel; int add;
     __device__ void setup() {}
-    __device__ void apply(int64_t i, double*, float&) {
+    __device__ EwIn load(int64_t i) const { return {x[i], dy[i]}; }
+    __device__ void apply(int64_t i, const EwIn& in, double*, float&) {
         const int64_t g = per_channel ? i / cols : 0;
-        const float ax = fabsf(x[i]);
+        const float ax = fabsf(in.a);
         const float nm = (ax != m[g]) ? 1.f : 0.f, im = (ax == m[g]) ? 1.f : 0.f;
-        put(dx, i, __fadd_rn(__fmul_rn(dy[i], nm), __fmul_rn(mgrad[g], im)), add);  // :85
+        put(dx, i, __fadd_rn(__fmul_rn(in.b, nm), __fmul_rn(mgrad[g], im)), add);  // :85
     }
     __device__ void finalize(const double*, float) {}
 };
@@ -157,8 +178,9 @@ struct PactBwd {
     const float* x; const float* dy; float* dx; float* dgamma; const float* gamma; int two_sided; int add; int req; int req_gamma;
     float g;
     __device__ void setup() { g = gamma[0]; }
-    __device__ void apply(int64_t i, double* s, float&) {
-        const float xv = x[i], d = dy[i];
+    __device__ EwIn load(int64_t i) const { return {x[i], dy[i]}; }
+    __device__ void apply(int64_t i, const EwIn& in, double* s, float&) {
+        const float xv = in.a, d = in.b;
         const bool cond = two_sided ? (fabsf(xv) < g) : (xv < g);
         if (req != B2Q_REQ_NULL) put(dx, i, cond ? d : 0.f, add);
         float other = cond ? 0.f : d;
@@ -175,7 +197,8 @@ struct DorefaMax {
     static const bool REDUCES = true;
     const float* x; float* vmax;
     __device__ void setup() {}
-    __device__ void apply(int64_t i, double*, float& m) { m = fmaxf(m, fabsf(tanhf(x[i]))); }
+    __device__ EwIn load(int64_t i) const { return {x[i], 0.f}; }
+    __device__ void apply(int64_t i, const EwIn& in, double*, float& m) { m = fmaxf(m, fabsf(tanhf(in.a))); }
     __device__ void finalize(const double*, float m) { vmax[0] = m; }
 };
 
@@ -184,8 +207,9 @@ struct DorefaFwd {
     const float* x; float* y; const float* vmax; float L; int add;
     float two_v;
     __device__ void setup() { two_v = __fmul_rn(2.f, vmax[0]); }
-    __device__ void apply(int64_t i, double*, float&) {
-        const float t = tanhf(x[i]);
+    __device__ EwIn load(int64_t i) const { return {x[i], 0.f}; }
+    __device__ void apply(int64_t i, const EwIn& in, double*, float&) {
+        const float t = tanhf(in.a);
         const float o = __fadd_rn(__fdiv_rn(t, two_v), 0.5f);                      // PACT.py:49
         const float code = roundf(__fmul_rn(L, o));                               // quantizeK, :26-28
         put(y, i, __fsub_rn(__fmul_rn(2.f, __fdiv_rn(code, L)), 1.f), add);        // :50
@@ -198,9 +222,10 @@ struct DorefaBwdSum {  // d(2v) = sum( g * (-t / (2v)^2) ),  g = 2*dy
     const float* x; const float* dy; const float* vmax; float* dv_out;
     float two_v, sq;
     __device__ void setup() { two_v = __fmul_rn(2.f, vmax[0]); sq = __fmul_rn(two_v, two_v); }
-    __device__ void apply(int64_t i, double* s, float&) {
-        const float t = tanhf(x[i]);
-        const float g = __fmul_rn(2.f, dy[i]);
+    __device__ EwIn load(int64_t i) const { return {x[i], dy[i]}; }
+    __device__ void apply(int64_t i, const EwIn& in, double* s, float&) {
+        const float t = tanhf(in.a);
+        const float g = __fmul_rn(2.f, in.b);
         s[0] += (double)__fmul_rn(g, __fdiv_rn(-t, sq));
     }
     __device__ void finalize(const double* s, float) { dv_out[0] = __fmul_rn(2.f, (float)s[0]); }
@@ -211,9 +236,10 @@ struct DorefaBwdApply {
     const float* x; const float* dy; float* dx; const float* vmax; const float* dv; int add;
     float v, two_v, dvv;
     __device__ void setup() { v = vmax[0]; two_v = __fmul_rn(2.f, v); dvv = dv[0]; }
-    __device__ void apply(int64_t i, double*, float&) {
-        const float t = tanhf(x[i]);
-        const float g = __fmul_rn(2.f, dy[i]);
+    __device__ EwIn load(int64_t i) const { return {x[i], dy[i]}; }
+    __device__ void apply(int64_t i, const EwIn& in, double*, float&) {
+        const float t = tanhf(in.a);
+        const float g = __fmul_rn(2.f, in.b);
         float dt = __fdiv_rn(g, two_v);
         const float ismax = (fabsf(t) == v) ? 1.f : 0.f;
         dt = __fadd_rn(dt, __fmul_rn(__fmul_rn(ismax, dvv), mx_sign(t)));
@@ -258,8 +284,9 @@ struct QilFwd {
     int variant; const float* x; float* y; const float* p0; const float* p1; float L; int add;
     QilParams q;
     __device__ void setup() { q = qil_params(variant, p0[0], p1[0]); }
-    __device__ void apply(int64_t i, double*, float&) {
-        const float xv = x[i], ax = fabsf(xv), sg = mx_sign(xv);
+    __device__ EwIn load(int64_t i) const { return {x[i], 0.f}; }
+    __device__ void apply(int64_t i, const EwIn& in, double*, float&) {
+        const float xv = in.a, ax = fabsf(xv), sg = mx_sign(xv);
         const float inter = __fmul_rn((ax >= q.pp) ? 1.f : 0.f, (ax <= q.cp) ? 1.f : 0.f);
         const float lin = (variant == 3) ? __fdiv_rn(__fsub_rn(ax, q.pp), q.distance)
                                          : __fadd_rn(__fmul_rn(q.a, ax), q.b);
@@ -276,10 +303,11 @@ struct QilBwd {
     int req, add, req_p0, req_p1;
     QilParams q;
     __device__ void setup() { q = qil_params(variant, p0[0], p1[0]); }
-    __device__ void apply(int64_t i, double* s, float&) {
-        const float xv = x[i], ax = fabsf(xv), sg = mx_sign(xv);
+    __device__ EwIn load(int64_t i) const { return {x[i], dy[i]}; }
+    __device__ void apply(int64_t i, const EwIn& in, double* s, float&) {
+        const float xv = in.a, ax = fabsf(xv), sg = mx_sign(xv);
         const float inter = __fmul_rn((ax >= q.pp) ? 1.f : 0.f, (ax <= q.cp) ? 1.f : 0.f);
-        const float g = __fmul_rn(__fmul_rn(dy[i], sg), inter);     // d out / d lin
+        const float g = __fmul_rn(__fmul_rn(in.b, sg), inter);     // d out / d lin
         float d;
         if (variant == 3) {
             d = __fmul_rn(__fdiv_rn(g, q.distance), sg);

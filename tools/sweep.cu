@@ -81,7 +81,7 @@ static void sweep_qdq(int64_t n, int nbuf, int reps) {
             FlatSplit sp = b2q_flat_split(x, n);
             const int64_t tile = (int64_t)B2Q_THREADS * U;
             int64_t grid = std::min<int64_t>((sp.n8 + tile - 1) / tile, (int64_t)g_sms * bps);
-            qdq_flat_hot_kernel<true, U, L, S, false><<<(unsigned)grid, B2Q_THREADS>>>(x, y, sp, a, 1, none, 0);
+            qdq_flat_hot_kernel<B2Q_CLIP_SYM, U, L, S, false><<<(unsigned)grid, B2Q_THREADS>>>(x, y, sp, a, 1, none, 0);
         }, reps);
         report("qdq", n, U, L, S, bps, 8.0, ms);
     }
@@ -105,11 +105,11 @@ static void sweep_pair(int64_t n, int nbuf, int reps, int rbps, int qbps, int re
             DeferredUpdate d;
             d.partial = g_slot->partial; d.max64 = &g_slot->max64; d.epoch = &g_slot->epoch; d.aux_old = g_slot->scale; d.n_partials = (int)rgrid; d.is_max = 1;
             d.count = (float)n; d.u = u;
-            qdq_flat_hot_kernel<true, 2, 2, 0, true><<<(unsigned)qgrid, B2Q_THREADS>>>(x, y, sp, a, reverse, d, 0);
+            qdq_flat_hot_kernel<B2Q_CLIP_SYM, 2, 2, 0, true><<<(unsigned)qgrid, B2Q_THREADS>>>(x, y, sp, a, reverse, d, 0);
         } else {
             DeferredUpdate none = {};
             reduce_flat_kernel<true, 4, 0, true><<<(unsigned)rgrid, B2Q_THREADS>>>(x, sp, g_slot, u, (float)n);
-            qdq_flat_hot_kernel<true, 2, 2, 0, false><<<(unsigned)qgrid, B2Q_THREADS>>>(x, y, sp, a, reverse, none, 0);
+            qdq_flat_hot_kernel<B2Q_CLIP_SYM, 2, 2, 0, false><<<(unsigned)qgrid, B2Q_THREADS>>>(x, y, sp, a, reverse, none, 0);
         }
     }, reps);
     char name[64];

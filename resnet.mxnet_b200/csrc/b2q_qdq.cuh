@@ -263,6 +263,37 @@ struct FoldBias {
     const float* mean;
 };
 
+// Grouped ACTIVATIONS (GDRQ group_size > 0 on NCHW, tensors of hundreds of MB): every piece is a contiguous range with
+// one threshold, so the block runs the hot sweep's inner loop (256-bit accesses, 8-wide fast path) on its range.
+template <int CLIP>
+__global__ void __launch_bounds__(B2Q_THREADS)
+qdq_seg_hot_kernel(const float* __restrict__ x, float* __restrict__ y, SegPlan pl, QdqArgs a) {
+    const SegPiece pc = seg_piece(pl);
+    const float T = __ldg(a.thr + pc.g);
+    const float Tc = a.clip_thr ? __ldg(a.clip_thr + pc.g) : T;
+    const bool needs_pos = (CLIP != B2Q_CLIP_NONE && CLIP != B2Q_CLIP_PACT);
+    const QScale s = make_qscale(T, a.qlevel, a.fast != 0 && !(needs_pos && !(Tc >= 0.f)));
+    for (int64_t o = pc.o0; o < pc.o1; ++o) {
+        const int64_t off = (o * pl.groups + pc.g) * pl.inner;
+        const float* xb = x + off;
+        float* yb = y + off;
+        const int64_t end = pc.i1 >> 3;
+        for (int64_t i0 = (pc.i0 >> 3) + threadIdx.x; i0 < end; i0 += 2 * (int64_t)blockDim.x) {
+            const int64_t i1 = i0 + blockDim.x;
+            f8 v0, v1;
+            v0 = ld_f8<B2Q_QDQ_LDPOL>(xb + 8 * i0);
+            if (i1 < end) v1 = ld_f8<B2Q_QDQ_LDPOL>(xb + 8 * i1);
+            f8 r;
+            qdq8<CLIP>(v0, r, Tc, s);
+            st_f8<1>(yb + 8 * i0, r);
+            if (i1 < end) {
+                qdq8<CLIP>(v1, r, Tc, s);
+                st_f8<1>(yb + 8 * i1, r);
+            }
+        }
+    }
+}
+
 template <int VEC>
 __global__ void __launch_bounds__(128)
 qdq_seg_kernel(const float* __restrict__ x, float* __restrict__ y, SegPlan pl, Prescale ps, FoldBias fb, QdqArgs a) {
@@ -586,6 +617,19 @@ static inline bool same_misalignment(const void* a, const void* b) {
     SegPlan pl = b2q_seg_plan(x, y, outer, groups, inner, ctx->num_sms * 16);
     const unsigned grid = (unsigned)(groups * pl.S * pl.P);
     b2q_timed_launch tl(ctx, B2Q_KIND_OTHER, 8.0 * (double)n, st);
+    // large grouped tensors: hot inner loop per piece (needs 32-byte aligned ranges: inner and part multiples of 8)
+    if (ps.gamma == nullptr && fb.bias == nullptr && a.thr != nullptr && a.do_round && a.req != B2Q_REQ_ADD && !a.codes &&
+        (inner % 8 == 0) && (pl.part % 8 == 0) && ((((uintptr_t)x) | ((uintptr_t)y)) & 31) == 0 && n >= (1 << 20)) {
+        switch (a.clip_mode) {
+            case B2Q_CLIP_WHERE_LE: qdq_seg_hot_kernel<B2Q_CLIP_WHERE_LE><<<grid, B2Q_THREADS, 0, st>>>(x, y, pl, a); break;
+            case B2Q_CLIP_SYM: qdq_seg_hot_kernel<B2Q_CLIP_SYM><<<grid, B2Q_THREADS, 0, st>>>(x, y, pl, a); break;
+            default: qdq_seg_hot_kernel<B2Q_CLIP_NONE><<<grid, B2Q_THREADS, 0, st>>>(x, y, pl, a); break;
+        }
+        if (a.clip_mode == B2Q_CLIP_WHERE_LE || a.clip_mode == B2Q_CLIP_SYM || a.clip_mode == B2Q_CLIP_NONE) {
+            B2Q_LAUNCH_CHECK(ctx);
+            return 0;
+        }
+    }
     if (pl.vec == 4) qdq_seg_kernel<4><<<grid, 128, 0, st>>>(x, y, pl, ps, fb, a);
     else qdq_seg_kernel<1><<<grid, 128, 0, st>>>(x, y, pl, ps, fb, a);
     B2Q_LAUNCH_CHECK(ctx);

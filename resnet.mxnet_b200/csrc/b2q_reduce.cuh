@@ -135,7 +135,7 @@ reduce_flat_kernel(const float* __restrict__ x, FlatSplit sp, b2q_slot* slot, Up
 struct SegPlan {
     int64_t outer, groups, inner;
     int S, P;            // splits of outer / inner
-    int64_t part;        // inner elements per p-part (multiple of 4)
+    int64_t part;        // inner elements per p-part (multiple of 8)
     int vec;             // 1 or 4
 };
 
@@ -157,7 +157,7 @@ static inline SegPlan b2q_seg_plan(const void* x, const void* y, int64_t outer, 
     while (groups * S * P > B2Q_MAX_PIECES && P > 1) --P;
     while (groups * S * P > B2Q_MAX_PIECES && S > 1) --S;
     int64_t part = (inner + P - 1) / P;
-    part = (part + 3) & ~(int64_t)3;
+    part = (part + 7) & ~(int64_t)7;   // 32-byte granules: pieces stay 256-bit aligned
     P = (inner + part - 1) / part;
     if (P < 1) P = 1;
     pl.S = (int)S; pl.P = (int)P; pl.part = part;
@@ -196,7 +196,7 @@ __device__ __forceinline__ float prescale_factor(const Prescale& ps, int64_t row
 }
 
 template <bool IS_MAX, int VEC>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(VEC == 8 ? B2Q_THREADS : 128)
 reduce_seg_kernel(const float* __restrict__ x, SegPlan pl, Prescale ps, b2q_slot* slot, UpdateArgs u) {
     __shared__ double smem[32];
     __shared__ unsigned int s_ticket;
@@ -207,7 +207,29 @@ reduce_seg_kernel(const float* __restrict__ x, SegPlan pl, Prescale ps, b2q_slot
         const int64_t row = o * pl.groups + pc.g;
         const float* base = x + row * pl.inner;
         const float f = ps.gamma ? prescale_factor(ps, row) : 1.f;
-        if (VEC == 4) {
+        if (VEC == 8) {   // 256-bit loads, four in flight per thread (same inner loop as the flat kernel)
+            const int64_t end = pc.i1 >> 3;
+            for (int64_t i = (pc.i0 >> 3) + threadIdx.x; i < end; i += 4 * (int64_t)blockDim.x) {
+                f8 v[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int64_t j = i + (int64_t)k * blockDim.x;
+                    if (j < end) v[k] = ld_f8<0>(base + 8 * j);
+                    else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[k].v[e] = 0.f;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (ps.gamma) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[k].v[e] = __fmul_rn(v[k].v[e], f);
+                    }
+                    acc8<IS_MAX>(acc, mx, v[k]);
+                }
+            }
+        } else if (VEC == 4) {
             const float4* b4 = reinterpret_cast<const float4*>(base);
             const int64_t end = pc.i1 >> 2;
             for (int64_t i = (pc.i0 >> 2) + threadIdx.x; i < end; i += 4 * (int64_t)blockDim.x) {
@@ -334,7 +356,9 @@ static int launch_reduce(b2q_ctx* ctx, b2q_slot* slot, const float* x, int64_t o
     SegPlan pl = b2q_seg_plan(x, nullptr, outer, groups, inner, ctx->num_sms * 16);
     const unsigned grid = (unsigned)(groups * pl.S * pl.P);
     b2q_timed_launch tl(ctx, B2Q_KIND_OTHER, 4.0 * (double)n, st);
-    if (pl.vec == 4) reduce_seg_kernel<IS_MAX, 4><<<grid, 128, 0, st>>>(x, pl, ps, slot, u);
+    if (pl.vec == 4 && inner % 8 == 0 && pl.part % 8 == 0 && (((uintptr_t)x) & 31) == 0 && n >= (1 << 20))
+        reduce_seg_kernel<IS_MAX, 8><<<grid, B2Q_THREADS, 0, st>>>(x, pl, ps, slot, u);
+    else if (pl.vec == 4) reduce_seg_kernel<IS_MAX, 4><<<grid, 128, 0, st>>>(x, pl, ps, slot, u);
     else reduce_seg_kernel<IS_MAX, 1><<<grid, 128, 0, st>>>(x, pl, ps, slot, u);
     B2Q_LAUNCH_CHECK(ctx);
     return 0;

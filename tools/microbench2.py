@@ -53,6 +53,19 @@ for gs in (-1, 16, 1):
     bench("GDRQ act bwd group_size=%d (|x|<=alpha mask)" % gs,
           lambda i: o.backward(["write"], [dys[i]], [xs[i]], [ys[i]], [ys[(i + 1) % NB]], [alpha]), 12 * n)
 
+# ---- grouped pieces in isolation ----
+for gs in (16, 1):
+    g = 64 // gs
+    view = (256, g, gs * 56 * 56)
+    st_ = torch.zeros(g, device="cuda")
+    th_ = torch.ones(g, device="cuda")
+    bench("  meanabs only, grouped gs=%d" % gs, lambda i: K.meanabs(xs[i], st_, view), 4 * n)
+    bench("  absmax only, grouped gs=%d" % gs, lambda i: K.absmax(xs[i], st_, view), 4 * n)
+    bench("  sweep only (where_le), grouped gs=%d" % gs,
+          lambda i: K.qdq(xs[i], ys[i], th_, 255, _lib.CLIP_WHERE_LE, "write", view=view), 8 * n)
+st1 = torch.zeros(1, device="cuda")
+bench("  meanabs only, whole tensor", lambda i: K.meanabs(xs[i], st1), 4 * n)
+
 # ---- ClipGrad activation ----
 o = op("ClipGrad_Quantization_int8", quant_mode="minmax", is_weight=False)
 o.init = False

@@ -96,3 +96,14 @@ def test_pact_and_qil_nodes_learn_their_scalars():
     q = m[2]
     assert q.data_quant.gamma.grad is not None and q.weight_quant.clipping_point.grad is not None
     assert q.weight_quant.gamma.grad is None
+
+
+def test_quant_attrs_schema_validates_reference_settings():
+    from b200quant.quant_attrs import validate, validate_quantize_setting
+    validate_quantize_setting(SETTING)
+    with pytest.raises(ValueError):
+        validate({"quantize_op_name": "GDRQ", "attrs": {"nbits": 4}})            # not a string
+    with pytest.raises(ValueError):
+        validate({"quantize_op_name": "PACT", "attrs": {"group_size": "2"}})      # foreign attribute
+    with pytest.raises(ValueError):
+        validate({"quantize_op_name": "nope", "attrs": {}})

@@ -353,7 +353,7 @@ def main():
     wnodes = [nd for nd in nodes if nd["kind"] == "weight"]
     anodes = [nd for nd in nodes if nd["kind"] == "act"]
     group = None
-    if minmax:
+    if minmax or op_type == "GDRQ_PY":
         group = WeightGroup([nd["op"] for nd in wnodes], [nd["x"] for nd in wnodes], [nd["y"] for nd in wnodes],
                             [nd["aux"] for nd in wnodes], [nd["dy"] for nd in wnodes], [nd["dx"] for nd in wnodes])
 

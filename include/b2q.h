@@ -209,6 +209,11 @@ typedef struct b2q_multi_plan b2q_multi_plan;
 int b2q_multi_plan_create(b2q_ctx* ctx, const b2q_weight_desc* descs, int count, b2q_multi_plan** out);
 int b2q_multi_plan_destroy(b2q_ctx* ctx, b2q_multi_plan* plan);
 int b2q_multi_weight_quant_fwd_f32(b2q_ctx* ctx, b2q_multi_plan* plan, int variant, int is_train, void* stream);
+/* GDRQ_PY weight nodes (core/operator/GDRQ.py:69-74,97-102,109-114): aux = alpha; descriptors use per_channel=0 for
+ * group_size == -1 and (rows = channels/group_size, cols = group_size * elements per channel, per_channel=1) for
+ * grouped weights.  One |w| sum launch (skipped when fix_alpha) + one clip/round launch for all tensors.            */
+int b2q_multi_gdrq_weight_fwd_f32(b2q_ctx* ctx, b2q_multi_plan* plan, int fix_alpha, int do_round, float qlevel,
+                                  float ktimes, void* stream);
 int b2q_multi_weight_ste_bwd_f32(b2q_ctx* ctx, b2q_multi_plan* plan, void* stream);
 
 /* ---- cross-rank threshold exchange over peer memory (NVLink / NVSwitch), fused into the forward kernels ----

@@ -66,6 +66,7 @@ _CTX_FUNCS = {
     "b2q_multi_plan_create": [_P, _I, ctypes.POINTER(ctypes.c_void_p)],
     "b2q_multi_plan_destroy": [_P],
     "b2q_multi_weight_quant_fwd_f32": [_P, _I, _I, _P],
+    "b2q_multi_gdrq_weight_fwd_f32": [_P, _I, _I, _F, _F, _P],
     "b2q_multi_weight_ste_bwd_f32": [_P, _P],
 }
 

@@ -39,6 +39,8 @@ struct MtItem {
     int kind;        // 0 RANGE, 1 ROWS
     int group;       // RANGE: group (row) inside the tensor
     int first;       // RANGE: 1 if this item starts its group (it owns the aux write)
+    int pfirst;      // RANGE: index of the first item of this group ...
+    int pcount;      // ... and how many items the group has (their double partials are combined in order)
     long long a, b;  // RANGE: element range inside the group; ROWS: row range
 };
 
@@ -49,6 +51,7 @@ struct b2q_multi_plan {
     MtItem* d_items;
     unsigned long long* d_stat;
     unsigned int* d_epoch;
+    double* d_partial;   // one per item (mean-based operators)
     long long elements;
     int has_grad;
 };
@@ -156,6 +159,75 @@ mt_copy_kernel(const MtTensor* __restrict__ tensors, const MtItem* __restrict__ 
     }
 }
 
+// ---- mean-based weights: GDRQ_PY with is_weight (core/operator/GDRQ.py:69-74,97-102) -------------------------------
+// launch A: one double partial per RANGE item (ROWS items do their own sum in launch B).
+__global__ void __launch_bounds__(B2Q_THREADS)
+mt_sumabs_kernel(const MtTensor* __restrict__ tensors, const MtItem* __restrict__ items, double* __restrict__ partial) {
+    __shared__ double smem[32];
+    const MtItem it = items[blockIdx.x];
+    if (it.kind != 0) return;
+    const MtTensor t = tensors[it.tensor];
+    const float* base = mt_group_base(t, it.group);
+    double acc = 0.0;
+    for (long long i = it.a + threadIdx.x; i < it.b; i += blockDim.x) acc += (double)fabsf(base[i]);
+    const double r = block_reduce<false>(acc, smem);
+    if (threadIdx.x == 0) partial[blockIdx.x] = r;
+}
+
+// launch B: alpha = ktimes * mean|w| (unless fix_alpha), clip, round to qlevel levels.
+__global__ void __launch_bounds__(B2Q_THREADS)
+mt_gdrq_kernel(const MtTensor* __restrict__ tensors, const MtItem* __restrict__ items, const double* __restrict__ partial,
+               int fix_alpha, int do_round, float qlevel, float ktimes, int fast) {
+    __shared__ double smem[32];
+    __shared__ float s_T;
+    const MtItem it = items[blockIdx.x];
+    const MtTensor t = tensors[it.tensor];
+    if (it.kind == 0) {
+        if (!fix_alpha) {   // every block of the group combines the group's partials in the same fixed order
+            double acc = 0.0;
+            for (int i = threadIdx.x; i < it.pcount; i += blockDim.x) acc += partial[it.pfirst + i];
+            const double tot = block_reduce<false>(acc, smem);
+            if (threadIdx.x == 0) {
+                const float count = (float)(t.per_channel ? t.cols : t.rows * t.cols);
+                s_T = __fmul_rn(ktimes, __fdiv_rn((float)tot, count));
+                if (it.first) t.aux[it.group] = s_T;
+            }
+        } else if (threadIdx.x == 0) {
+            s_T = t.aux[it.group];
+        }
+        __syncthreads();
+        const float T = s_T;
+        const QScale s = make_qscale(T, qlevel, fast != 0);
+        const int clip = t.per_channel ? B2Q_CLIP_WHERE_LE : B2Q_CLIP_SYM;   // GDRQ.py:109 vs :79
+        const long long off = (t.per_channel ? (long long)it.group * t.cols : 0);
+        for (long long i = off + it.a + threadIdx.x; i < off + it.b; i += blockDim.x) {
+            const float c = clip_value(clip, t.x[i], T);
+            t.y[i] = do_round ? __fmul_rn(quant_code(c, s), s.q) : c;
+        }
+    } else {
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        for (long long row = it.a + wid; row < it.b; row += nw) {
+            const float* p = t.x + row * t.cols;
+            float* o = t.y + row * t.cols;
+            float T;
+            if (!fix_alpha) {
+                double acc = 0.0;
+                for (long long c = lane; c < t.cols; c += 32) acc += (double)fabsf(p[c]);
+                acc = warp_sum(acc);
+                T = __fmul_rn(ktimes, __fdiv_rn((float)acc, (float)t.cols));
+                if (lane == 0) t.aux[row] = T;
+            } else {
+                T = t.aux[row];
+            }
+            const QScale s = make_qscale(T, qlevel, fast != 0);
+            for (long long c = lane; c < t.cols; c += 32) {
+                const float v = clip_value(B2Q_CLIP_WHERE_LE, p[c], T);
+                o[c] = do_round ? __fmul_rn(quant_code(v, s), s.q) : v;
+            }
+        }
+    }
+}
+
 extern "C" {
 
 int b2q_multi_plan_create(b2q_ctx* ctx, const b2q_weight_desc* descs, int count, b2q_multi_plan** out) {
@@ -173,17 +245,23 @@ int b2q_multi_plan_create(b2q_ctx* ctx, const b2q_weight_desc* descs, int count,
         const long long n = t.rows * t.cols;
         elements += n;
         if (!t.per_channel) {
+            const int first = (int)items.size();
+            const int cnt = (int)((n + MT_ITEM_ELEMS - 1) / MT_ITEM_ELEMS);
             for (long long a = 0; a < n; a += MT_ITEM_ELEMS)
-                items.push_back({k, 0, 0, a == 0, a, a + MT_ITEM_ELEMS < n ? a + MT_ITEM_ELEMS : n});
+                items.push_back({k, 0, 0, a == 0, first, cnt, a, a + MT_ITEM_ELEMS < n ? a + MT_ITEM_ELEMS : n});
             gbase += 1;
         } else if (t.cols <= MT_SHORT_ROW) {
             for (long long r = 0; r < t.rows; r += MT_ROWS_PER_ITEM)
-                items.push_back({k, 1, 0, 0, r, r + MT_ROWS_PER_ITEM < t.rows ? r + MT_ROWS_PER_ITEM : t.rows});
+                items.push_back({k, 1, 0, 0, 0, 0, r, r + MT_ROWS_PER_ITEM < t.rows ? r + MT_ROWS_PER_ITEM : t.rows});
             gbase += (int)t.rows;
         } else {
-            for (long long r = 0; r < t.rows; ++r)
+            const int cnt = (int)((t.cols + MT_ITEM_ELEMS - 1) / MT_ITEM_ELEMS);
+            for (long long r = 0; r < t.rows; ++r) {
+                const int first = (int)items.size();
                 for (long long a = 0; a < t.cols; a += MT_ITEM_ELEMS)
-                    items.push_back({k, 0, (int)r, a == 0, a, a + MT_ITEM_ELEMS < t.cols ? a + MT_ITEM_ELEMS : t.cols});
+                    items.push_back({k, 0, (int)r, a == 0, first, cnt, a,
+                                     a + MT_ITEM_ELEMS < t.cols ? a + MT_ITEM_ELEMS : t.cols});
+            }
             gbase += (int)t.rows;
         }
         tensors.push_back(t);
@@ -200,12 +278,13 @@ int b2q_multi_plan_create(b2q_ctx* ctx, const b2q_weight_desc* descs, int count,
     if (e == cudaSuccess) e = cudaMalloc(&p->d_items, sizeof(MtItem) * items.size());
     if (e == cudaSuccess) e = cudaMalloc(&p->d_stat, sizeof(unsigned long long) * gbase);
     if (e == cudaSuccess) e = cudaMalloc(&p->d_epoch, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_partial, sizeof(double) * items.size());
     if (e == cudaSuccess) e = cudaMemcpy(p->d_tensors, tensors.data(), sizeof(MtTensor) * tensors.size(), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(p->d_items, items.data(), sizeof(MtItem) * items.size(), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemset(p->d_stat, 0, sizeof(unsigned long long) * gbase);
     if (e == cudaSuccess) e = cudaMemset(p->d_epoch, 0, sizeof(unsigned int));
     if (e != cudaSuccess) {
-        cudaFree(p->d_tensors); cudaFree(p->d_items); cudaFree(p->d_stat); cudaFree(p->d_epoch);
+        cudaFree(p->d_tensors); cudaFree(p->d_items); cudaFree(p->d_stat); cudaFree(p->d_epoch); cudaFree(p->d_partial);
         delete p;
         b2q_set_error(std::string("multi plan allocation failed: ") + cudaGetErrorString(e));
         return 1;
@@ -217,7 +296,7 @@ int b2q_multi_plan_create(b2q_ctx* ctx, const b2q_weight_desc* descs, int count,
 int b2q_multi_plan_destroy(b2q_ctx* ctx, b2q_multi_plan* p) {
     if (!p) return 0;
     if (ctx) cudaSetDevice(ctx->device);
-    cudaFree(p->d_tensors); cudaFree(p->d_items); cudaFree(p->d_stat); cudaFree(p->d_epoch);
+    cudaFree(p->d_tensors); cudaFree(p->d_items); cudaFree(p->d_stat); cudaFree(p->d_epoch); cudaFree(p->d_partial);
     delete p;
     return 0;
 }
@@ -241,6 +320,23 @@ int b2q_multi_weight_quant_fwd_f32(b2q_ctx* ctx, b2q_multi_plan* p, int variant,
                                                                     do_reduce, is_train ? 1 : 0, ctx->fast_div);
         B2Q_LAUNCH_CHECK(ctx);
     }
+    return 0;
+}
+
+int b2q_multi_gdrq_weight_fwd_f32(b2q_ctx* ctx, b2q_multi_plan* p, int fix_alpha, int do_round, float qlevel,
+                                  float ktimes, void* stream) {
+    B2Q_CTX(ctx);
+    B2Q_REQUIRE(p && p->device == ctx->device, "plan belongs to another device");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!fix_alpha) {
+        b2q_timed_launch tl(ctx, B2Q_KIND_OTHER, 4.0 * (double)p->elements, st);
+        mt_sumabs_kernel<<<(unsigned)p->n_items, B2Q_THREADS, 0, st>>>(p->d_tensors, p->d_items, p->d_partial);
+        B2Q_LAUNCH_CHECK(ctx);
+    }
+    b2q_timed_launch tl(ctx, B2Q_KIND_OTHER, 8.0 * (double)p->elements, st);
+    mt_gdrq_kernel<<<(unsigned)p->n_items, B2Q_THREADS, 0, st>>>(p->d_tensors, p->d_items, p->d_partial, fix_alpha, do_round,
+                                                                 qlevel, ktimes, ctx->fast_div);
+    B2Q_LAUNCH_CHECK(ctx);
     return 0;
 }
 

@@ -63,3 +63,39 @@ def test_weight_group_respects_delay_quant():
     group.forward(True)                       # quantised now
     assert all(float(a) == float(w.abs().max()) for a, w in zip(auxs, ws))
     assert not torch.equal(ys[0], ws[0])
+
+
+@pytest.mark.parametrize("fix_alpha", [False, True])
+def test_gdrq_weight_group_equals_per_op(fix_alpha):
+    import torch
+    import b200quant
+    from b200quant.multi import WeightGroup
+    shapes = [((64, 3, 7, 7), -1), ((256, 64, 1, 1), -1), ((32, 1, 3, 3), 4), ((512, 512, 3, 3), -1), ((64, 32, 3, 3), 8),
+              ((16, 1200), 2), ((1000, 1024), -1)]
+
+    def mk():
+        return [b200quant.get_prop("GDRQ_PY")(nbits="8", group_size=str(gs), is_weight="True", lamda="0.001",
+                                               delay_quant="1", fix_alpha=str(fix_alpha), ktimes="3")
+                .create_operator(None, None, None) for _, gs in shapes]
+
+    g = torch.Generator(device="cuda").manual_seed(7)
+    ops_a, ops_b = mk(), mk()
+    ws = [torch.randn(s, device="cuda", generator=g) * 0.1 for s, _ in shapes]
+    ya, yb = [torch.zeros_like(w) for w in ws], [torch.zeros_like(w) for w in ws]
+    auxa = [torch.full((1 if gs == -1 else s[0] // gs,), 0.2, device="cuda") for s, gs in shapes]
+    auxb = [a.clone() for a in auxa]
+    group = WeightGroup(ops_b, ws, yb, auxb)
+    for step in range(3):                       # step 0 runs the delay_quant (clip only) branch
+        for w in ws:
+            w.mul_(1.0 + 0.5 * step)
+        for op, w, y, a in zip(ops_a, ws, ya, auxa):
+            op.forward(True, ["write"], [w], [y], [a])
+        group.forward(True)
+        torch.cuda.synchronize()
+        for i in range(len(ws)):
+            assert torch.allclose(auxa[i], auxb[i], rtol=1e-6, atol=0), (step, i)
+            if torch.equal(auxa[i].view(torch.int32), auxb[i].view(torch.int32)):
+                assert torch.equal(ya[i].view(torch.int32), yb[i].view(torch.int32)), (step, i)
+            else:  # summation order differs between the two schedules: thresholds may differ in the last ulp
+                assert torch.allclose(ya[i], yb[i], rtol=1e-5, atol=1e-6), (step, i)
+    group.close()

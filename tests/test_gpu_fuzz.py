@@ -1,0 +1,99 @@
+"""Randomised CUDA-vs-oracle checks (hypothesis): arbitrary shapes, value scales, views at odd offsets, all req modes,
+plus the error behaviour of the boundary (bad arguments raise B2QError / ValueError, nothing is silently copied)."""
+import numpy as np
+import pytest
+from hypothesis import HealthCheck, given, settings, strategies as st
+
+from oracle import quant_oracle as qo
+from tests.golden_util import bits_equal
+
+pytestmark = pytest.mark.gpu
+F = np.float32
+_SET = dict(max_examples=60, deadline=None, suppress_health_check=list(HealthCheck))
+
+
+def _ops(op_type, **attrs):
+    import b200quant
+    attrs = {k: str(v) for k, v in attrs.items()}
+    return b200quant.get_prop(op_type)(**attrs).create_operator(None, None, None), qo.create(op_type, **attrs)
+
+
+@given(st.lists(st.integers(1, 9), min_size=1, max_size=4), st.sampled_from([1e-3, 0.3, 1.0, 40.0]),
+       st.sampled_from(["Quantization_int8_V2", "ClipGrad_Quantization_int8"]), st.booleans(), st.booleans(),
+       st.sampled_from(["write", "add"]), st.integers(0, 7), st.integers(0, 2 ** 31 - 1))
+@settings(**_SET)
+def test_minmax_random(shape, scale, op_type, is_weight, per_channel, req, offset, seed):
+    import torch
+    rng = np.random.default_rng(seed)
+    shape = tuple(shape)
+    per_channel = per_channel and is_weight
+    op, ref = _ops(op_type, quant_mode="minmax", is_weight=is_weight, is_weight_perchannel=per_channel)
+    n = int(np.prod(shape))
+    naux = shape[0] if per_channel else 1
+    x = (rng.standard_normal(shape) * scale).astype(F)
+    x.flat[0] = F(scale)                                        # never all zero
+    y0 = rng.standard_normal(shape).astype(F)
+    # device tensors are views at an odd element offset inside larger buffers (exercises the unaligned paths)
+    xbuf = torch.zeros(n + 16, device="cuda")
+    ybuf = torch.zeros(n + 16, device="cuda")
+    xd = xbuf[offset:offset + n].view(shape)
+    yd = ybuf[offset:offset + n].view(shape)
+    xd.copy_(torch.from_numpy(x))
+    yd.copy_(torch.from_numpy(y0))
+    aux_d, aux_r = [torch.full((naux,), 0.9, device="cuda")], [np.full(naux, 0.9, F)]
+    yr = y0.copy()
+    for train in (True, False):
+        op.forward(train, [req], [xd], [yd], aux_d)
+        ref.forward(train, [req], [x], [yr], aux_r)
+        assert bits_equal(aux_d[0].cpu().numpy(), aux_r[0])
+        assert bits_equal(yd.cpu().numpy(), yr)
+    assert float(ybuf[:offset].abs().sum()) == 0 and float(ybuf[offset + n:].abs().sum()) == 0   # no out-of-range writes
+
+
+@given(st.integers(1, 4), st.integers(1, 6), st.integers(1, 3), st.integers(1, 7), st.integers(1, 7), st.booleans(),
+       st.integers(0, 2 ** 31 - 1))
+@settings(**_SET)
+def test_gdrq_grouped_random(n, groups, gs, h, w, is_weight, seed):
+    import torch
+    rng = np.random.default_rng(seed)
+    c = groups * gs
+    shape = (c, n, h, w) if is_weight else (n, c, h, w)
+    op, ref = _ops("GDRQ_PY", nbits=6, group_size=gs, is_weight=is_weight, lamda=0.01, delay_quant=0, fix_alpha=False,
+                   ktimes=2)
+    x = rng.standard_normal(shape).astype(F)
+    dy = rng.standard_normal(shape).astype(F)
+    aux_d, aux_r = [torch.ones(groups, device="cuda")], [np.ones(groups, F)]
+    xd, yd, yr = torch.from_numpy(x).cuda(), torch.zeros(shape, device="cuda"), np.zeros(shape, F)
+    op.forward(True, ["write"], [xd], [yd], aux_d)
+    ref.forward(True, ["write"], [x], [yr], aux_r)
+    np.testing.assert_allclose(aux_d[0].cpu().numpy(), aux_r[0], rtol=1e-6)
+    if bits_equal(aux_d[0].cpu().numpy(), aux_r[0]):
+        assert bits_equal(yd.cpu().numpy(), yr)
+    gd, gr = torch.zeros(shape, device="cuda"), np.zeros(shape, F)
+    op.backward(["write"], [torch.from_numpy(dy).cuda()], [xd], [yd], [gd], aux_d)
+    ref.backward(["write"], [dy], [x], [yr], [gr], [aux_d[0].cpu().numpy()])
+    assert bits_equal(gd.cpu().numpy(), gr)
+
+
+def test_bad_arguments_raise():
+    import torch
+    import b200quant
+    from b200quant import _kernels as K
+    from b200quant._lib import B2QError
+    op = b200quant.get_prop("Quantization_int8_V2")(quant_mode="minmax", is_weight="False").create_operator(None, None, None)
+    x = torch.randn(4, 4, device="cuda")
+    with pytest.raises(ValueError):      # wrong aux size
+        op.forward(True, ["write"], [x], [torch.empty_like(x)], [torch.ones(3, device="cuda")])
+    with pytest.raises(ValueError):      # output size mismatch
+        op.forward(True, ["write"], [x], [torch.empty(5, device="cuda")], [torch.ones(1, device="cuda")])
+    with pytest.raises(TypeError):       # not float32
+        op.forward(True, ["write"], [x.double()], [torch.empty_like(x)], [torch.ones(1, device="cuda")])
+    with pytest.raises(ValueError):      # non-contiguous view: never copied silently
+        op.forward(True, ["write"], [x.t()], [torch.empty_like(x)], [torch.ones(1, device="cuda")])
+    with pytest.raises(ValueError):      # unknown req
+        op.forward(True, ["overwrite"], [x], [torch.empty_like(x)], [torch.ones(1, device="cuda")])
+    with pytest.raises(ValueError):      # mixed host / device tensors
+        op.forward(True, ["write"], [x], [torch.empty(4, 4)], [torch.ones(1, device="cuda")])
+    with pytest.raises(B2QError):        # C ABI argument check surfaces with the library's message
+        K.qdq(x, torch.empty_like(x), torch.ones(1, device="cuda"), 127, 99, "write")
+    op.forward(True, ["null"], [x], [torch.empty_like(x)], [torch.ones(1, device="cuda")])   # null req is legal

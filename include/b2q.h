@@ -100,6 +100,12 @@ int b2q_qdq_f32(b2q_ctx* ctx, const float* x, float* y, int64_t outer, int64_t g
                 int req, int32_t* codes, const float* prescale_gamma, const float* prescale_var,
                 float prescale_eps, void* stream);
 
+/* True-int8 export (inference): codes[i] = clamp(roundf(c(x[i]) / q), -128, 127) as int8 and steps[g] = q[g] =
+ * fl(thr[g] / qlevel), i.e. exactly the integers the QDQ sweep multiplies by q, so a
+ * convolution can consume them on int8 / fp8 tensor cores.  steps may be NULL.                               */
+int b2q_export_int8_f32(b2q_ctx* ctx, const float* x, int8_t* codes, float* steps, int64_t outer, int64_t groups,
+                        int64_t inner, const float* thr, float qlevel, int clip_mode, void* stream);
+
 /* K5  straight-through backward: in_grad (req) out_grad      quant_ops.py:41-42, GDRQ.py:126        */
 int b2q_ste_bwd_f32(b2q_ctx* ctx, const float* dy, float* dx, int64_t n, int req, void* stream);
 

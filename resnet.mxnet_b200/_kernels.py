@@ -333,3 +333,17 @@ def qil_bwd(variant, x, dy, dx, p0, p1, dp0, dp1, req, req_p0, req_p1):
     require_device(on_dev, "QIL")
     _lib.context(dev).call("b2q_qil_bwd_f32", int(variant), xb.ptr, gb.ptr, ob.ptr, b0.ptr, b1.ptr, d0.ptr, d1.ptr,
                            xb.numel, _req(req), _req(req_p0), _req(req_p1), current_stream(xb))
+
+
+def export_int8(x, thr, qlevel, clip_mode, view=None):
+    """(int8 codes, float32 steps): the integers and the per-group step the fake-quant output is made of."""
+    import torch
+    xb, tb = as_buffer(x), as_buffer(thr)
+    outer, groups, inner = view if view is not None else (1, 1, xb.numel)
+    on_dev, dev = _same_place(xb, tb)
+    require_device(on_dev, "export_int8")
+    codes = torch.empty(xb.shape, dtype=torch.int8, device=x.device)
+    steps = torch.empty(groups, dtype=torch.float32, device=x.device)
+    _lib.context(dev).call("b2q_export_int8_f32", xb.ptr, codes.data_ptr(), steps.data_ptr(), outer, groups, inner,
+                           tb.ptr, _f32(qlevel), int(clip_mode), current_stream(xb))
+    return codes, steps

@@ -341,6 +341,27 @@ struct QilBwd {
     }
 };
 
+// ------------------------------------------------------------------------------------------------
+// True-int8 export: the integer codes the QDQ sweep computes, packed as int8, plus
+// the per-group step q = T / qlevel, so that an inference engine can run the convolution on int8 / fp8 tensor cores.
+// codes[i] = clamp(roundf(clip(x[i]) / q), -128, 127); dequantised value = codes[i] * q (bit-identical to the
+// fake-quant output whenever |code| <= 127, which holds for every clipping operator and for weights).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(B2Q_THREADS)
+export_int8_kernel(const float* __restrict__ x, int8_t* __restrict__ codes, float* __restrict__ steps, int64_t outer,
+                   int64_t groups, int64_t inner, const float* __restrict__ thr, float qlevel, int clip_mode, int fast) {
+    const int64_t n = outer * groups * inner;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int64_t g = (groups == 1) ? 0 : (i / inner) % groups;
+        const float T = thr[g];
+        const QScale s = make_qscale(T, qlevel, fast != 0);
+        const float c = quant_code(clip_value(clip_mode, x[i], T), s);
+        codes[i] = (int8_t)max(-128, min(127, __float2int_rn(c)));
+        if (i < groups && steps) steps[i] = make_qscale(thr[i], qlevel, false).q;
+    }
+}
+
 extern "C" {
 
 int b2q_clip_relu_fwd_f32(b2q_ctx* ctx, const float* x, float* y, int64_t n, float threshold, float q, int req,
@@ -351,6 +372,21 @@ int b2q_clip_relu_fwd_f32(b2q_ctx* ctx, const float* x, float* y, int64_t n, flo
     // GDRQ.py:202-204: clip(x, 0, thr); q = thr/L computed in python double, applied in float32
     QdqArgs a = {nullptr, nullptr, q, threshold, 0.f, ctx->fast_div, nullptr, B2Q_CLIP_ZERO_T, 1, req};
     return launch_qdq(ctx, x, y, 1, 1, n, kNoPrescale, kNoBias, a, (cudaStream_t)stream);
+}
+
+int b2q_export_int8_f32(b2q_ctx* ctx, const float* x, int8_t* codes, float* steps, int64_t outer, int64_t groups,
+                        int64_t inner, const float* thr, float qlevel, int clip_mode, void* stream) {
+    B2Q_CTX(ctx);
+    B2Q_REQUIRE(x && codes && thr && outer >= 1 && groups >= 1 && inner >= 1, "bad argument");
+    B2Q_REQUIRE(clip_mode >= B2Q_CLIP_NONE && clip_mode <= B2Q_CLIP_WHERE_LT, "unknown clip_mode");
+    const int64_t n = outer * groups * inner;
+    int64_t grid = (n + B2Q_THREADS - 1) / B2Q_THREADS;
+    if (grid > (int64_t)ctx->num_sms * 32) grid = (int64_t)ctx->num_sms * 32;
+    b2q_timed_launch tl(ctx, B2Q_KIND_OTHER, 5.0 * (double)n, (cudaStream_t)stream);
+    export_int8_kernel<<<(unsigned)grid, B2Q_THREADS, 0, (cudaStream_t)stream>>>(x, codes, steps, outer, groups, inner, thr,
+                                                                                 qlevel, clip_mode, ctx->fast_div);
+    B2Q_LAUNCH_CHECK(ctx);
+    return 0;
 }
 
 int b2q_wnq_fwd_f32(b2q_ctx* ctx, const float* x, float* y, int64_t rows, int64_t cols, int per_channel, float qlevel,

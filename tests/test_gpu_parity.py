@@ -326,3 +326,25 @@ def test_full_size_properties(T, shape):
     op_cg.backward(["write"], [dy], [x], [y], [dx], [aux])
     inside = (x > -aux) & (x < aux)
     assert T.equal(dx, dy * inside)
+
+
+def test_int8_export_reproduces_fake_quant(T):
+    """codes * step must equal the fake-quant output exactly (weights per channel, clipped activations)."""
+    import b200quant._kernels as K
+    from b200quant import _lib
+    rng = np.random.default_rng(12)
+    w = (rng.standard_normal((64, 32, 3, 3)) * 0.05).astype(F)
+    op, _ = make("Quantization_int8_V2", quant_mode="minmax", is_weight=True, is_weight_perchannel=True)
+    wd, wq, aux = dev(T, w), dev(T, np.zeros_like(w)), dev(T, np.ones(64, F))
+    op.forward(True, ["write"], [wd], [wq], [aux])
+    codes, steps = K.export_int8(wd, aux, 127, _lib.CLIP_NONE, view=(1, 64, 32 * 9))
+    assert codes.dtype == T.int8 and int(codes.abs().max()) == 127
+    deq = codes.float() * steps.view(-1, 1, 1, 1)
+    assert T.equal(deq, wq)          # value-equal (an int8 zero cannot carry the sign of -0.0)
+    x = (rng.standard_normal((8, 16, 14, 14)) * 2).astype(F)
+    opc, _ = make("ClipGrad_Quantization_int8", quant_mode="minmax", is_weight=False)
+    xd, xq, a1 = dev(T, x), dev(T, np.zeros_like(x)), dev(T, np.full(1, 1.5, F))
+    opc.forward(False, ["write"], [xd], [xq], [a1])
+    codes, steps = K.export_int8(xd, a1, 127, _lib.CLIP_SYM)
+    assert T.equal(codes.float() * steps, xq)
+    assert int(codes.max()) == 127 and int(codes.min()) == -127

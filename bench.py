@@ -535,26 +535,33 @@ def main():
 
     # ---- e2e: host buffers through the host C ABI (rank-local; N ranks run it concurrently) ----
     if not args.no_e2e and op_type == "Quantization_int8_V2":
-        hstep, b_in, b_out = host_step_factory(torch, nodes, ctx)
-        hstep()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
+        try:
+            hstep, b_in, b_out = host_step_factory(torch, nodes, ctx)
             hstep()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        line["e2e"] = {"value": world * batch * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": b_in,
-                       "d2h_bytes_per_step": b_out, "steps": args.e2e_steps, "ms_per_step": dt / args.e2e_steps * 1e3,
-                       "path": "CustomOp.forward/backward with pinned HOST tensors -> b2q_*_host_f32"}
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                hstep()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dt], device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            line["e2e"] = {"value": world * batch * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": b_in,
+                           "d2h_bytes_per_step": b_out, "steps": args.e2e_steps, "ms_per_step": dt / args.e2e_steps * 1e3,
+                           "path": "CustomOp.forward/backward with pinned HOST tensors -> b2q_*_host_f32 (three-stream "
+                                   "pipeline over a staging ring; PCIe-bound: ~46 GB/s per direction on this box)"}
+        except Exception as e:  # pragma: no cover - e.g. not enough lockable host memory
+            line["e2e"] = {"value": None, "unit": UNIT, "error": str(e).splitlines()[0][:200]}
 
     if rank == 0 and world == 1 and not args.no_cpu and op_type == "Quantization_int8_V2":
-        line["cpu_baseline"] = cpu_baseline(total_elems, batch)
+        try:
+            line["cpu_baseline"] = cpu_baseline(total_elems, batch)
+        except Exception as e:  # pragma: no cover
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "error": str(e).splitlines()[0][:200]}
 
     if rank == 0:
         emit(line)

@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-full-model", action="store_true",
+                    help="skip the context leg that trains the whole ResNet-50 (library convolutions + these operators)")
     ap.add_argument("--profile", action="store_true",
                     help="profiling aid: only the per-node eager step (warm-up + timed), nothing else")
     return ap.parse_args()
@@ -188,6 +190,40 @@ def host_step_factory(torch, nodes, ctx):
 # ---------------------------------------------------------------------------------------------------------
 CPU_SAMPLE = [("act", (256, 64, 56, 56)), ("act", (256, 256, 14, 14)), ("act", (256, 2048)),
               ("weight", (512, 512, 3, 3)), ("weight", (64, 3, 7, 7))]
+
+
+def full_model_leg(torch, device, batch, steps=8, warmup=3):
+    """Context only (not the metric): one SGD step of the whole ResNet-50 int8-QAT network of symbol/resnet_int8.py --
+    cuDNN/cuBLAS convolutions, BatchNorm and pooling from torch, every conv/FC input and weight through this package's
+    Quantization_int8_V2 nodes -- to show what share of a training step the quantization path is."""
+    from b200quant.harness import ResNetInt8
+    torch.manual_seed(11)
+    model = ResNetInt8().to(device)
+    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+    x = torch.randn(batch, 3, 224, 224, device=device)
+    y = torch.randint(0, 1000, (batch,), device=device)
+
+    def train_step():
+        opt.zero_grad(set_to_none=True)
+        loss = torch.nn.functional.cross_entropy(model(x), y)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(warmup):
+        train_step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = train_step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"images_per_sec": batch / (ms / 1e3), "ms_per_step": ms, "batch": batch, "steps": steps,
+            "loss": float(loss), "conv_math": "torch/cuDNN fp32 (TF32 %s)" % ("on" if torch.backends.cudnn.allow_tf32 else "off"),
+            "note": "whole ResNet-50 int8-QAT SGD step, eager torch autograd; convolutions/BN are library code, "
+                    "quantization nodes are this package's (108 nodes); context for the metric, not the metric"}
 
 
 def cpu_reference_step(sample_state):
@@ -562,6 +598,16 @@ def main():
             line["cpu_baseline"] = cpu_baseline(total_elems, batch)
         except Exception as e:  # pragma: no cover
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "error": str(e).splitlines()[0][:200]}
+
+    if world == 1 and not args.no_full_model and not args.profile and args.workload == "resnet50_int8":
+        try:
+            del nodes
+            torch.cuda.empty_cache()
+            fm = full_model_leg(torch, device, batch)
+            fm["quant_path_share_of_step"] = (ms / args.steps) / fm["ms_per_step"]
+            line["full_model"] = fm
+        except Exception as e:  # pragma: no cover
+            line["full_model"] = {"images_per_sec": None, "error": str(e).splitlines()[0][:200]}
 
     if rank == 0:
         emit(line)

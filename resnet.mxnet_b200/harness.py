@@ -195,3 +195,79 @@ class SimpleCifarNet(nn.Module):
         x = torch.relu(self.stage2_bn(self.stage2_conv(x)))
         x = x.mean(dim=(2, 3))                       # global average pool (simple.py:14)
         return self.fc1(x)
+
+
+class _ResidualUnitInt8(nn.Module):
+    """residual_unit_int8 (symbol/resnet_int8.py:12-67): pre-activation unit, every conv through quant_conv; the
+    shortcut conv of a dim-changing unit quantizes act1 again with its own node (:38)."""
+
+    def __init__(self, name, channel, num_filter, stride, dim_match, bottle_neck, style, bn_mom=0.9, eps=1e-5, **qkw):
+        super(_ResidualUnitInt8, self).__init__()
+        self.dim_match, self.bottle_neck = dim_match, bottle_neck
+        mom = 1.0 - bn_mom
+        if bottle_neck:
+            mid = int(num_filter * 0.25)
+            self.bn1 = nn.BatchNorm2d(channel, eps=eps, momentum=mom)
+            self.conv1 = QuantConv2d(name + "_conv1", channel, mid, (1, 1), (1, 1), (0, 0), True, style=style, **qkw)
+            self.bn2 = nn.BatchNorm2d(mid, eps=eps, momentum=mom)
+            self.conv2 = QuantConv2d(name + "_conv2", mid, mid, (3, 3), stride, (1, 1), True, style=style, **qkw)
+            self.bn3 = nn.BatchNorm2d(mid, eps=eps, momentum=mom)
+            self.conv3 = QuantConv2d(name + "_conv3", mid, num_filter, (1, 1), (1, 1), (0, 0), True, style=style, **qkw)
+        else:
+            self.bn1 = nn.BatchNorm2d(channel, eps=eps, momentum=mom)
+            self.conv1 = QuantConv2d(name + "_conv1", channel, num_filter, (3, 3), stride, (1, 1), True, style=style, **qkw)
+            self.bn2 = nn.BatchNorm2d(num_filter, eps=eps, momentum=mom)
+            self.conv2 = QuantConv2d(name + "_conv2", num_filter, num_filter, (3, 3), (1, 1), (1, 1), True, style=style, **qkw)
+        self.sc = None if dim_match else QuantConv2d(name + "_sc", channel, num_filter, (1, 1), stride, (0, 0), True,
+                                                     style=style, **qkw)
+
+    def forward(self, x):
+        act1 = torch.relu(self.bn1(x))
+        if self.bottle_neck:
+            out = self.conv1(act1)
+            out = self.conv2(torch.relu(self.bn2(out)))
+            out = self.conv3(torch.relu(self.bn3(out)))
+        else:
+            out = self.conv1(act1)
+            out = self.conv2(torch.relu(self.bn2(out)))
+        return out + (x if self.sc is None else self.sc(act1))
+
+
+class ResNetInt8(nn.Module):
+    """resnet_int8 (symbol/resnet_int8.py:69-131) as a torch benchmark harness: the convolutions / BatchNorm / pooling
+    are library code; every conv and the FC go through the quantization operators of this package."""
+
+    def __init__(self, units=(3, 4, 6, 3), filter_list=(64, 256, 512, 1024, 2048), num_classes=1000, bottle_neck=True,
+                 dataset_type="imagenet", style="quant_ops", bn_mom=0.9, **qkw):
+        super(ResNetInt8, self).__init__()
+        self.dataset_type = dataset_type
+        self.bn_data = nn.BatchNorm2d(3, eps=2e-5, momentum=1.0 - bn_mom, affine=False)    # fix_gamma=True (:86)
+        if dataset_type == "imagenet":
+            self.conv0 = QuantConv2d("conv0", 3, filter_list[0], (7, 7), (2, 2), (3, 3), True, style=style, **qkw)
+            self.bn0 = nn.BatchNorm2d(filter_list[0], eps=1e-5, momentum=1.0 - bn_mom)
+        else:
+            self.conv0 = QuantConv2d("conv0", 3, filter_list[0], (3, 3), (1, 1), (1, 1), True, style=style, **qkw)
+        blocks = []
+        for i, n_units in enumerate(units):
+            stride = (1, 1) if i == 0 else (2, 2)
+            blocks.append(_ResidualUnitInt8("stage%d_unit1" % (i + 1), filter_list[i], filter_list[i + 1], stride, False,
+                                            bottle_neck, style, bn_mom, **qkw))
+            for j in range(n_units - 1):
+                blocks.append(_ResidualUnitInt8("stage%d_unit%d" % (i + 1, j + 2), filter_list[i + 1], filter_list[i + 1],
+                                                (1, 1), True, bottle_neck, style, bn_mom, **qkw))
+        self.blocks = nn.Sequential(*blocks)
+        self.bn1 = nn.BatchNorm2d(filter_list[-1], eps=1e-5, momentum=1.0 - bn_mom)
+        self.fc1 = QuantLinear("fc1", filter_list[-1], num_classes, style=style, **qkw)
+
+    def forward(self, x):
+        x = self.conv0(self.bn_data(x))
+        if self.dataset_type == "imagenet":
+            x = torch.nn.functional.max_pool2d(torch.relu(self.bn0(x)), 3, 2, 1)
+        x = self.blocks(x)
+        x = torch.relu(self.bn1(x)).mean(dim=(2, 3))
+        return self.fc1(x)
+
+
+def quant_nodes(model):
+    """All Custom quantization nodes of a model, in definition order."""
+    return [m for m in model.modules() if isinstance(m, Custom)]

@@ -96,3 +96,31 @@ def test_simple_net_training_matches_oracle_twin(style):
             np.testing.assert_allclose(got, want, rtol=2e-3), (n, suf)
     assert set(aux) == {n + s + "_minmax" for n in names for s in suffix}
     assert all(v["delay_quant"] == 0 for v in state.values())
+
+
+@pytest.mark.gpu
+def test_resnet_int8_cifar_trains():
+    """resnet_int8 topology (symbol/resnet_int8.py) at CIFAR size: every conv / FC through the quantization nodes,
+    loss falls over a few SGD steps and the aux thresholds are populated."""
+    import torch
+    from b200quant.harness import ResNetInt8, quant_nodes
+    torch.manual_seed(3)
+    dev = torch.device("cuda", 0)
+    model = ResNetInt8(units=(1, 1, 1), filter_list=(16, 16, 32, 64), num_classes=10, bottle_neck=False,
+                       dataset_type="cifar10").to(dev)
+    assert len(quant_nodes(model)) == 2 * (1 + 2 + 3 + 3 + 1)
+    opt = torch.optim.SGD(model.parameters(), lr=0.05, momentum=0.9)
+    x = torch.randn(64, 3, 32, 32, device=dev)
+    y = torch.randint(0, 10, (64,), device=dev)
+    losses = []
+    for _ in range(25):
+        opt.zero_grad()
+        loss = torch.nn.functional.cross_entropy(model(x), y)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert all(l == l for l in losses)
+    assert losses[-1] < 0.5 * losses[0]
+    for node in quant_nodes(model):
+        for a in node.aux_list():
+            assert float(a.abs().max()) > 0

@@ -371,6 +371,10 @@ def main():
                 exchange = "fused peer-memory kernels (b2q_peer_minmax_quant_fwd_f32)"
             except Exception as e:  # pragma: no cover
                 exchange += " (peer path unavailable: %s)" % (str(e).splitlines()[0][:100],)
+        # operators without a fused exchange (the mean-based GDRQ thresholds) keep the NCCL call on their forward path
+        nccl_forward = any(getattr(nd["op"], "sync", None) is not None for nd in nodes)
+        if nccl_forward and exchange.startswith("fused peer"):
+            exchange = "nccl allreduce(max) of the per-node statistic (no fused exchange for this operator)"
         wn = [nd for nd in nodes if nd["kind"] == "weight"]
         bucket = GradBucket([nd["shape"] for nd in wn], device)
         for nd, view in zip(wn, bucket.views):

@@ -20,11 +20,27 @@ class GDRQ_PY(CustomOp):
         self.QUANT_LEVEL = 2 ** (self.nbits) - 1
         self.fix_alpha = fix_alpha
         self.ktimes = ktimes
+        self.sync = None        # dist.ThresholdSync: max over ranks of the mean|x| statistic (activations only)
+        self._stat = None
 
     def forward(self, is_train, req, in_data, out_data, aux):
         do_round = not (self.delay_quant > 0)          # GDRQ.py:81-85 / :110-114
         if self.delay_quant > 0:
             self.delay_quant -= 1
+        if self.sync is not None and not self.is_weight and not self.fix_alpha:
+            # data parallel: mean|x| per group -> allreduce(max) -> alpha update -> clip + round, so that every rank
+            # applies the same alpha (k*max(mean) == max(k*mean): the scaling is monotonic)
+            x, alpha = in_data[0], aux[0]
+            view = K._gdrq_view(tuple(x.shape), self.group_size, False)
+            if self._stat is None:
+                import torch
+                self._stat = torch.empty(view[1], dtype=torch.float32, device=x.device)
+            K.meanabs(x, self._stat, view)
+            self.sync(self._stat)
+            K.threshold_update(_lib.UPD_GDRQ_ACT, self._stat, alpha, self.ktimes, self.lamda)
+            K.qdq(x, out_data[0], alpha, self.QUANT_LEVEL, _lib.CLIP_SYM if view[1] == 1 else _lib.CLIP_WHERE_LE,
+                  req[0], view=view, do_round=do_round)
+            return
         K.gdrq_fwd(in_data[0], out_data[0], aux[0], self.group_size, self.is_weight, self.fix_alpha, do_round,
                    self.QUANT_LEVEL, self.ktimes, self.lamda, req[0])
 

@@ -12,6 +12,7 @@ backward (:122-129): gradient only to ``bn_output``; the six other inputs get ze
 import os
 
 from . import _kernels as K
+from . import _lib
 from .operator import CustomOp, CustomOpProp, py_bool, py_literal, register
 
 try:
@@ -32,6 +33,7 @@ class GDRQ_Fold_BN(CustomOp):
         self.ema_decay = ema_decay
         self.QUANT_LEVEL = 127
         self.init = True
+        self.sync = None        # dist.ThresholdSync: max over ranks of mean|data| before the EMA
         self.name = name
         self.num_filter = num_filter
         self.num_group = num_group
@@ -82,7 +84,18 @@ class GDRQ_Fold_BN(CustomOp):
                 # the reference only binds `thresholds` when training (:55-58) and then reads it (:67)
                 raise NameError("name 'thresholds' is not defined")
             data_q = self._empty_like(data)
-            K.foldbn_data_fwd(data, data_q, aux[0], self.init, self.ema_decay)   # :53-68
+            if self.sync is not None:
+                # data parallel: mean|x| -> allreduce(max) -> t = 2*mean, EMA (:58-64) -> clip by t, scale by aux (:65-68)
+                if getattr(self, "_stat", None) is None:
+                    self._stat = self._empty_like(aux[0], (1,))
+                    self._clip = self._empty_like(aux[0], (1,))
+                K.meanabs(data, self._stat)
+                self.sync(self._stat)
+                K.threshold_update(_lib.UPD_TWICE_STORE if self.init else _lib.UPD_TWICE_EMA, self._stat, aux[0],
+                                   self.ema_decay, 1 - self.ema_decay, clip_out=self._clip)
+                K.qdq(data, data_q, aux[0], 127.0, _lib.CLIP_SYM, "write", clip_thr=self._clip)
+            else:
+                K.foldbn_data_fwd(data, data_q, aux[0], self.init, self.ema_decay)   # :53-68
             self.init = False
         else:
             data_q = data

@@ -15,9 +15,12 @@ from ``graph_optimize.py:199-292``:
 ``quantize_op_name`` mapping (``:165-195``): Quantization_int8 -> the Python Quantization_int8_V2 (the reference maps it
 to the fork's C++ contrib op, whose source is absent: SURVEY.md F3), QIL -> QIL_PY, DoReFa_PY, PACT -> PACT_PY,
 GDRQ -> GDRQ_PY, WNQ -> WNQ_PY (the reference accepts the name and then fails with UnboundLocalError, ``:162-163``);
-the ``*_CXX`` names need the fork and raise.
+the ``*_CXX`` names (``mx.sym.contrib.{DoReFa,PACT,GDRQ}`` of the fork, source absent) run the Python twin's
+arithmetic on the same kernels, with a one-time warning that their parity is unpinned.
 ``fix_bn`` / ``merge_bn`` are the inference helpers of ``graph_optimize.py:37-157``.
 """
+import warnings
+
 import torch
 import torch.nn as nn
 
@@ -65,6 +68,12 @@ def create_quant_node(var_name, setting):
     attrs = dict(_get(setting, "attrs", {}) or {})
     init_value = _get(setting, "init_value", None)
     assert name in _KNOWN, "unknown quantize_op_name %r" % (name,)
+    if name.endswith("_CXX"):
+        warnings.warn("%s is a C++ operator of the modified MXNet fork (README.md:7) whose source is not available; "
+                      "using the arithmetic of its Python twin %s (parity with the C++ operator is unpinned)"
+                      % (name, {"DoReFa_CXX": "DoReFa_PY", "PACT_CXX": "PACT_PY", "GDRQ_CXX": "GDRQ_PY"}[name]),
+                      stacklevel=2)
+        name = {"DoReFa_CXX": "DoReFa_PY", "PACT_CXX": "PACT", "GDRQ_CXX": "GDRQ"}[name]
     if name == "Quantization_int8":
         # the C++ op's extra attributes (nbits, grad_mode, fix_act_scale) have no counterpart in the Python op
         keep = {k: v for k, v in attrs.items()
@@ -83,7 +92,7 @@ def create_quant_node(var_name, setting):
     if name == "WNQ":
         keep = {k: v for k, v in attrs.items() if k in ("nbits", "is_perchannel")}
         return QuantNode(var_name, "WNQ_PY", keep)
-    raise RuntimeError("%s needs the modified MXNet fork's C++ operator (README.md:7); use the *_PY operator" % name)
+    raise AssertionError("unreachable: %r" % (name,))
 
 
 class _Share(object):

@@ -69,6 +69,43 @@ def main():
                 torch.cuda.synchronize()
                 dist.barrier()
                 ex.close()
+    # GDRQ_PY activations (mean-based threshold): statistic = max over ranks of mean|x|, then the alpha update
+    for group_size in (-1, 4):
+        op = b200quant.get_prop("GDRQ_PY")(nbits="8", group_size=str(group_size), is_weight="False", lamda="0.001",
+                                           ktimes="3").create_operator(None, None, None)
+        op.sync = ThresholdSync()
+        groups = 1 if group_size == -1 else 16 // group_size
+        alpha = torch.ones(groups, device="cuda")
+        alpha_ref = np.ones(groups, F)
+        for step in range(3):
+            rng = np.random.default_rng(77 * step + 5 + rank)
+            x = (rng.standard_normal((4, 16, 14, 14)) * (1.0 + rank + 0.5 * step)).astype(F)
+            xd = torch.from_numpy(x).cuda()
+            yd = torch.zeros_like(xd)
+            op.forward(True, ["write"], [xd], [yd], [alpha])
+            if group_size == -1:
+                mean = np.atleast_1d(qo.mx_mean(np.abs(x))).astype(F)
+                a_full = None
+            else:   # channel-major groups of `group_size` channels (GDRQ.py:88-98)
+                xg = np.ascontiguousarray(np.swapaxes(x, 0, 1)).reshape(groups, -1)
+                mean = np.array([qo.mx_mean(np.abs(xg[g])) for g in range(groups)], F)
+            m = torch.from_numpy(mean).cuda()
+            dist.all_reduce(m, op=dist.ReduceOp.MAX)
+            thr = qo.mx_mul(m.cpu().numpy(), F(3.0))
+            alpha_ref = qo.mx_add(alpha_ref, qo.mx_mul(F(0.001), qo.mx_sub(alpha_ref, thr)))
+            a_el = alpha_ref[0] if group_size == -1 else np.repeat(alpha_ref, group_size)[None, :, None, None]
+            if group_size == -1:
+                c = qo.mx_clip(x, -float(a_el), float(a_el))
+            else:
+                c = np.where(np.abs(x) <= a_el, x, (a_el * np.sign(x)).astype(F)).astype(F)
+            q = qo.mx_div(np.broadcast_to(np.asarray(a_el, F), x.shape), F(255))
+            want, _ = qo.qdq(c, q)
+            ok = bits(alpha.cpu().numpy(), alpha_ref) and bits(yd.cpu().numpy(), want)
+            if not ok:
+                failures += 1
+                print("rank %d FAIL GDRQ_PY group_size=%d step=%d alpha=%r want=%r" % (
+                    rank, group_size, step, alpha.cpu().numpy(), alpha_ref), flush=True)
+
     t = torch.tensor([failures], device="cuda")
     dist.all_reduce(t)
     if rank == 0:

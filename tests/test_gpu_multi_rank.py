@@ -33,6 +33,50 @@ def test_peer_exchange_world1_matches_plain_path():
         ex.close()
 
 
+def test_mean_based_ops_sync_path_matches_fused_path():
+    """GDRQ_PY / GDRQ_Fold_BN with a (world = 1, no-op) ThresholdSync take the reduce -> exchange -> update -> sweep
+    route built from the primitives; it has to give the bits of the fused entry points."""
+    import torch
+    import b200quant
+    from b200quant.dist import ThresholdSync
+    g = torch.Generator(device="cuda").manual_seed(9)
+    for group_size in (-1, 2, 8):
+        mk = lambda: b200quant.get_prop("GDRQ_PY")(nbits="4", group_size=str(group_size), is_weight="False",
+                                                   delay_quant="1").create_operator(None, None, None)
+        a, b = mk(), mk()
+        b.sync = ThresholdSync()
+        groups = 1 if group_size == -1 else 16 // group_size
+        al_a, al_b = torch.ones(groups, device="cuda"), torch.ones(groups, device="cuda")
+        for step, shape in enumerate([(4, 16, 9, 9), (2, 16, 28, 28), (3, 16, 1, 5)]):
+            x = torch.randn(shape, device="cuda", generator=g) * (1 + step)
+            ya, yb = torch.zeros_like(x), torch.zeros_like(x)
+            a.forward(True, ["write"], [x], [ya], [al_a])
+            b.forward(True, ["write"], [x], [yb], [al_b])
+            assert torch.equal(al_a.view(torch.int32), al_b.view(torch.int32)), (group_size, step)
+            assert torch.equal(ya.view(torch.int32), yb.view(torch.int32)), (group_size, step)
+        assert b.sync.calls == 3
+
+    mk = lambda: b200quant.get_prop("GDRQ_Fold_BN")(
+        quant_mode="minmax", is_weight_perchannel="True", name="c", num_filter="8", num_group="1", kernel="(3, 3)",
+        stride="(1, 1)", pad="(1, 1)", no_bias="True").create_operator(None, None, None)
+    a, b = mk(), mk()
+    b.sync = ThresholdSync()
+    w = torch.randn(8, 4, 3, 3, device="cuda", generator=g) * 0.2
+    gamma, beta = torch.rand(8, device="cuda", generator=g) + 0.5, torch.randn(8, device="cuda", generator=g)
+    mean, var = torch.randn(8, device="cuda", generator=g), torch.rand(8, device="cuda", generator=g) + 0.1
+    aux_a = [torch.ones(1, device="cuda"), torch.ones(8, device="cuda")]
+    aux_b = [torch.ones(1, device="cuda"), torch.ones(8, device="cuda")]
+    for step in range(3):
+        x = torch.randn(2, 4, 10, 10, device="cuda", generator=g) * (1 + step)
+        bn_out = torch.zeros(2, 8, 10, 10, device="cuda")
+        ya, yb = torch.zeros_like(bn_out), torch.zeros_like(bn_out)
+        a.forward(True, ["write"], [x, w, bn_out, gamma, beta, mean, var], [ya], aux_a)
+        b.forward(True, ["write"], [x, w, bn_out, gamma, beta, mean, var], [yb], aux_b)
+        assert torch.equal(aux_a[0].view(torch.int32), aux_b[0].view(torch.int32)), step
+        assert torch.equal(a.data_q.view(torch.int32), b.data_q.view(torch.int32)), step
+        assert torch.equal(ya.view(torch.int32), yb.view(torch.int32)), step
+
+
 def test_two_rank_threshold_exchange():
     import torch
     if torch.cuda.device_count() < 2:

@@ -58,8 +58,11 @@ def test_create_quant_node_mapping():
                                  "attrs": {"nbits": "4", "fix_alpha": "False", "group_size": "-1", "is_weight": "True",
                                            "lamda": "0.001", "delay_quant": "0", "ktimes": "3"}})
     assert gd.node.op_type == "GDRQ_PY" and gd.node.aux_init == 0.5
-    with pytest.raises(RuntimeError):
-        create_quant_node("x", {"quantize_op_name": "GDRQ_CXX", "attrs": {}})
+    with pytest.warns(UserWarning, match="parity with the C\\+\\+ operator is unpinned"):
+        cxx = create_quant_node("x", {"quantize_op_name": "GDRQ_CXX", "attrs": {"nbits": "8", "is_weight": "False"}})
+    assert cxx.node.op_type == "GDRQ_PY"
+    with pytest.warns(UserWarning):
+        assert create_quant_node("r", {"quantize_op_name": "PACT_CXX", "attrs": {}}).param_names == ["gamma"]
     with pytest.raises(AssertionError):
         create_quant_node("x", {"quantize_op_name": "nope", "attrs": {}})
 

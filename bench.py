@@ -346,6 +346,15 @@ def main():
 
     fn, batch, op_type = WORKLOADS[args.workload]
     batch = args.batch or batch
+    full_model = None
+    if world == 1 and not args.no_full_model and not args.profile and args.workload == "resnet50_int8":
+        try:   # context leg, run first while the device memory is still free
+            full_model = full_model_leg(torch, device, batch)
+        except Exception as e:  # pragma: no cover
+            full_model = {"images_per_sec": None, "error": str(e).splitlines()[0][:200]}
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
     node_list = fn(batch)
     sm = summary(node_list)
     total_elems = sm["act_elems"] + sm["weight_elems"]
@@ -603,15 +612,10 @@ def main():
         except Exception as e:  # pragma: no cover
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "error": str(e).splitlines()[0][:200]}
 
-    if world == 1 and not args.no_full_model and not args.profile and args.workload == "resnet50_int8":
-        try:
-            del nodes
-            torch.cuda.empty_cache()
-            fm = full_model_leg(torch, device, batch)
-            fm["quant_path_share_of_step"] = (ms / args.steps) / fm["ms_per_step"]
-            line["full_model"] = fm
-        except Exception as e:  # pragma: no cover
-            line["full_model"] = {"images_per_sec": None, "error": str(e).splitlines()[0][:200]}
+    if full_model is not None:
+        if full_model.get("ms_per_step"):
+            full_model["quant_path_share_of_step"] = (ms / args.steps) / full_model["ms_per_step"]
+        line["full_model"] = full_model
 
     if rank == 0:
         emit(line)

@@ -242,6 +242,14 @@ int b2q_peer_mailbox_destroy(b2q_ctx* ctx, void* mailbox);
 int b2q_peer_minmax_quant_fwd_f32(b2q_ctx* ctx, int variant, const float* x, float* y, float* aux, int64_t n,
                                   int init, float ema_decay, float one_minus_decay, void* const* mailboxes,
                                   int rank, int world, uint32_t sequence, void* stream);
+/* The same exchange for the operators whose threshold comes from mean|x| (statistic = max over ranks of the per-rank
+ * mean): whole-tensor activations of GDRQ_PY (upd_mode B2Q_UPD_GDRQ_ACT, p0 = ktimes,
+ * p1 = lamda, qlevel = 2^nbits-1; core/operator/GDRQ.py:69-86 with rounding on) and the data path of GDRQ_Fold_BN
+ * (B2Q_UPD_TWICE_STORE on the first batch, then B2Q_UPD_TWICE_EMA, p0 = ema_decay, p1 = 1-ema_decay, qlevel = 127:
+ * clip with the batch threshold, scale with the EMA one; symbol/fold_bn_v1_gdrq.py:53-68).                       */
+int b2q_peer_meanabs_quant_fwd_f32(b2q_ctx* ctx, int upd_mode, const float* x, float* y, float* aux, int64_t n,
+                                   float p0, float p1, float qlevel, void* const* mailboxes, int rank, int world,
+                                   void* stream);
 
 /* ---- host-buffer path: the call a framework whose tensors live in HOST memory makes (bench.py "e2e") --
  * Same semantics as the device entry points but x / y / aux are HOST pointers (pinned for full speed).

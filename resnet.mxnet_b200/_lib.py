@@ -64,6 +64,7 @@ _CTX_FUNCS = {
     "b2q_peer_mailbox_destroy": [_P],
     "b2q_peer_minmax_quant_fwd_f32": [_I, _P, _P, _P, _L, _I, _F, _F, ctypes.POINTER(ctypes.c_void_p), _I, _I,
                                       ctypes.c_uint32, _P],
+    "b2q_peer_meanabs_quant_fwd_f32": [_I, _P, _P, _P, _L, _F, _F, _F, ctypes.POINTER(ctypes.c_void_p), _I, _I, _P],
     "b2q_multi_plan_create": [_P, _I, ctypes.POINTER(ctypes.c_void_p)],
     "b2q_multi_plan_destroy": [_P],
     "b2q_multi_weight_quant_fwd_f32": [_P, _I, _I, _P],

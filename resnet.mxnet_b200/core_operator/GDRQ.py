@@ -21,13 +21,19 @@ class GDRQ_PY(CustomOp):
         self.fix_alpha = fix_alpha
         self.ktimes = ktimes
         self.sync = None        # dist.ThresholdSync: max over ranks of the mean|x| statistic (activations only)
+        self.peer = None        # dist.PeerThresholdExchange: the same exchange fused into the two forward kernels
         self._stat = None
 
     def forward(self, is_train, req, in_data, out_data, aux):
         do_round = not (self.delay_quant > 0)          # GDRQ.py:81-85 / :110-114
         if self.delay_quant > 0:
             self.delay_quant -= 1
-        if self.sync is not None and not self.is_weight and not self.fix_alpha:
+        if (self.peer is not None and not self.is_weight and not self.fix_alpha and do_round and self.group_size == -1
+                and req[0] in ("write", "inplace")):
+            self.peer.quantize_mean(_lib.UPD_GDRQ_ACT, in_data[0], out_data[0], aux[0], self.ktimes, self.lamda,
+                                    self.QUANT_LEVEL)
+            return
+        if (self.sync is not None or self.peer is not None) and not self.is_weight and not self.fix_alpha:
             # data parallel: mean|x| per group -> allreduce(max) -> alpha update -> clip + round, so that every rank
             # applies the same alpha (k*max(mean) == max(k*mean): the scaling is monotonic)
             x, alpha = in_data[0], aux[0]
@@ -36,6 +42,9 @@ class GDRQ_PY(CustomOp):
                 import torch
                 self._stat = torch.empty(view[1], dtype=torch.float32, device=x.device)
             K.meanabs(x, self._stat, view)
+            if self.sync is None:   # peer exchange attached but this call is outside its fused case (delay_quant)
+                from ..dist import ThresholdSync
+                self.sync = ThresholdSync()
             self.sync(self._stat)
             K.threshold_update(_lib.UPD_GDRQ_ACT, self._stat, alpha, self.ktimes, self.lamda)
             K.qdq(x, out_data[0], alpha, self.QUANT_LEVEL, _lib.CLIP_SYM if view[1] == 1 else _lib.CLIP_WHERE_LE,

@@ -44,14 +44,16 @@ __device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long lon
     return v;
 }
 
-// kernel 1: whole-tensor max|x|, last block publishes to every rank's mailbox
-template <int UNROLL>
+// kernel 1: whole-tensor max|x| (IS_MAX) or mean|x| (sum of |x| in double, rounded once, / count -- the arithmetic of
+// reduce_flat_kernel), last block publishes to every rank's mailbox
+template <bool IS_MAX, int UNROLL>
 __global__ void __launch_bounds__(B2Q_THREADS)
-reduce_peer_kernel(const float* __restrict__ x, FlatSplit sp, b2q_slot* slot, const float* aux, PeerBoxes pb) {
+reduce_peer_kernel(const float* __restrict__ x, FlatSplit sp, b2q_slot* slot, const float* aux, PeerBoxes pb,
+                   float count) {
     __shared__ double smem[32];
     __shared__ unsigned int s_ticket;
     float mx = 0.f;
-    double unused = 0.0;
+    double acc = 0.0;
     const float* xb = x + sp.head;
     const int64_t tile = (int64_t)B2Q_THREADS * UNROLL;
     const int64_t ntiles = (sp.n8 + tile - 1) / tile;
@@ -68,15 +70,15 @@ reduce_peer_kernel(const float* __restrict__ x, FlatSplit sp, b2q_slot* slot, co
             }
         }
 #pragma unroll
-        for (int k = 0; k < UNROLL; ++k) acc8<true>(unused, mx, v[k]);
+        for (int k = 0; k < UNROLL; ++k) acc8<IS_MAX>(acc, mx, v[k]);
     }
     if (blockIdx.x == 0) {
-        if ((int64_t)threadIdx.x < sp.head) mx = fmaxf(mx, fabsf(x[threadIdx.x]));
-        if ((int64_t)threadIdx.x < sp.tail) mx = fmaxf(mx, fabsf(x[sp.head + 8 * sp.n8 + threadIdx.x]));
+        if ((int64_t)threadIdx.x < sp.head) acc1<IS_MAX>(acc, mx, x[threadIdx.x]);
+        if ((int64_t)threadIdx.x < sp.tail) acc1<IS_MAX>(acc, mx, x[sp.head + 8 * sp.n8 + threadIdx.x]);
     }
-    const float r = (float)block_reduce<true>((double)mx, smem);
+    const double r = block_reduce<IS_MAX>(IS_MAX ? (double)mx : acc, smem);
     if (threadIdx.x == 0) {
-        slot->partial[blockIdx.x] = (double)r;
+        slot->partial[blockIdx.x] = r;
         __threadfence();
         s_ticket = atomicAdd(&slot->ticket, 1u);
     }
@@ -84,12 +86,16 @@ reduce_peer_kernel(const float* __restrict__ x, FlatSplit sp, b2q_slot* slot, co
     if (s_ticket != gridDim.x - 1) return;
     __threadfence();
     float m = 0.f;
-    for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) m = fmaxf(m, (float)__ldcg(&slot->partial[i]));
-    const float tot = (float)block_reduce<true>((double)m, smem);
+    double a = 0.0;
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
+        const double p = __ldcg(&slot->partial[i]);
+        if (IS_MAX) m = fmaxf(m, (float)p); else a += p;
+    }
+    const double tot = block_reduce<IS_MAX>(IS_MAX ? (double)m : a, smem);
     __shared__ float s_tot;
     __shared__ unsigned int s_seq;
     if (threadIdx.x == 0) {
-        s_tot = tot;
+        s_tot = IS_MAX ? (float)tot : __fdiv_rn((float)tot, count);
         slot->scale[0] = aux[0];   // snapshot of the old threshold for the sweep
         slot->ticket = 0;
         // the sequence number lives on the device (every rank issues the same calls, so the counters stay in step);
@@ -111,7 +117,7 @@ template <int CLIP, int UNROLL, int LDPOL, int STPOL>
 __global__ void __launch_bounds__(B2Q_THREADS)
 qdq_peer_kernel(const float* __restrict__ x, float* __restrict__ y, FlatSplit sp, const unsigned long long* mybox,
                 int world, const unsigned int* counters, const float* aux_old, UpdateArgs u, float qlevel, int fast,
-                int reverse) {
+                int reverse, int clip_with_fresh) {
     __shared__ float s_stat;
     if (threadIdx.x < 32) {
         const unsigned int seq = counters[1];   // written by this call's reduction kernel (same stream)
@@ -135,8 +141,9 @@ qdq_peer_kernel(const float* __restrict__ x, float* __restrict__ y, FlatSplit sp
     float fresh, next;
     compute_update(u.mode, u.p0, u.p1, a_old, s_stat, fresh, next);
     const float T = next;
+    const float Tc = clip_with_fresh ? fresh : T;   // fold_bn_v1_gdrq.py:67 clips with the batch threshold
     if (blockIdx.x == 0 && threadIdx.x == 0) u.aux[0] = next;
-    const QScale s = make_qscale(T, qlevel, fast != 0 && !(CLIP != B2Q_CLIP_NONE && !(T >= 0.f)));
+    const QScale s = make_qscale(T, qlevel, fast != 0 && !(CLIP != B2Q_CLIP_NONE && !(Tc >= 0.f)));
     const float* xb = x + sp.head;
     float* yb = y + sp.head;
     const int64_t tile = (int64_t)B2Q_THREADS * UNROLL;
@@ -155,7 +162,7 @@ qdq_peer_kernel(const float* __restrict__ x, float* __restrict__ y, FlatSplit sp
             const int64_t i = base + (int64_t)k * B2Q_THREADS;
             if (i < sp.n8) {
                 f8 o;
-                qdq8<CLIP>(v[k], o, T, s);
+                qdq8<CLIP>(v[k], o, Tc, s);
                 st_f8<STPOL>(yb + 8 * i, o);
             }
         }
@@ -166,7 +173,7 @@ qdq_peer_kernel(const float* __restrict__ x, float* __restrict__ y, FlatSplit sp
         if (tid < sp.head) idx = tid;
         else if (tid - sp.head < sp.tail) idx = sp.head + 8 * sp.n8 + (tid - sp.head);
         if (idx >= 0) {
-            y[idx] = __fmul_rn(quant_code_exact(clip_value(CLIP, x[idx], T), s.q), s.q);
+            y[idx] = __fmul_rn(quant_code_exact(clip_value(CLIP, x[idx], Tc), s.q), s.q);
         }
     }
 }
@@ -215,15 +222,12 @@ int b2q_peer_mailbox_destroy(b2q_ctx* ctx, void* mailbox) {
     return 0;
 }
 
-int b2q_peer_minmax_quant_fwd_f32(b2q_ctx* ctx, int variant, const float* x, float* y, float* aux, int64_t n, int init,
-                                  float ema_decay, float one_minus_decay, void* const* mailboxes, int rank, int world,
-                                  uint32_t sequence, void* stream) {
-    B2Q_CTX(ctx);
+// shared body: [reduce + publish] -> [poll + update + sweep]
+static int peer_quant_fwd(b2q_ctx* ctx, bool is_max, int upd_mode, float p0, float p1, int clip_mode, int clip_with_fresh,
+                          float qlevel, const float* x, float* y, float* aux, int64_t n, void* const* mailboxes, int rank,
+                          int world, cudaStream_t st) {
     B2Q_REQUIRE(x && y && aux && mailboxes && n >= 1, "bad argument");
-    B2Q_REQUIRE(variant == 0 || variant == 1, "variant must be 0 or 1");
     B2Q_REQUIRE(world >= 1 && world <= B2Q_PEER_MAX_RANKS && rank >= 0 && rank < world, "bad rank / world");
-    (void)sequence;   // kept in the ABI for logging; the authoritative counter is on the device
-    cudaStream_t st = (cudaStream_t)stream;
     FlatSplit sp = b2q_flat_split(x, n);
     B2Q_REQUIRE(same_misalignment(x, y) && sp.head <= B2Q_THREADS, "peer path needs equally aligned float32 buffers");
     PeerBoxes pb;
@@ -238,27 +242,53 @@ int b2q_peer_minmax_quant_fwd_f32(b2q_ctx* ctx, int variant, const float* x, flo
     {
         const int64_t grid = b2q_flat_grid(ctx, sp.n8, B2Q_REDUCE_UNROLL, ctx->reduce_blocks_per_sm);
         b2q_timed_launch tl(ctx, B2Q_KIND_REDUCE_FLAT, 4.0 * (double)n, st);
-        reduce_peer_kernel<B2Q_REDUCE_UNROLL><<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, sp, slot, aux, pb);
+        if (is_max)
+            reduce_peer_kernel<true, B2Q_REDUCE_UNROLL><<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, sp, slot, aux, pb, (float)n);
+        else
+            reduce_peer_kernel<false, B2Q_REDUCE_UNROLL><<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, sp, slot, aux, pb, (float)n);
         B2Q_LAUNCH_CHECK(ctx);
     }
     UpdateArgs u;
     memset(&u, 0, sizeof(u));
-    u.mode = (variant == 1 && init) ? B2Q_UPD_STORE : B2Q_UPD_EMA;   // clip_grad...py:42-46 / quant_ops.py:37
-    u.write_aux = 1; u.use_aux_as_scale = 1; u.p0 = ema_decay; u.p1 = one_minus_decay; u.aux = aux;
+    u.mode = upd_mode;
+    u.write_aux = 1; u.use_aux_as_scale = 1; u.p0 = p0; u.p1 = p1; u.aux = aux;
     {
         const int64_t grid = b2q_flat_grid(ctx, sp.n8, B2Q_QDQ_UNROLL);
         const unsigned long long* mybox = (const unsigned long long*)mailboxes[rank];
         const int rev = (ctx->reverse && n * 4 > ctx->reverse_min_bytes) ? 1 : 0;
         b2q_timed_launch tl(ctx, B2Q_KIND_QDQ_HOT, 8.0 * (double)n, st);
-        if (variant == 1)
+        if (clip_mode == B2Q_CLIP_SYM)
             qdq_peer_kernel<B2Q_CLIP_SYM, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, B2Q_QDQ_STPOL><<<(unsigned)grid, B2Q_THREADS, 0, st>>>(
-                x, y, sp, mybox, world, pb.counters, slot->scale, u, 127.f, ctx->fast_div, rev);
+                x, y, sp, mybox, world, pb.counters, slot->scale, u, qlevel, ctx->fast_div, rev, clip_with_fresh);
         else
             qdq_peer_kernel<B2Q_CLIP_NONE, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, B2Q_QDQ_STPOL><<<(unsigned)grid, B2Q_THREADS, 0, st>>>(
-                x, y, sp, mybox, world, pb.counters, slot->scale, u, 127.f, ctx->fast_div, rev);
+                x, y, sp, mybox, world, pb.counters, slot->scale, u, qlevel, ctx->fast_div, rev, clip_with_fresh);
         B2Q_LAUNCH_CHECK(ctx);
     }
     return 0;
+}
+
+int b2q_peer_minmax_quant_fwd_f32(b2q_ctx* ctx, int variant, const float* x, float* y, float* aux, int64_t n, int init,
+                                  float ema_decay, float one_minus_decay, void* const* mailboxes, int rank, int world,
+                                  uint32_t sequence, void* stream) {
+    B2Q_CTX(ctx);
+    B2Q_REQUIRE(variant == 0 || variant == 1, "variant must be 0 or 1");
+    (void)sequence;   // kept in the ABI for logging; the authoritative counter is on the device
+    // clip_grad...py:42-46 / quant_ops.py:37
+    return peer_quant_fwd(ctx, true, (variant == 1 && init) ? B2Q_UPD_STORE : B2Q_UPD_EMA, ema_decay, one_minus_decay,
+                          variant == 1 ? B2Q_CLIP_SYM : B2Q_CLIP_NONE, 0, 127.f, x, y, aux, n, mailboxes, rank, world,
+                          (cudaStream_t)stream);
+}
+
+int b2q_peer_meanabs_quant_fwd_f32(b2q_ctx* ctx, int upd_mode, const float* x, float* y, float* aux, int64_t n, float p0,
+                                   float p1, float qlevel, void* const* mailboxes, int rank, int world, void* stream) {
+    B2Q_CTX(ctx);
+    B2Q_REQUIRE(upd_mode == B2Q_UPD_GDRQ_ACT || upd_mode == B2Q_UPD_TWICE_STORE || upd_mode == B2Q_UPD_TWICE_EMA,
+                "upd_mode must be B2Q_UPD_GDRQ_ACT, B2Q_UPD_TWICE_STORE or B2Q_UPD_TWICE_EMA");
+    B2Q_REQUIRE(qlevel > 0.f, "qlevel must be positive");
+    // GDRQ.py:76-86 clips with the updated alpha; fold_bn_v1_gdrq.py:65-68 clips with the batch threshold
+    return peer_quant_fwd(ctx, false, upd_mode, p0, p1, B2Q_CLIP_SYM, upd_mode == B2Q_UPD_GDRQ_ACT ? 0 : 1, qlevel, x, y,
+                          aux, n, mailboxes, rank, world, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -103,6 +103,18 @@ class PeerThresholdExchange(object):
                       float(np.float32(ema_decay)), float(np.float32(1 - ema_decay)), self._boxes, self.rank, self.world,
                       self.sequence, current_stream(xb))
 
+    def quantize_mean(self, upd_mode, x, y, aux, p0, p1, qlevel):
+        """Whole-tensor activation forward of the mean-based operators (GDRQ_PY: upd_mode UPD_GDRQ_ACT, p0 = ktimes,
+        p1 = lamda; GDRQ_Fold_BN data: UPD_TWICE_STORE / UPD_TWICE_EMA, p0 = ema_decay, p1 = 1 - ema_decay) with the
+        mean|x| statistic maximised over all ranks."""
+        import numpy as np
+        from .dlpack import as_buffer, current_stream
+        xb, yb, ab = as_buffer(x), as_buffer(y, write=True), as_buffer(aux, write=True)
+        self.sequence += 1
+        self.ctx.call("b2q_peer_meanabs_quant_fwd_f32", int(upd_mode), xb.ptr, yb.ptr, ab.ptr, xb.numel,
+                      float(np.float32(p0)), float(np.float32(p1)), float(np.float32(qlevel)), self._boxes, self.rank,
+                      self.world, current_stream(xb))
+
     def close(self):
         for p in self._opened:
             self.ctx.call("b2q_peer_mailbox_close", p)
@@ -113,10 +125,14 @@ class PeerThresholdExchange(object):
 
 
 def attach_peer_exchange(ops, device, group=None):
-    """Route every activation minmax node in ``ops`` through the fused peer-memory exchange."""
+    """Route every activation node in ``ops`` that has a fused peer-memory exchange through it: the minmax operators,
+    whole-tensor GDRQ_PY activations and the data path of GDRQ_Fold_BN.  Grouped GDRQ activations (one threshold per
+    channel group) keep the NCCL sync."""
     ex = PeerThresholdExchange(device, group)
     for op in ops:
-        if not getattr(op, "is_weight", True) and hasattr(op, "VARIANT"):
+        kind = op.__class__.__name__
+        if (not getattr(op, "is_weight", True) and hasattr(op, "VARIANT")) \
+                or (kind == "GDRQ_PY" and not op.is_weight and op.group_size == -1) or kind == "GDRQ_Fold_BN":
             op.peer = ex
             op.sync = None
     return ex

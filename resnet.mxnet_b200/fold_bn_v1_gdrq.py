@@ -34,6 +34,7 @@ class GDRQ_Fold_BN(CustomOp):
         self.QUANT_LEVEL = 127
         self.init = True
         self.sync = None        # dist.ThresholdSync: max over ranks of mean|data| before the EMA
+        self.peer = None        # dist.PeerThresholdExchange: the same exchange fused into the two data kernels
         self.name = name
         self.num_filter = num_filter
         self.num_group = num_group
@@ -84,7 +85,10 @@ class GDRQ_Fold_BN(CustomOp):
                 # the reference only binds `thresholds` when training (:55-58) and then reads it (:67)
                 raise NameError("name 'thresholds' is not defined")
             data_q = self._empty_like(data)
-            if self.sync is not None:
+            if self.peer is not None:
+                self.peer.quantize_mean(_lib.UPD_TWICE_STORE if self.init else _lib.UPD_TWICE_EMA, data, data_q, aux[0],
+                                        self.ema_decay, 1 - self.ema_decay, 127.0)
+            elif self.sync is not None:
                 # data parallel: mean|x| -> allreduce(max) -> t = 2*mean, EMA (:58-64) -> clip by t, scale by aux (:65-68)
                 if getattr(self, "_stat", None) is None:
                     self._stat = self._empty_like(aux[0], (1,))

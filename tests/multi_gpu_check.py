@@ -70,10 +70,14 @@ def main():
                 dist.barrier()
                 ex.close()
     # GDRQ_PY activations (mean-based threshold): statistic = max over ranks of mean|x|, then the alpha update
-    for group_size in (-1, 4):
+    for group_size, mode in ((-1, "nccl"), (4, "nccl"), (-1, "peer")):
         op = b200quant.get_prop("GDRQ_PY")(nbits="8", group_size=str(group_size), is_weight="False", lamda="0.001",
                                            ktimes="3").create_operator(None, None, None)
-        op.sync = ThresholdSync()
+        ex = None
+        if mode == "nccl":
+            op.sync = ThresholdSync()
+        else:
+            ex = attach_peer_exchange([op], torch.device("cuda", local))
         groups = 1 if group_size == -1 else 16 // group_size
         alpha = torch.ones(groups, device="cuda")
         alpha_ref = np.ones(groups, F)
@@ -103,8 +107,12 @@ def main():
             ok = bits(alpha.cpu().numpy(), alpha_ref) and bits(yd.cpu().numpy(), want)
             if not ok:
                 failures += 1
-                print("rank %d FAIL GDRQ_PY group_size=%d step=%d alpha=%r want=%r" % (
-                    rank, group_size, step, alpha.cpu().numpy(), alpha_ref), flush=True)
+                print("rank %d FAIL GDRQ_PY %s group_size=%d step=%d alpha=%r want=%r" % (
+                    rank, mode, group_size, step, alpha.cpu().numpy(), alpha_ref), flush=True)
+        if ex is not None:
+            torch.cuda.synchronize()
+            dist.barrier()
+            ex.close()
 
     t = torch.tensor([failures], device="cuda")
     dist.all_reduce(t)

@@ -108,7 +108,7 @@ def test_resnet_int8_cifar_trains():
     dev = torch.device("cuda", 0)
     model = ResNetInt8(units=(1, 1, 1), filter_list=(16, 16, 32, 64), num_classes=10, bottle_neck=False,
                        dataset_type="cifar10").to(dev)
-    assert len(quant_nodes(model)) == 2 * (1 + 2 + 3 + 3 + 1)
+    assert len(quant_nodes(model)) == 2 * (1 + 3 + 3 + 3 + 1)   # conv0, three units of conv1+conv2+sc, fc1
     opt = torch.optim.SGD(model.parameters(), lr=0.05, momentum=0.9)
     x = torch.randn(64, 3, 32, 32, device=dev)
     y = torch.randint(0, 10, (64,), device=dev)

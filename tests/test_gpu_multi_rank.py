@@ -33,6 +33,46 @@ def test_peer_exchange_world1_matches_plain_path():
         ex.close()
 
 
+def test_peer_exchange_world1_mean_based_ops():
+    """Whole-tensor GDRQ_PY activations and the GDRQ_Fold_BN data path through b2q_peer_meanabs_quant_fwd_f32."""
+    import torch
+    import b200quant
+    from b200quant.dist import attach_peer_exchange
+    g = torch.Generator(device="cuda").manual_seed(21)
+    mk = lambda: b200quant.get_prop("GDRQ_PY")(nbits="8", group_size="-1", is_weight="False",
+                                               delay_quant="1").create_operator(None, None, None)
+    a, b = mk(), mk()
+    mkf = lambda: b200quant.get_prop("GDRQ_Fold_BN")(
+        quant_mode="minmax", is_weight_perchannel="False", name="c", num_filter="8", num_group="1", kernel="(1, 1)",
+        stride="(1, 1)", pad="(0, 0)", no_bias="True").create_operator(None, None, None)
+    fa, fb = mkf(), mkf()
+    ex = attach_peer_exchange([b, fb], torch.device("cuda", 0))
+    assert b.peer is ex and fb.peer is ex
+    al_a, al_b = torch.ones(1, device="cuda"), torch.ones(1, device="cuda")
+    for step, shape in enumerate([(4, 16, 9, 9), (2, 16, 56, 56), (3, 5, 7), (64, 64, 28, 28)]):
+        x = torch.randn(shape, device="cuda", generator=g) * (1 + step)
+        ya, yb = torch.zeros_like(x), torch.zeros_like(x)
+        a.forward(True, ["write"], [x], [ya], [al_a])
+        b.forward(True, ["write"], [x], [yb], [al_b])
+        assert torch.equal(al_a.view(torch.int32), al_b.view(torch.int32)), step
+        assert torch.equal(ya.view(torch.int32), yb.view(torch.int32)), step
+    w = torch.randn(8, 4, 1, 1, device="cuda", generator=g) * 0.2
+    gamma, beta = torch.rand(8, device="cuda", generator=g) + 0.5, torch.randn(8, device="cuda", generator=g)
+    mean, var = torch.randn(8, device="cuda", generator=g), torch.rand(8, device="cuda", generator=g) + 0.1
+    aux_a = [torch.ones(1, device="cuda"), torch.ones(1, device="cuda")]
+    aux_b = [torch.ones(1, device="cuda"), torch.ones(1, device="cuda")]
+    for step in range(3):
+        x = torch.randn(2, 4, 30, 30, device="cuda", generator=g) * (1 + step)
+        bn_out = torch.zeros(2, 8, 30, 30, device="cuda")
+        ya, yb = torch.zeros_like(bn_out), torch.zeros_like(bn_out)
+        fa.forward(True, ["write"], [x, w, bn_out, gamma, beta, mean, var], [ya], aux_a)
+        fb.forward(True, ["write"], [x, w, bn_out, gamma, beta, mean, var], [yb], aux_b)
+        assert torch.equal(aux_a[0].view(torch.int32), aux_b[0].view(torch.int32)), step
+        assert torch.equal(fa.data_q.view(torch.int32), fb.data_q.view(torch.int32)), step
+    torch.cuda.synchronize()
+    ex.close()
+
+
 def test_mean_based_ops_sync_path_matches_fused_path():
     """GDRQ_PY / GDRQ_Fold_BN with a (world = 1, no-op) ThresholdSync take the reduce -> exchange -> update -> sweep
     route built from the primitives; it has to give the bits of the fused entry points."""

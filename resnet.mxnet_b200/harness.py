@@ -19,19 +19,21 @@ class _CustomFn(torch.autograd.Function):
         out = node._alloc_out(in_data)
         node.op.forward(bool(node.training), ["write"], in_data, [out], node.aux_list())
         ctx.node = node
-        ctx.in_data = in_data
-        ctx.out = out
+        # save_for_backward, not attributes: an output kept as ctx.out would form a reference cycle through the
+        # autograd node and keep every activation of the step alive
+        ctx.save_for_backward(*in_data, out)
         ctx.needs = [bool(t.requires_grad) for t in inputs]
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
         node = ctx.node
-        in_data = ctx.in_data
+        saved = ctx.saved_tensors
+        in_data, out = list(saved[:-1]), saved[-1]
         if node.alias_ste and node.is_identity_backward():
             return (None, grad_out) + (None,) * (len(in_data) - 1)
         grads = [torch.empty_like(t) for t in in_data]
-        node.op.backward(["write"] * len(in_data), [grad_out.contiguous()], in_data, [ctx.out], grads,
+        node.op.backward(["write"] * len(in_data), [grad_out.contiguous()], in_data, [out], grads,
                          node.aux_list())
         return (None,) + tuple(g if need else None for g, need in zip(grads, ctx.needs))
 

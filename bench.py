@@ -377,7 +377,7 @@ def main():
             try:   # fused peer-memory exchange (NVLink): no NCCL call on the forward critical path
                 from b200quant.dist import attach_peer_exchange
                 attach_peer_exchange([nd["op"] for nd in nodes], device)
-                exchange = "fused peer-memory kernels (b2q_peer_minmax_quant_fwd_f32)"
+                exchange = "fused peer-memory kernels (b2q_peer_%s_quant_fwd_f32)" % ("minmax" if minmax else "meanabs",)
             except Exception as e:  # pragma: no cover
                 exchange += " (peer path unavailable: %s)" % (str(e).splitlines()[0][:100],)
         # operators without a fused exchange (the mean-based GDRQ thresholds) keep the NCCL call on their forward path

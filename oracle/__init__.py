@@ -19,6 +19,7 @@ c/                Plain-C (OpenMP) restatement with MXNet's kernel-per-expressio
 
 Parity status: the true MXNet binary is not installable here, so the oracle is pinned
 against the reference op sources executed over ``mxshim`` (whose numerics encode the [upstream]
-assumptions listed in quant_oracle.py), not against a real libmxnet.  The fork's C++ contrib ops
+assumptions listed in quant_oracle.py), not against a real libmxnet; and against the NumPy simulators the
+reference ships next to its ops (tests/golden/simulators.npz, tests/test_simulators.py).  The fork's C++ contrib ops
 (``contrib.Quantization_int8`` etc.) have no source in the reference tree: parity unpinned.
 """

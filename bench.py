@@ -580,7 +580,12 @@ def main():
                        "mode": mode},
             "ms_per_step_by_mode": timings,
             "hbm_frac_whole_step": alg_bytes_step / (ms / args.steps / 1e3) / 1e9 / peak_gbs,
-            "roofline": roofline, "kernels": kernels, "clocks": clocks, "gpu_launches": launches}
+            "roofline": roofline, "kernels": kernels,
+            "kernels_note": "event-timed per launch in a separate pass, all tensor sizes pooled (54 of the 108 launches "
+                            "per kind are weight tensors of a few KB..MB that cost a launch each); a kernel that follows "
+                            "a sweep also pays for the write-back of the output lines its predecessor left dirty in L2, "
+                            "so reduce_flat reads low and qdq_flat_hot high; hbm_frac_whole_step is the unbiased figure",
+            "clocks": clocks, "gpu_launches": launches}
 
     # ---- e2e: host buffers through the host C ABI (rank-local; N ranks run it concurrently) ----
     if not args.no_e2e and op_type == "Quantization_int8_V2":

@@ -359,6 +359,9 @@ def main():
     sm = summary(node_list)
     total_elems = sm["act_elems"] + sm["weight_elems"]
     ctx = _lib.context(local)
+    for k, v in os.environ.items():   # tuning experiments: B2Q_OPT_<option>=<int> (results never depend on them)
+        if k.startswith("B2Q_OPT_"):
+            ctx.set_option(k[len("B2Q_OPT_"):].lower(), int(v))
     if op_type == "GDRQ_Fold_BN":
         raise SystemExit("the fold-BN workload is a parity case (tests/test_gpu_configs.py), not a bench line")
     nodes = build_nodes(torch, node_list, op_type, device, seed=5 + rank)
@@ -370,6 +373,10 @@ def main():
 
     bucket = None
     exchange = "none"
+    if world == 1 and os.environ.get("B2Q_DEBUG_PEER_WORLD1") == "1":   # experiment: mailbox kernels without a peer
+        from b200quant.dist import attach_peer_exchange
+        attach_peer_exchange([nd["op"] for nd in nodes], device)
+        exchange = "fused peer-memory kernels at world 1 [DEBUG experiment]"
     if world > 1:   # data parallel: thresholds max over ranks per activation node, weight grads allreduce(sum)
         exchange = "nccl allreduce(max) per activation node"
         attach_threshold_sync([nd["op"] for nd in nodes])
@@ -388,6 +395,9 @@ def main():
         bucket = GradBucket([nd["shape"] for nd in wn], device)
         for nd, view in zip(wn, bucket.views):
             nd["dx"] = view
+        if os.environ.get("B2Q_DEBUG_SKIP_GRAD_ALLREDUCE") == "1":   # experiment only: isolates the exchange cost
+            bucket.allreduce = lambda *a, **k: None
+            exchange += " [DEBUG: gradient allreduce skipped -- not a valid result]"
 
     def step_local():
         run_step(nodes)

@@ -50,6 +50,7 @@ struct b2q_ctx {
                                      // 16 KB tile per block (no grid-stride loop) is fastest: dynamic balance over SMs
     int reduce_blocks_per_sm = 4;    // flat reductions that finalise in their last block (partials are re-read)
     int reduce_deferred_blocks_per_sm = 16;   // flat reductions with deferred update (one atomicMax per block)
+    int peer_reduce_blocks_per_sm = 8;        // max reductions of the peer-memory exchange (atomicMax + ticket per block)
     int deferred = 1;                // consumer-side threshold update in the fused whole-tensor forward
     int reverse = 1;                 // QDQ sweep walks descending addresses when the tensor exceeds reverse_min_bytes
     long long reverse_min_bytes = 96ll << 20;
@@ -155,6 +156,18 @@ __device__ __forceinline__ void st_i8(int32_t* p, const int (&c)[8]) {
     asm volatile("st.global.v8.s32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(c[0]), "r"(c[1]), "r"(c[2]),
                  "r"(c[3]), "r"(c[4]), "r"(c[5]), "r"(c[6]), "r"(c[7])
                  : "memory");
+}
+
+// "Last block finishes" ticket: a release atomic (+ an acquire fence in the one block that draws `last`) instead of
+// __threadfence() + atomicAdd.  __threadfence() is a sequentially consistent fence that also invalidates the SM's whole
+// L1 (MEMBAR.SC.GPU + CCTL.IVALL) in every block; the release orders the block's earlier writes (partials, atomicMax)
+// before the ticket, and the acquire lets the last block (and, through the following barrier, its other threads) see
+// everybody's.
+__device__ __forceinline__ unsigned int b2q_take_ticket(unsigned int* ticket, unsigned int last) {
+    unsigned int t;
+    asm volatile("atom.release.gpu.global.add.u32 %0, [%1], 1;" : "=r"(t) : "l"(ticket) : "memory");
+    if (t == last) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    return t;
 }
 
 __device__ __forceinline__ float warp_max(float v) {

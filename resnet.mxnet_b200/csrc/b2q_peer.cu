@@ -2,16 +2,20 @@
 // forward pass.  Replaces  [reduce kernel] -> ncclAllReduce(max, 4 bytes) -> [update kernel] -> [QDQ kernel]
 // (3 launches + a latency-bound collective on the forward critical path of every activation node) by
 //
-//   kernel 1  reduce_peer_kernel   local max|x|; its last block stores (sequence << 32 | float bits) into slot
+//   kernel 1  reduce_peer_kernel   local max|x| (one sequence-tagged atomicMax per block: exact, order independent, never
+//                                  reset because a newer sequence always wins) or fp64 partial sums of |x|; the block
+//                                  that takes the last ticket stores (sequence << 32 | float bits) into slot
 //                                  [sequence % 64][rank] of EVERY rank's mailbox with 8-byte system-scope stores
-//                                  (P2P over NVLink for peers), and snapshots the old aux
-//   kernel 2  the QDQ sweep        each block polls its OWN (local) mailbox until all `world` entries of the slot carry
-//                                  this sequence number, takes the max over ranks (exact, order independent), applies
-//                                  the EMA / first-batch update in registers and sweeps; block 0 writes the new aux
+//                                  (P2P over NVLink for peers) and snapshots the old aux.  The stores travel while the
+//                                  kernel drains and the sweep launches.
+//   kernel 2  the QDQ sweep        every warp reads its OWN (local) mailbox -- one lane per rank, no shared memory, no
+//                                  barrier; the first wave waits until all `world` entries of the slot carry this
+//                                  sequence -- takes the max over ranks (exact, order independent), applies the EMA /
+//                                  first-batch / alpha update in registers and sweeps; block 0 writes the new aux.
 //
 // Every rank launches the same sequence of calls (data parallel), so rank A's sweep only ever waits for kernels that
 // rank B has already enqueued or will enqueue without depending on A's later work: progress is guaranteed as long as
-// all ranks run on different GPUs.  A slot is reused after 64 calls; no rank can be more than one call ahead because
+// all ranks run on different GPUs.  Two mailbox slots alternate: no rank can be more than one call ahead because
 // each call needs every rank's value.  The poll is bounded: after ~20 s it traps (CUDA error) instead of hanging.
 #include <cstring>
 
@@ -26,12 +30,24 @@
 #define B2Q_PEER_MAX_RANKS 16
 #define B2Q_PEER_SLOTS 64
 #define B2Q_PEER_BOX_BYTES (B2Q_PEER_SLOTS * B2Q_PEER_MAX_RANKS * 8)
-#define B2Q_PEER_BYTES (B2Q_PEER_BOX_BYTES + 256)   // + device-side sequence counters (so CUDA graphs can replay)
+#define B2Q_PEER_MAX_SMS 256
+#define B2Q_PEER_STATE_BYTES 256                    // device-side sequence state (so CUDA graphs can replay)
+#define B2Q_PEER_BYTES (B2Q_PEER_BOX_BYTES + B2Q_PEER_STATE_BYTES + B2Q_PEER_MAX_SMS * 128)   // + per-SM resolved words
+
+// Device-side state behind the mailbox words (own mailbox + B2Q_PEER_BOX_BYTES); every rank issues the same calls, so
+// the sequence numbers stay in step, and a CUDA graph that replays the kernels publishes fresh numbers every time.
+struct PeerState {
+    unsigned int done;              // calls published so far; advanced by the last block of the reduction, after
+                                    // every block of that kernel has read it (they read it before taking a ticket)
+    unsigned int seq;               // sequence number of the call in flight, for the sweep
+    unsigned long long local_max;   // (seq << 32 | bits): running local max|x| of the call in flight
+};
 
 struct PeerBoxes {
     unsigned long long* box[B2Q_PEER_MAX_RANKS];
     int rank, world;
-    unsigned int* counters;   // own mailbox + B2Q_PEER_BOX_BYTES: [0] calls so far, [1] sequence of the call in flight
+    PeerState* state;
+    unsigned long long* resolved;   // [B2Q_PEER_MAX_SMS][16]: per-SM copy of the all-rank statistic, sequence-tagged
 };
 
 __device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
@@ -44,14 +60,19 @@ __device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long lon
     return v;
 }
 
-// kernel 1: whole-tensor max|x| (IS_MAX) or mean|x| (sum of |x| in double, rounded once, / count -- the arithmetic of
-// reduce_flat_kernel), last block publishes to every rank's mailbox
-template <bool IS_MAX, int UNROLL>
+#define B2Q_PEER_SPIN_LIMIT (1u << 24)   // x >= 64 ns sleeps, then trap: a peer never arrived
+
+// kernel 1: whole-tensor max|x| (IS_MAX) or mean|x| (sum of |x| in fp64, rounded once, / count -- the arithmetic of
+// reduce_flat_kernel); the last block publishes to every rank's mailbox
+template <bool IS_MAX, int UNROLL, int LDPOL>
 __global__ void __launch_bounds__(B2Q_THREADS)
 reduce_peer_kernel(const float* __restrict__ x, FlatSplit sp, b2q_slot* slot, const float* aux, PeerBoxes pb,
                    float count) {
     __shared__ double smem[32];
     __shared__ unsigned int s_ticket;
+    __shared__ float s_tot;
+    __shared__ unsigned int s_seq;
+    PeerState* state = pb.state;
     float mx = 0.f;
     double acc = 0.0;
     const float* xb = x + sp.head;
@@ -63,7 +84,7 @@ reduce_peer_kernel(const float* __restrict__ x, FlatSplit sp, b2q_slot* slot, co
 #pragma unroll
         for (int k = 0; k < UNROLL; ++k) {
             const int64_t i = base + (int64_t)k * B2Q_THREADS;
-            if (i < sp.n8) v[k] = ld_f8<0>(xb + 8 * i);
+            if (i < sp.n8) v[k] = ld_f8<LDPOL>(xb + 8 * i);
             else {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[k].v[j] = 0.f;
@@ -77,85 +98,116 @@ reduce_peer_kernel(const float* __restrict__ x, FlatSplit sp, b2q_slot* slot, co
         if ((int64_t)threadIdx.x < sp.tail) acc1<IS_MAX>(acc, mx, x[sp.head + 8 * sp.n8 + threadIdx.x]);
     }
     const double r = block_reduce<IS_MAX>(IS_MAX ? (double)mx : acc, smem);
-    if (threadIdx.x == 0) {
-        slot->partial[blockIdx.x] = r;
-        __threadfence();
-        s_ticket = atomicAdd(&slot->ticket, 1u);
+    if (IS_MAX) {
+        if (threadIdx.x == 0) {
+            const unsigned int seq = __ldcg(&state->done) + 1u;
+            atomicMax(&state->local_max, ((unsigned long long)seq << 32) | __float_as_uint((float)r));
+            s_ticket = b2q_take_ticket(&slot->ticket, gridDim.x - 1);
+            if (s_ticket == gridDim.x - 1) {   // everybody's maximum is in the word: read it back, no second reduction
+                s_tot = __uint_as_float((unsigned int)(__ldcg(&state->local_max) & 0xffffffffull));
+                s_seq = seq;
+            }
+        }
+        __syncthreads();
+        if (s_ticket != gridDim.x - 1) return;
+    } else {
+        if (threadIdx.x == 0) {
+            slot->partial[blockIdx.x] = r;
+            s_ticket = b2q_take_ticket(&slot->ticket, gridDim.x - 1);
+        }
+        __syncthreads();
+        if (s_ticket != gridDim.x - 1) return;
+        double a = 0.0;   // fixed-order combine of the fp64 partial sums
+        for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) a += __ldcg(&slot->partial[i]);
+        const double tot = block_reduce<false>(a, smem);
+        if (threadIdx.x == 0) {
+            s_tot = __fdiv_rn((float)tot, count);
+            s_seq = __ldcg(&state->done) + 1u;
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    if (s_ticket != gridDim.x - 1) return;
-    __threadfence();
-    float m = 0.f;
-    double a = 0.0;
-    for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
-        const double p = __ldcg(&slot->partial[i]);
-        if (IS_MAX) m = fmaxf(m, (float)p); else a += p;
+    if ((int)threadIdx.x < pb.world) {   // one lane per destination rank: 8-byte P2P store, first thing the block does
+        const unsigned long long word = ((unsigned long long)s_seq << 32) | __float_as_uint(s_tot);
+        st_sys_u64(pb.box[threadIdx.x] + (size_t)(s_seq & 1u) * B2Q_PEER_MAX_RANKS + pb.rank, word);
     }
-    const double tot = block_reduce<IS_MAX>(IS_MAX ? (double)m : a, smem);
-    __shared__ float s_tot;
-    __shared__ unsigned int s_seq;
     if (threadIdx.x == 0) {
-        s_tot = IS_MAX ? (float)tot : __fdiv_rn((float)tot, count);
         slot->scale[0] = aux[0];   // snapshot of the old threshold for the sweep
         slot->ticket = 0;
-        // the sequence number lives on the device (every rank issues the same calls, so the counters stay in step);
-        // a CUDA graph that replays this kernel therefore publishes fresh numbers every time
-        s_seq = pb.counters[0] + 1u;
-        pb.counters[0] = s_seq;
-        pb.counters[1] = s_seq;
+        state->seq = s_seq;
+        state->done = s_seq;
     }
-    __syncthreads();
-    if ((int)threadIdx.x < pb.world) {   // one lane per destination rank: 8-byte P2P store
-        const unsigned long long word = ((unsigned long long)s_seq << 32) | __float_as_uint(s_tot);
-        st_sys_u64(pb.box[threadIdx.x] + (size_t)(s_seq % B2Q_PEER_SLOTS) * B2Q_PEER_MAX_RANKS + pb.rank, word);
+}
+
+// Prologue of the sweep: the statistic maximised over all ranks.  Tens of thousands of short blocks asking one L2 line
+// the same question is what costs (measured: 8 requests per block to the mailbox line added 24 us per node), so the
+// answer is cached per SM: the first warps on an SM read the mailbox (one lane per rank; they wait there until all
+// `world` entries carry this sequence), take the max (exact, order independent) and store it, sequence-tagged, in that
+// SM's own line of `resolved`; every later block on the SM finds it with ordinary L1-cacheable loads -- the cost of the
+// single-GPU kernel's prologue.  A stale or missing line only ever sends a warp down the mailbox path again.
+__device__ __forceinline__ float peer_gather(const PeerBoxes& pb) {
+    const unsigned int seq = pb.state->seq;   // written by this call's reduction kernel (same stream); L1-cacheable
+    unsigned int smid;
+    asm("mov.u32 %0, %%smid;" : "=r"(smid));
+    unsigned long long* mine = pb.resolved + (size_t)(smid % B2Q_PEER_MAX_SMS) * 16;   // 128 bytes apart
+    unsigned long long w;
+    asm volatile("ld.global.ca.u64 %0, [%1];" : "=l"(w) : "l"(mine) : "memory");
+    if ((unsigned int)(w >> 32) == seq) return __uint_as_float((unsigned int)(w & 0xffffffffull));   // warp-uniform
+    const int lane = threadIdx.x & 31;
+    float v = 0.f;
+    if (lane < pb.world) {
+        const unsigned long long* p = pb.box[pb.rank] + (size_t)(seq & 1u) * B2Q_PEER_MAX_RANKS + lane;
+        unsigned long long m = ld_sys_u64(p);
+        unsigned int spins = 0;
+        while ((unsigned int)(m >> 32) != seq) {
+            __nanosleep(64 + 8 * (threadIdx.x >> 5));
+            m = ld_sys_u64(p);
+            if (++spins > B2Q_PEER_SPIN_LIMIT) __trap();   // a peer never arrived: fail loudly instead of hanging
+        }
+        v = __uint_as_float((unsigned int)(m & 0xffffffffull));
     }
-    __threadfence_system();
+    v = warp_max(v);
+    if (lane == 0) *mine = ((unsigned long long)seq << 32) | __float_as_uint(v);
+    return v;
 }
 
 // kernel 2: QDQ sweep whose prologue gathers every rank's statistic from the local mailbox
 template <int CLIP, int UNROLL, int LDPOL, int STPOL>
 __global__ void __launch_bounds__(B2Q_THREADS)
-qdq_peer_kernel(const float* __restrict__ x, float* __restrict__ y, FlatSplit sp, const unsigned long long* mybox,
-                int world, const unsigned int* counters, const float* aux_old, UpdateArgs u, float qlevel, int fast,
-                int reverse, int clip_with_fresh) {
-    __shared__ float s_stat;
-    if (threadIdx.x < 32) {
-        const unsigned int seq = counters[1];   // written by this call's reduction kernel (same stream)
-        float v = 0.f;
-        if ((int)threadIdx.x < world) {
-            const unsigned long long* p = mybox + (size_t)(seq % B2Q_PEER_SLOTS) * B2Q_PEER_MAX_RANKS + threadIdx.x;
-            unsigned long long w = ld_sys_u64(p);
-            unsigned int spins = 0;
-            while ((unsigned int)(w >> 32) != seq) {
-                __nanosleep(64);
-                w = ld_sys_u64(p);
-                if (++spins > (1u << 24)) __trap();   // a peer never arrived: fail loudly instead of hanging
-            }
-            v = __uint_as_float((unsigned int)(w & 0xffffffffull));
-        }
-        v = warp_max(v);
-        if (threadIdx.x == 0) s_stat = v;
-    }
-    __syncthreads();
-    const float a_old = aux_old[0];
-    float fresh, next;
-    compute_update(u.mode, u.p0, u.p1, a_old, s_stat, fresh, next);
-    const float T = next;
-    const float Tc = clip_with_fresh ? fresh : T;   // fold_bn_v1_gdrq.py:67 clips with the batch threshold
-    if (blockIdx.x == 0 && threadIdx.x == 0) u.aux[0] = next;
-    const QScale s = make_qscale(T, qlevel, fast != 0 && !(CLIP != B2Q_CLIP_NONE && !(Tc >= 0.f)));
+qdq_peer_kernel(const float* __restrict__ x, float* __restrict__ y, FlatSplit sp, PeerBoxes pb, const b2q_slot* slot,
+                UpdateArgs u, float qlevel, int fast, int reverse, int clip_with_fresh) {
     const float* xb = x + sp.head;
     float* yb = y + sp.head;
     const int64_t tile = (int64_t)B2Q_THREADS * UNROLL;
     const int64_t ntiles = (sp.n8 + tile - 1) / tile;
-    for (int64_t tt = blockIdx.x; tt < ntiles; tt += gridDim.x) {
+    // first tile's loads go out before the mailbox is read: the gather's L2 round trip hides behind the HBM latency
+    f8 v[UNROLL];
+    int64_t tt = blockIdx.x;
+    {
         const int64_t t = reverse ? (ntiles - 1 - tt) : tt;
         const int64_t base = t * tile + threadIdx.x;
-        f8 v[UNROLL];
 #pragma unroll
         for (int k = 0; k < UNROLL; ++k) {
             const int64_t i = base + (int64_t)k * B2Q_THREADS;
-            if (i < sp.n8) v[k] = ld_f8<LDPOL>(xb + 8 * i);
+            if (tt < ntiles && i < sp.n8) v[k] = ld_f8<LDPOL>(xb + 8 * i);
+        }
+    }
+    const float a_old = slot->scale[0];
+    const float stat = peer_gather(pb);
+    float fresh, next;
+    compute_update(u.mode, u.p0, u.p1, a_old, stat, fresh, next);
+    const float T = next;
+    const float Tc = clip_with_fresh ? fresh : T;   // fold_bn_v1_gdrq.py:67 clips with the batch threshold
+    if (blockIdx.x == 0 && threadIdx.x == 0) u.aux[0] = next;
+    const QScale s = make_qscale(T, qlevel, fast != 0 && !(CLIP != B2Q_CLIP_NONE && !(Tc >= 0.f)));
+    for (; tt < ntiles; tt += gridDim.x) {
+        const int64_t t = reverse ? (ntiles - 1 - tt) : tt;
+        const int64_t base = t * tile + threadIdx.x;
+        if (tt != (int64_t)blockIdx.x) {
+#pragma unroll
+            for (int k = 0; k < UNROLL; ++k) {
+                const int64_t i = base + (int64_t)k * B2Q_THREADS;
+                if (i < sp.n8) v[k] = ld_f8<LDPOL>(xb + 8 * i);
+            }
         }
 #pragma unroll
         for (int k = 0; k < UNROLL; ++k) {
@@ -237,15 +289,17 @@ static int peer_quant_fwd(b2q_ctx* ctx, bool is_max, int upd_mode, float p0, flo
         pb.box[r] = (unsigned long long*)mailboxes[r];
     }
     pb.rank = rank; pb.world = world;
-    pb.counters = (unsigned int*)((char*)mailboxes[rank] + B2Q_PEER_BOX_BYTES);
+    pb.state = (PeerState*)((char*)mailboxes[rank] + B2Q_PEER_BOX_BYTES);
+    static_assert(sizeof(PeerState) <= B2Q_PEER_STATE_BYTES, "mailbox state area");
+    pb.resolved = (unsigned long long*)((char*)mailboxes[rank] + B2Q_PEER_BOX_BYTES + B2Q_PEER_STATE_BYTES);
     b2q_slot* slot = b2q_take_slot(ctx);
     {
-        const int64_t grid = b2q_flat_grid(ctx, sp.n8, B2Q_REDUCE_UNROLL, ctx->reduce_blocks_per_sm);
+        const int64_t grid = b2q_flat_grid(ctx, sp.n8, B2Q_REDUCE_UNROLL, is_max ? ctx->peer_reduce_blocks_per_sm : ctx->reduce_blocks_per_sm);
         b2q_timed_launch tl(ctx, B2Q_KIND_REDUCE_FLAT, 4.0 * (double)n, st);
         if (is_max)
-            reduce_peer_kernel<true, B2Q_REDUCE_UNROLL><<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, sp, slot, aux, pb, (float)n);
+            reduce_peer_kernel<true, B2Q_REDUCE_UNROLL, B2Q_REDUCE_LDPOL><<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, sp, slot, aux, pb, (float)n);
         else
-            reduce_peer_kernel<false, B2Q_REDUCE_UNROLL><<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, sp, slot, aux, pb, (float)n);
+            reduce_peer_kernel<false, B2Q_REDUCE_UNROLL, B2Q_REDUCE_LDPOL><<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, sp, slot, aux, pb, (float)n);
         B2Q_LAUNCH_CHECK(ctx);
     }
     UpdateArgs u;
@@ -254,15 +308,15 @@ static int peer_quant_fwd(b2q_ctx* ctx, bool is_max, int upd_mode, float p0, flo
     u.write_aux = 1; u.use_aux_as_scale = 1; u.p0 = p0; u.p1 = p1; u.aux = aux;
     {
         const int64_t grid = b2q_flat_grid(ctx, sp.n8, B2Q_QDQ_UNROLL);
-        const unsigned long long* mybox = (const unsigned long long*)mailboxes[rank];
         const int rev = (ctx->reverse && n * 4 > ctx->reverse_min_bytes) ? 1 : 0;
+        const bool stream_out = n * 4 > B2Q_STREAM_BYTES;   // outputs that cannot stay in L2 anyway: streaming stores
         b2q_timed_launch tl(ctx, B2Q_KIND_QDQ_HOT, 8.0 * (double)n, st);
-        if (clip_mode == B2Q_CLIP_SYM)
-            qdq_peer_kernel<B2Q_CLIP_SYM, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, B2Q_QDQ_STPOL><<<(unsigned)grid, B2Q_THREADS, 0, st>>>(
-                x, y, sp, mybox, world, pb.counters, slot->scale, u, qlevel, ctx->fast_div, rev, clip_with_fresh);
-        else
-            qdq_peer_kernel<B2Q_CLIP_NONE, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, B2Q_QDQ_STPOL><<<(unsigned)grid, B2Q_THREADS, 0, st>>>(
-                x, y, sp, mybox, world, pb.counters, slot->scale, u, qlevel, ctx->fast_div, rev, clip_with_fresh);
+#define B2Q_PEER_SWEEP(C, S) qdq_peer_kernel<C, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, S><<<(unsigned)grid, B2Q_THREADS, 0, st>>>( \
+            x, y, sp, pb, slot, u, qlevel, ctx->fast_div, rev, clip_with_fresh)
+#define B2Q_PEER_SWEEP_S(C) do { if (stream_out) B2Q_PEER_SWEEP(C, 1); else B2Q_PEER_SWEEP(C, B2Q_QDQ_STPOL); } while (0)
+        if (clip_mode == B2Q_CLIP_SYM) B2Q_PEER_SWEEP_S(B2Q_CLIP_SYM); else B2Q_PEER_SWEEP_S(B2Q_CLIP_NONE);
+#undef B2Q_PEER_SWEEP_S
+#undef B2Q_PEER_SWEEP
         B2Q_LAUNCH_CHECK(ctx);
     }
     return 0;

@@ -107,13 +107,11 @@ reduce_flat_kernel(const float* __restrict__ x, FlatSplit sp, b2q_slot* slot, Up
     }
     if (threadIdx.x == 0) {
         slot->partial[blockIdx.x] = r;
-        __threadfence();
-        s_ticket = atomicAdd(&slot->ticket, 1u);
+        s_ticket = b2q_take_ticket(&slot->ticket, gridDim.x - 1);
     }
     __syncthreads();
     if (s_ticket != gridDim.x - 1) return;
     // ---- last block: combine in fixed order, update the threshold ----
-    __threadfence();
     double a = 0.0;
     float m = 0.f;
     for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
@@ -263,12 +261,10 @@ reduce_seg_kernel(const float* __restrict__ x, SegPlan pl, Prescale ps, b2q_slot
     }
     if (threadIdx.x == 0) {
         slot->partial[blockIdx.x] = r;
-        __threadfence();
-        s_ticket = atomicAdd(&slot->ticket, 1u);
+        s_ticket = b2q_take_ticket(&slot->ticket, gridDim.x - 1);
     }
     __syncthreads();
     if (s_ticket != gridDim.x - 1) return;
-    __threadfence();
     if (pl.groups >= 64) {
         // many groups: one thread per group walks its SP partials in order (fixed order => deterministic)
         for (int64_t gg = threadIdx.x; gg < pl.groups; gg += blockDim.x) {

@@ -64,12 +64,10 @@ __global__ void __launch_bounds__(B2Q_THREADS) ew_kernel(Op op, int64_t n, b2q_s
     r[3] = block_reduce<true>((double)m, smem);
     if (threadIdx.x == 0) {
         for (int k = 0; k < 4; ++k) slot->partial[4 * blockIdx.x + k] = r[k];
-        __threadfence();
-        s_ticket = atomicAdd(&slot->ticket, 1u);
+        s_ticket = b2q_take_ticket(&slot->ticket, gridDim.x - 1);
     }
     __syncthreads();
     if (s_ticket != gridDim.x - 1) return;
-    __threadfence();
     double a[3] = {0.0, 0.0, 0.0};
     float mm = 0.f;
     for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
@@ -138,12 +136,10 @@ wnq_bwd_sum_kernel(const float* __restrict__ x, const float* __restrict__ dy, Se
     double r = block_reduce<false>(acc, smem);
     if (threadIdx.x == 0) {
         slot->partial[blockIdx.x] = r;
-        __threadfence();
-        s_ticket = atomicAdd(&slot->ticket, 1u);
+        s_ticket = b2q_take_ticket(&slot->ticket, gridDim.x - 1);
     }
     __syncthreads();
     if (s_ticket != gridDim.x - 1) return;
-    __threadfence();
     const int SP = pl.S * pl.P;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     for (int64_t gg = wid; gg < pl.groups; gg += nw) {

@@ -48,9 +48,12 @@ class GradBucket(object):
 
     def allreduce(self, group=None, average=True):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
-            if average:
-                self.flat.div_(dist.get_world_size(group))
+            if average and self.flat.is_cuda and dist.get_backend(group) == "nccl":
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group)   # the division rides in the collective
+            else:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+                if average:
+                    self.flat.div_(dist.get_world_size(group))
         return self.flat
 
 

@@ -226,8 +226,9 @@ int b2q_multi_weight_ste_bwd_f32(b2q_ctx* ctx, b2q_multi_plan* plan, void* strea
  * Data-parallel training needs allreduce(max) of every activation node's statistic before its threshold update
  * (BASELINE.json north_star).  Instead of reduce kernel -> ncclAllReduce(4 bytes) -> update kernel -> QDQ kernel,
  * b2q_peer_minmax_quant_fwd_f32 runs two kernels: the reduction's last block stores (sequence, max|x|) into every
- * rank's mailbox with 8-byte P2P stores, and the QDQ sweep polls its own mailbox until all `world` entries of that
- * sequence number are present, takes their max, applies the EMA / first-batch update in registers and sweeps.
+ * rank's mailbox with 8-byte P2P stores, and the QDQ sweep reads its own mailbox (the first warps on each SM wait
+ * until all `world` entries of that sequence number are present, take their max and cache it for the SM's later
+ * blocks), applies the EMA / first-batch update in registers and sweeps.
  * Semantics = Quantization_int8 / ClipGrad_Quantization_int8 activation forward in training mode
  * (symbol/quant_ops.py:32-40, symbol/clip_grad_quantization_int8.py:37-51) with max|x| taken over all ranks.
  * mailboxes[r] = rank r's mailbox as mapped on THIS device (own: b2q_peer_mailbox_create; peers: the 64-byte CUDA
@@ -253,9 +254,10 @@ int b2q_peer_meanabs_quant_fwd_f32(b2q_ctx* ctx, int upd_mode, const float* x, f
 
 /* ---- host-buffer path: the call a framework whose tensors live in HOST memory makes (bench.py "e2e") --
  * Same semantics as the device entry points but x / y / aux are HOST pointers (pinned for full speed).
- * Each call stages its tensor through one of two device staging sets on that set's own stream
- * (H2D -> reduction + threshold update -> QDQ sweep -> D2H) and returns without waiting, so the D2H of one
- * call overlaps the H2D of the next; b2q_host_sync() waits for all of them.  host_aux is read at enqueue
+ * Each call stages its tensor through a device staging ring on three internal streams
+ * (H2D -> reduction + threshold update -> QDQ sweep -> D2H, per-segment events) and returns without waiting, so
+ * the H2D of the next call, the kernels of this one and the D2H of the previous one overlap; b2q_host_sync()
+ * waits for all of them.  host_aux is read at enqueue
  * order and written back by the same call; calls sharing an aux array must be separated by a sync.       */
 int b2q_minmax_quant_fwd_host_f32(b2q_ctx* ctx, int variant, const float* host_x, float* host_y,
                                   float* host_aux, int64_t rows, int64_t cols, int is_weight,

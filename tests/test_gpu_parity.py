@@ -348,3 +348,31 @@ def test_int8_export_reproduces_fake_quant(T):
     codes, steps = K.export_int8(xd, a1, 127, _lib.CLIP_SYM)
     assert T.equal(codes.float() * steps, xq)
     assert int(codes.max()) == 127 and int(codes.min()) == -127
+
+
+def test_int8_export_feeds_an_integer_gemm(T):
+    """the exported codes + steps are what a true-int8 layer consumes.  An int8 GEMM on the
+    codes (torch._int_mm: int32 accumulation, exact) times the two steps reproduces the fp32 FullyConnected of the
+    fake-quantized tensors up to fp32 accumulation order."""
+    import b200quant._kernels as K
+    from b200quant import _lib
+    if not hasattr(T, "_int_mm"):
+        pytest.skip("torch._int_mm not available")
+    rng = np.random.default_rng(13)
+    x = (rng.standard_normal((64, 256)) * 1.5).astype(F)
+    w = (rng.standard_normal((128, 256)) * 0.05).astype(F)
+    opx, _ = make("ClipGrad_Quantization_int8", quant_mode="minmax", is_weight=False)
+    opw, _ = make("ClipGrad_Quantization_int8", quant_mode="minmax", is_weight=True)
+    xd, xq, ax = dev(T, x), dev(T, np.zeros_like(x)), dev(T, np.ones(1, F))
+    wd, wq, aw = dev(T, w), dev(T, np.zeros_like(w)), dev(T, np.ones(1, F))
+    opx.forward(True, ["write"], [xd], [xq], [ax])
+    opw.forward(True, ["write"], [wd], [wq], [aw])
+    cx, sx = K.export_int8(xd, ax, 127, _lib.CLIP_SYM)
+    cw, sw = K.export_int8(wd, aw, 127, _lib.CLIP_NONE)
+    acc = T._int_mm(cx, cw.t().contiguous())                   # int32, exact
+    got = acc.to(T.float64) * (float(sx) * float(sw))
+    want = xq.to(T.float64) @ wq.to(T.float64).t()             # the fake-quant layer, in fp64 to remove order effects
+    assert T.allclose(got, want, rtol=1e-6, atol=1e-9)
+    # and the fp32 layer the training graph runs agrees with both within fp32 accumulation error
+    fp32 = T.nn.functional.linear(xq, wq).to(T.float64)
+    assert T.allclose(fp32, want, rtol=1e-4, atol=1e-5)

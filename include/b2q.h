@@ -45,7 +45,8 @@ int b2q_destroy(b2q_ctx* ctx);
 int b2q_num_sms(b2q_ctx* ctx);
 /* run-time knobs for benchmarking sweeps: "blocks_per_sm" (grid = SMs x this), "reverse" (QDQ sweep walks
  * descending addresses to reuse what the reduction left in L2), "fast_div" (reciprocal fast path on/off),
- * "peer_reduce_blocks_per_sm" (grid of the max reduction in the peer-memory exchange), "timing" (see b2q_timing_read).
+ * "peer_reduce_blocks_per_sm" (grid of the max reduction in the peer-memory exchange), "pdl" (programmatic dependent
+ * launch between consecutive whole-tensor kernels on/off), "timing" (see b2q_timing_read).
  * Results never depend on them. */
 int b2q_set_option(b2q_ctx* ctx, const char* key, int value);
 int b2q_get_option(b2q_ctx* ctx, const char* key, int* value);

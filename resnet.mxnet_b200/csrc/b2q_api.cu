@@ -71,6 +71,7 @@ static int* option_slot(b2q_ctx* ctx, const char* key) {
     if (!strcmp(key, "reduce_blocks_per_sm")) return &ctx->reduce_blocks_per_sm;
     if (!strcmp(key, "peer_reduce_blocks_per_sm")) return &ctx->peer_reduce_blocks_per_sm;
     if (!strcmp(key, "deferred")) return &ctx->deferred;
+    if (!strcmp(key, "pdl")) return &ctx->pdl;
     if (!strcmp(key, "reverse")) return &ctx->reverse;
     if (!strcmp(key, "fast_div")) return &ctx->fast_div;
     if (!strcmp(key, "timing")) return &ctx->timing;

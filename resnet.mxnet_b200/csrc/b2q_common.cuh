@@ -1,5 +1,6 @@
 // Shared device/host infrastructure of libb2q.so (sm_100a only).
 #pragma once
+#include <utility>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
@@ -50,6 +51,7 @@ struct b2q_ctx {
                                      // 16 KB tile per block (no grid-stride loop) is fastest: dynamic balance over SMs
     int reduce_blocks_per_sm = 4;    // flat reductions that finalise in their last block (partials are re-read)
     int reduce_deferred_blocks_per_sm = 16;   // flat reductions with deferred update (one atomicMax per block)
+    int pdl = 1;                              // programmatic dependent launch between consecutive whole-tensor kernels
     int peer_reduce_blocks_per_sm = 8;        // max reductions of the peer-memory exchange (atomicMax + ticket per block)
     int deferred = 1;                // consumer-side threshold update in the fused whole-tensor forward
     int reverse = 1;                 // QDQ sweep walks descending addresses when the tensor exceeds reverse_min_bytes
@@ -107,6 +109,25 @@ int b2q_host_release(b2q_ctx* ctx);  // b2q_host.cu
         B2Q_CHECK_CUDA(cudaGetLastError());                                                        \
     } while (0)
 
+// Launch with the programmatic-stream-serialization attribute: the blocks of this kernel may become resident while the
+// previous kernel of the stream drains its last wave (every kernel launched this way starts with b2q_pdl_sync(), which
+// waits for the predecessor to complete and flush before touching memory, then lets its own successor do the same).
+// It hides the launch latency and prologue of ~300 back-to-back kernels per step; ordering and results are unchanged.
+template <typename... KArgs, typename... Args>
+static inline void b2q_launch(const b2q_ctx* ctx, void (*kernel)(KArgs...), unsigned grid, unsigned block,
+                              cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(block, 1, 1);
+    cfg.stream = st;
+    cudaLaunchAttribute attr = {};
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = ctx->pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);   // error picked up by B2Q_LAUNCH_CHECK
+}
+
 static inline b2q_slot* b2q_take_slot(b2q_ctx* ctx) {
     unsigned int i = __atomic_fetch_add(&ctx->next_slot, 1u, __ATOMIC_RELAXED);
     return ctx->slots + (i % B2Q_NSLOTS);
@@ -156,6 +177,12 @@ __device__ __forceinline__ void st_i8(int32_t* p, const int (&c)[8]) {
     asm volatile("st.global.v8.s32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(c[0]), "r"(c[1]), "r"(c[2]),
                  "r"(c[3]), "r"(c[4]), "r"(c[5]), "r"(c[6]), "r"(c[7])
                  : "memory");
+}
+
+// First statement of every kernel launched through b2q_launch (no effect for an ordinary launch).
+__device__ __forceinline__ void b2q_pdl_sync() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
 // "Last block finishes" ticket: a release atomic (+ an acquire fence in the one block that draws `last`) instead of

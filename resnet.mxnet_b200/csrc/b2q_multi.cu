@@ -63,6 +63,7 @@ __device__ __forceinline__ const float* mt_group_base(const MtTensor& t, int gro
 __global__ void __launch_bounds__(B2Q_THREADS)
 mt_absmax_kernel(const MtTensor* __restrict__ tensors, const MtItem* __restrict__ items,
                  unsigned long long* __restrict__ stat, const unsigned int* __restrict__ epoch) {
+    b2q_pdl_sync();
     __shared__ double smem[32];
     const unsigned long long tag = (unsigned long long)(*epoch + 1u) << 32;
     const MtItem it = items[blockIdx.x];
@@ -99,6 +100,7 @@ __global__ void __launch_bounds__(B2Q_THREADS)
 mt_qdq_kernel(const MtTensor* __restrict__ tensors, const MtItem* __restrict__ items,
               const unsigned long long* __restrict__ stat, unsigned int* __restrict__ epoch, int from_stat, int write_aux,
               int fast) {
+    b2q_pdl_sync();
     if (from_stat && blockIdx.x == 0 && threadIdx.x == 0) *epoch = (unsigned int)(stat[0] >> 32);   // consume the tag
     const MtItem it = items[blockIdx.x];
     const MtTensor t = tensors[it.tensor];
@@ -140,6 +142,7 @@ mt_qdq_kernel(const MtTensor* __restrict__ tensors, const MtItem* __restrict__ i
 
 __global__ void __launch_bounds__(B2Q_THREADS)
 mt_copy_kernel(const MtTensor* __restrict__ tensors, const MtItem* __restrict__ items) {
+    b2q_pdl_sync();
     const MtItem it = items[blockIdx.x];
     const MtTensor t = tensors[it.tensor];
     long long a, b;
@@ -163,6 +166,7 @@ mt_copy_kernel(const MtTensor* __restrict__ tensors, const MtItem* __restrict__ 
 // launch A: one double partial per RANGE item (ROWS items do their own sum in launch B).
 __global__ void __launch_bounds__(B2Q_THREADS)
 mt_sumabs_kernel(const MtTensor* __restrict__ tensors, const MtItem* __restrict__ items, double* __restrict__ partial) {
+    b2q_pdl_sync();
     __shared__ double smem[32];
     const MtItem it = items[blockIdx.x];
     if (it.kind != 0) return;
@@ -178,6 +182,7 @@ mt_sumabs_kernel(const MtTensor* __restrict__ tensors, const MtItem* __restrict_
 __global__ void __launch_bounds__(B2Q_THREADS)
 mt_gdrq_kernel(const MtTensor* __restrict__ tensors, const MtItem* __restrict__ items, const double* __restrict__ partial,
                int fix_alpha, int do_round, float qlevel, float ktimes, int fast) {
+    b2q_pdl_sync();
     __shared__ double smem[32];
     __shared__ float s_T;
     const MtItem it = items[blockIdx.x];
@@ -311,13 +316,13 @@ int b2q_multi_weight_quant_fwd_f32(b2q_ctx* ctx, b2q_multi_plan* p, int variant,
     const int do_reduce = (variant == 0 || is_train) ? 1 : 0;
     if (do_reduce) {
         b2q_timed_launch tl(ctx, B2Q_KIND_OTHER, 4.0 * (double)p->elements, st);
-        mt_absmax_kernel<<<(unsigned)p->n_items, B2Q_THREADS, 0, st>>>(p->d_tensors, p->d_items, p->d_stat, p->d_epoch);
+        b2q_launch(ctx, mt_absmax_kernel, (unsigned)p->n_items, B2Q_THREADS, st, p->d_tensors, p->d_items, p->d_stat, p->d_epoch);
         B2Q_LAUNCH_CHECK(ctx);
     }
     {
         b2q_timed_launch tl(ctx, B2Q_KIND_OTHER, 8.0 * (double)p->elements, st);
-        mt_qdq_kernel<<<(unsigned)p->n_items, B2Q_THREADS, 0, st>>>(p->d_tensors, p->d_items, p->d_stat, p->d_epoch,
-                                                                    do_reduce, is_train ? 1 : 0, ctx->fast_div);
+        b2q_launch(ctx, mt_qdq_kernel, (unsigned)p->n_items, B2Q_THREADS, st, p->d_tensors, p->d_items, p->d_stat, p->d_epoch,
+                   do_reduce, is_train ? 1 : 0, ctx->fast_div);
         B2Q_LAUNCH_CHECK(ctx);
     }
     return 0;
@@ -330,12 +335,12 @@ int b2q_multi_gdrq_weight_fwd_f32(b2q_ctx* ctx, b2q_multi_plan* p, int fix_alpha
     cudaStream_t st = (cudaStream_t)stream;
     if (!fix_alpha) {
         b2q_timed_launch tl(ctx, B2Q_KIND_OTHER, 4.0 * (double)p->elements, st);
-        mt_sumabs_kernel<<<(unsigned)p->n_items, B2Q_THREADS, 0, st>>>(p->d_tensors, p->d_items, p->d_partial);
+        b2q_launch(ctx, mt_sumabs_kernel, (unsigned)p->n_items, B2Q_THREADS, st, p->d_tensors, p->d_items, p->d_partial);
         B2Q_LAUNCH_CHECK(ctx);
     }
     b2q_timed_launch tl(ctx, B2Q_KIND_OTHER, 8.0 * (double)p->elements, st);
-    mt_gdrq_kernel<<<(unsigned)p->n_items, B2Q_THREADS, 0, st>>>(p->d_tensors, p->d_items, p->d_partial, fix_alpha, do_round,
-                                                                 qlevel, ktimes, ctx->fast_div);
+    b2q_launch(ctx, mt_gdrq_kernel, (unsigned)p->n_items, B2Q_THREADS, st, p->d_tensors, p->d_items, p->d_partial, fix_alpha,
+               do_round, qlevel, ktimes, ctx->fast_div);
     B2Q_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -346,7 +351,7 @@ int b2q_multi_weight_ste_bwd_f32(b2q_ctx* ctx, b2q_multi_plan* p, void* stream) 
     B2Q_REQUIRE(p->has_grad, "plan was created without dy/dx pointers");
     cudaStream_t st = (cudaStream_t)stream;
     b2q_timed_launch tl(ctx, B2Q_KIND_OTHER, 8.0 * (double)p->elements, st);
-    mt_copy_kernel<<<(unsigned)p->n_items, B2Q_THREADS, 0, st>>>(p->d_tensors, p->d_items);
+    b2q_launch(ctx, mt_copy_kernel, (unsigned)p->n_items, B2Q_THREADS, st, p->d_tensors, p->d_items);
     B2Q_LAUNCH_CHECK(ctx);
     return 0;
 }

@@ -68,6 +68,7 @@ template <bool IS_MAX, int UNROLL, int LDPOL>
 __global__ void __launch_bounds__(B2Q_THREADS)
 reduce_peer_kernel(const float* __restrict__ x, FlatSplit sp, b2q_slot* slot, const float* aux, PeerBoxes pb,
                    float count) {
+    b2q_pdl_sync();
     __shared__ double smem[32];
     __shared__ unsigned int s_ticket;
     __shared__ float s_tot;
@@ -175,6 +176,7 @@ template <int CLIP, int UNROLL, int LDPOL, int STPOL>
 __global__ void __launch_bounds__(B2Q_THREADS)
 qdq_peer_kernel(const float* __restrict__ x, float* __restrict__ y, FlatSplit sp, PeerBoxes pb, const b2q_slot* slot,
                 UpdateArgs u, float qlevel, int fast, int reverse, int clip_with_fresh) {
+    b2q_pdl_sync();
     const float* xb = x + sp.head;
     float* yb = y + sp.head;
     const int64_t tile = (int64_t)B2Q_THREADS * UNROLL;
@@ -297,9 +299,11 @@ static int peer_quant_fwd(b2q_ctx* ctx, bool is_max, int upd_mode, float p0, flo
         const int64_t grid = b2q_flat_grid(ctx, sp.n8, B2Q_REDUCE_UNROLL, is_max ? ctx->peer_reduce_blocks_per_sm : ctx->reduce_blocks_per_sm);
         b2q_timed_launch tl(ctx, B2Q_KIND_REDUCE_FLAT, 4.0 * (double)n, st);
         if (is_max)
-            reduce_peer_kernel<true, B2Q_REDUCE_UNROLL, B2Q_REDUCE_LDPOL><<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, sp, slot, aux, pb, (float)n);
+            b2q_launch(ctx, reduce_peer_kernel<true, B2Q_REDUCE_UNROLL, B2Q_REDUCE_LDPOL>, (unsigned)grid, B2Q_THREADS, st,
+                       x, sp, slot, aux, pb, (float)n);
         else
-            reduce_peer_kernel<false, B2Q_REDUCE_UNROLL, B2Q_REDUCE_LDPOL><<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, sp, slot, aux, pb, (float)n);
+            b2q_launch(ctx, reduce_peer_kernel<false, B2Q_REDUCE_UNROLL, B2Q_REDUCE_LDPOL>, (unsigned)grid, B2Q_THREADS, st,
+                       x, sp, slot, aux, pb, (float)n);
         B2Q_LAUNCH_CHECK(ctx);
     }
     UpdateArgs u;
@@ -311,8 +315,8 @@ static int peer_quant_fwd(b2q_ctx* ctx, bool is_max, int upd_mode, float p0, flo
         const int rev = (ctx->reverse && n * 4 > ctx->reverse_min_bytes) ? 1 : 0;
         const bool stream_out = n * 4 > B2Q_STREAM_BYTES;   // outputs that cannot stay in L2 anyway: streaming stores
         b2q_timed_launch tl(ctx, B2Q_KIND_QDQ_HOT, 8.0 * (double)n, st);
-#define B2Q_PEER_SWEEP(C, S) qdq_peer_kernel<C, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, S><<<(unsigned)grid, B2Q_THREADS, 0, st>>>( \
-            x, y, sp, pb, slot, u, qlevel, ctx->fast_div, rev, clip_with_fresh)
+#define B2Q_PEER_SWEEP(C, S) b2q_launch(ctx, qdq_peer_kernel<C, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, S>, (unsigned)grid, B2Q_THREADS, st, \
+            x, y, sp, pb, (const b2q_slot*)slot, u, qlevel, ctx->fast_div, rev, clip_with_fresh)
 #define B2Q_PEER_SWEEP_S(C) do { if (stream_out) B2Q_PEER_SWEEP(C, 1); else B2Q_PEER_SWEEP(C, B2Q_QDQ_STPOL); } while (0)
         if (clip_mode == B2Q_CLIP_SYM) B2Q_PEER_SWEEP_S(B2Q_CLIP_SYM); else B2Q_PEER_SWEEP_S(B2Q_CLIP_NONE);
 #undef B2Q_PEER_SWEEP_S

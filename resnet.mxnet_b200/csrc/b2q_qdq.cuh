@@ -135,6 +135,7 @@ template <int CLIP, int UNROLL, int LDPOL, int STPOL, bool DEFERRED>
 __global__ void __launch_bounds__(B2Q_THREADS)
 qdq_flat_hot_kernel(const float* __restrict__ x, float* __restrict__ y, FlatSplit sp, QdqArgs a, int reverse,
                     DeferredUpdate d, int clip_with_fresh) {
+    b2q_pdl_sync();
     float T, Tc;
     if (DEFERRED) {
         float stat;
@@ -205,6 +206,7 @@ qdq_flat_hot_kernel(const float* __restrict__ x, float* __restrict__ y, FlatSpli
 template <int UNROLL>
 __global__ void __launch_bounds__(B2Q_THREADS)
 qdq_flat_generic_kernel(const float* __restrict__ x, float* __restrict__ y, FlatSplit sp, QdqArgs a) {
+    b2q_pdl_sync();
     const float T = a.thr ? __ldg(a.thr) : a.thr_imm;
     const float Tc = a.clip_thr ? __ldg(a.clip_thr) : (a.thr ? T : a.clip_imm);
     const QScale s = make_qscale(T, a.qlevel, a.fast != 0);
@@ -268,6 +270,7 @@ struct FoldBias {
 template <int CLIP>
 __global__ void __launch_bounds__(B2Q_THREADS)
 qdq_seg_hot_kernel(const float* __restrict__ x, float* __restrict__ y, SegPlan pl, QdqArgs a) {
+    b2q_pdl_sync();
     const SegPiece pc = seg_piece(pl);
     const float T = __ldg(a.thr + pc.g);
     const float Tc = a.clip_thr ? __ldg(a.clip_thr + pc.g) : T;
@@ -297,6 +300,7 @@ qdq_seg_hot_kernel(const float* __restrict__ x, float* __restrict__ y, SegPlan p
 template <int VEC>
 __global__ void __launch_bounds__(128)
 qdq_seg_kernel(const float* __restrict__ x, float* __restrict__ y, SegPlan pl, Prescale ps, FoldBias fb, QdqArgs a) {
+    b2q_pdl_sync();
     const SegPiece pc = seg_piece(pl);
     const float T = a.thr ? __ldg(a.thr + pc.g) : a.thr_imm;
     const float Tc = a.clip_thr ? __ldg(a.clip_thr + pc.g) : (a.thr ? T : a.clip_imm);
@@ -374,6 +378,7 @@ template <bool IS_MAX>
 __global__ void __launch_bounds__(B2Q_THREADS)
 rows_fused_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t rows, int64_t inner, Prescale ps,
                   FoldBias fb, UpdateArgs u, QdqArgs a, int clip_with_fresh) {
+    b2q_pdl_sync();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int64_t row = (int64_t)blockIdx.x * nw + wid;
     if (row >= rows) return;
@@ -453,7 +458,7 @@ template <bool IS_MAX>
     const int nw = B2Q_THREADS / 32;
     const unsigned grid = (unsigned)((rows + nw - 1) / nw);
     b2q_timed_launch tl(ctx, B2Q_KIND_OTHER, 8.0 * (double)(rows * inner), st);
-    rows_fused_kernel<IS_MAX><<<grid, B2Q_THREADS, 0, st>>>(x, y, rows, inner, ps, fb, u, a, clip_with_fresh);
+    b2q_launch(ctx, rows_fused_kernel<IS_MAX>, (unsigned)grid, B2Q_THREADS, st, x, y, rows, inner, ps, fb, u, a, clip_with_fresh);
     B2Q_LAUNCH_CHECK(ctx);
     *done = 1;
     return 0;
@@ -477,6 +482,7 @@ template <int MASK, bool ADD, int UNROLL, int LDPOL, int STPOL>
 __global__ void __launch_bounds__(B2Q_THREADS)
 bwd_flat_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, FlatSplit sp,
                 const float* thr, float thr_imm) {
+    b2q_pdl_sync();
     const float T = (MASK != 0) ? (thr ? __ldg(thr) : thr_imm) : 0.f;
     const float* xb = x + sp.head;
     const float* gb = dy + sp.head;
@@ -526,6 +532,7 @@ template <int MASK, bool ADD>
 __global__ void __launch_bounds__(128)
 bwd_seg_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, SegPlan pl,
                const float* thr, float thr_imm) {
+    b2q_pdl_sync();
     const SegPiece pc = seg_piece(pl);
     const float T = thr ? __ldg(thr + pc.g) : thr_imm;
     for (int64_t o = pc.o0; o < pc.o1; ++o) {
@@ -592,8 +599,8 @@ static inline bool same_misalignment(const void* a, const void* b) {
                 DeferredUpdate none = {};
                 const bool stream_out = n * 4 > B2Q_STREAM_BYTES;
                 const int rev = (ctx->reverse && n * 4 > ctx->reverse_min_bytes) ? 1 : 0;
-#define B2Q_HOT(C, S) qdq_flat_hot_kernel<C, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, S, false> \
-                          <<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, y, sp, a, rev, none, 0)
+#define B2Q_HOT(C, S) b2q_launch(ctx, qdq_flat_hot_kernel<C, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, S, false>, \
+                                 (unsigned)grid, B2Q_THREADS, st, x, y, sp, a, rev, none, 0)
 #define B2Q_HOT_S(C) do { if (stream_out) B2Q_HOT(C, 1); else B2Q_HOT(C, B2Q_QDQ_STPOL); } while (0)
                 switch (a.clip_mode) {
                     case B2Q_CLIP_SYM: B2Q_HOT_S(B2Q_CLIP_SYM); break;
@@ -607,7 +614,7 @@ static inline bool same_misalignment(const void* a, const void* b) {
 #undef B2Q_HOT
             } else {
                 const int64_t grid = b2q_flat_grid(ctx, sp.n8, 2);
-                qdq_flat_generic_kernel<2><<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, y, sp, a);
+                b2q_launch(ctx, qdq_flat_generic_kernel<2>, (unsigned)grid, B2Q_THREADS, st, x, y, sp, a);
             }
             B2Q_LAUNCH_CHECK(ctx);
             return 0;
@@ -621,17 +628,17 @@ static inline bool same_misalignment(const void* a, const void* b) {
     if (ps.gamma == nullptr && fb.bias == nullptr && a.thr != nullptr && a.do_round && a.req != B2Q_REQ_ADD && !a.codes &&
         (inner % 8 == 0) && (pl.part % 8 == 0) && ((((uintptr_t)x) | ((uintptr_t)y)) & 31) == 0 && n >= (1 << 20)) {
         switch (a.clip_mode) {
-            case B2Q_CLIP_WHERE_LE: qdq_seg_hot_kernel<B2Q_CLIP_WHERE_LE><<<grid, B2Q_THREADS, 0, st>>>(x, y, pl, a); break;
-            case B2Q_CLIP_SYM: qdq_seg_hot_kernel<B2Q_CLIP_SYM><<<grid, B2Q_THREADS, 0, st>>>(x, y, pl, a); break;
-            default: qdq_seg_hot_kernel<B2Q_CLIP_NONE><<<grid, B2Q_THREADS, 0, st>>>(x, y, pl, a); break;
+            case B2Q_CLIP_WHERE_LE: b2q_launch(ctx, qdq_seg_hot_kernel<B2Q_CLIP_WHERE_LE>, grid, B2Q_THREADS, st, x, y, pl, a); break;
+            case B2Q_CLIP_SYM: b2q_launch(ctx, qdq_seg_hot_kernel<B2Q_CLIP_SYM>, grid, B2Q_THREADS, st, x, y, pl, a); break;
+            default: b2q_launch(ctx, qdq_seg_hot_kernel<B2Q_CLIP_NONE>, grid, B2Q_THREADS, st, x, y, pl, a); break;
         }
         if (a.clip_mode == B2Q_CLIP_WHERE_LE || a.clip_mode == B2Q_CLIP_SYM || a.clip_mode == B2Q_CLIP_NONE) {
             B2Q_LAUNCH_CHECK(ctx);
             return 0;
         }
     }
-    if (pl.vec == 4) qdq_seg_kernel<4><<<grid, 128, 0, st>>>(x, y, pl, ps, fb, a);
-    else qdq_seg_kernel<1><<<grid, 128, 0, st>>>(x, y, pl, ps, fb, a);
+    if (pl.vec == 4) b2q_launch(ctx, qdq_seg_kernel<4>, grid, 128, st, x, y, pl, ps, fb, a);
+    else b2q_launch(ctx, qdq_seg_kernel<1>, grid, 128, st, x, y, pl, ps, fb, a);
     B2Q_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -669,8 +676,8 @@ template <bool IS_MAX>
         b2q_timed_launch tl(ctx, B2Q_KIND_QDQ_HOT, 8.0 * (double)n, st);
         const bool stream_out = n * 4 > B2Q_STREAM_BYTES;
         const int rev = (ctx->reverse && n * 4 > ctx->reverse_min_bytes) ? 1 : 0;
-#define B2Q_HOT(C, S) qdq_flat_hot_kernel<C, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, S, true> \
-                          <<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, y, sp, a, rev, d, clip_with_fresh)
+#define B2Q_HOT(C, S) b2q_launch(ctx, qdq_flat_hot_kernel<C, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, S, true>, \
+                                 (unsigned)grid, B2Q_THREADS, st, x, y, sp, a, rev, d, clip_with_fresh)
         if (clip_mode == B2Q_CLIP_SYM) { if (stream_out) B2Q_HOT(B2Q_CLIP_SYM, 1); else B2Q_HOT(B2Q_CLIP_SYM, B2Q_QDQ_STPOL); }
         else { if (stream_out) B2Q_HOT(B2Q_CLIP_NONE, 1); else B2Q_HOT(B2Q_CLIP_NONE, B2Q_QDQ_STPOL); }
 #undef B2Q_HOT
@@ -692,12 +699,12 @@ static int launch_bwd_mask(b2q_ctx* ctx, const float* x, const float* dy, float*
             const int64_t grid = b2q_flat_grid(ctx, sp.n8, B2Q_BWD_UNROLL);
             b2q_timed_launch tl(ctx, MASK == 0 ? B2Q_KIND_BWD_STE : B2Q_KIND_BWD_MASK, (MASK == 0 ? 8.0 : 12.0) * (double)n, st);
             const bool stream_out = n * 4 > B2Q_STREAM_BYTES;
-            if (add) bwd_flat_kernel<MASK, true, B2Q_BWD_UNROLL, B2Q_BWD_LDPOL, B2Q_BWD_STPOL>
-                    <<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, dy, dx, sp, thr, thr_imm);
-            else if (stream_out) bwd_flat_kernel<MASK, false, B2Q_BWD_UNROLL, B2Q_BWD_LDPOL, 1>
-                    <<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, dy, dx, sp, thr, thr_imm);
-            else bwd_flat_kernel<MASK, false, B2Q_BWD_UNROLL, B2Q_BWD_LDPOL, B2Q_BWD_STPOL>
-                    <<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, dy, dx, sp, thr, thr_imm);
+            if (add) b2q_launch(ctx, bwd_flat_kernel<MASK, true, B2Q_BWD_UNROLL, B2Q_BWD_LDPOL, B2Q_BWD_STPOL>,
+                                (unsigned)grid, B2Q_THREADS, st, x, dy, dx, sp, thr, thr_imm);
+            else if (stream_out) b2q_launch(ctx, bwd_flat_kernel<MASK, false, B2Q_BWD_UNROLL, B2Q_BWD_LDPOL, 1>,
+                                            (unsigned)grid, B2Q_THREADS, st, x, dy, dx, sp, thr, thr_imm);
+            else b2q_launch(ctx, bwd_flat_kernel<MASK, false, B2Q_BWD_UNROLL, B2Q_BWD_LDPOL, B2Q_BWD_STPOL>,
+                            (unsigned)grid, B2Q_THREADS, st, x, dy, dx, sp, thr, thr_imm);
             B2Q_LAUNCH_CHECK(ctx);
             return 0;
         }
@@ -707,8 +714,8 @@ static int launch_bwd_mask(b2q_ctx* ctx, const float* x, const float* dy, float*
     SegPlan pl = b2q_seg_plan(dy, dx, outer, groups, inner, ctx->num_sms * 16);
     if (MASK != 0 && (((uintptr_t)x) & 15)) pl.vec = 1;
     const unsigned grid = (unsigned)(groups * pl.S * pl.P);
-    if (add) bwd_seg_kernel<MASK, true><<<grid, 128, 0, st>>>(x, dy, dx, pl, thr, thr_imm);
-    else bwd_seg_kernel<MASK, false><<<grid, 128, 0, st>>>(x, dy, dx, pl, thr, thr_imm);
+    if (add) b2q_launch(ctx, bwd_seg_kernel<MASK, true>, grid, 128, st, x, dy, dx, pl, thr, thr_imm);
+    else b2q_launch(ctx, bwd_seg_kernel<MASK, false>, grid, 128, st, x, dy, dx, pl, thr, thr_imm);
     B2Q_LAUNCH_CHECK(ctx);
     return 0;
 }

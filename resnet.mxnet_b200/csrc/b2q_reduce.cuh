@@ -60,6 +60,7 @@ __device__ __forceinline__ void acc8(double& a, float& m, const f8& r) {
 template <bool IS_MAX, int UNROLL, int LDPOL, bool FINALIZE>
 __global__ void __launch_bounds__(B2Q_THREADS)
 reduce_flat_kernel(const float* __restrict__ x, FlatSplit sp, b2q_slot* slot, UpdateArgs u, float count) {
+    b2q_pdl_sync();
     __shared__ double smem[32];
     __shared__ unsigned int s_ticket;
     double acc = 0.0;
@@ -196,6 +197,7 @@ __device__ __forceinline__ float prescale_factor(const Prescale& ps, int64_t row
 template <bool IS_MAX, int VEC>
 __global__ void __launch_bounds__(VEC == 8 ? B2Q_THREADS : 128)
 reduce_seg_kernel(const float* __restrict__ x, SegPlan pl, Prescale ps, b2q_slot* slot, UpdateArgs u) {
+    b2q_pdl_sync();
     __shared__ double smem[32];
     __shared__ unsigned int s_ticket;
     const SegPiece pc = seg_piece(pl);
@@ -324,8 +326,8 @@ static int launch_reduce_deferred(b2q_ctx* ctx, b2q_slot* slot, const float* x, 
     const int64_t grid = b2q_flat_grid(ctx, sp.n8, B2Q_REDUCE_UNROLL,
                                        IS_MAX ? ctx->reduce_deferred_blocks_per_sm : ctx->reduce_blocks_per_sm);
     b2q_timed_launch tl(ctx, B2Q_KIND_REDUCE_FLAT, 4.0 * (double)n, st);
-    reduce_flat_kernel<IS_MAX, B2Q_REDUCE_UNROLL, B2Q_REDUCE_LDPOL, false>
-        <<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, sp, slot, u, (float)n);
+    b2q_launch(ctx, reduce_flat_kernel<IS_MAX, B2Q_REDUCE_UNROLL, B2Q_REDUCE_LDPOL, false>, (unsigned)grid, B2Q_THREADS, st,
+               x, sp, slot, u, (float)n);
     B2Q_LAUNCH_CHECK(ctx);
     *n_partials = (int)grid;
     return 0;
@@ -342,8 +344,8 @@ static int launch_reduce(b2q_ctx* ctx, b2q_slot* slot, const float* x, int64_t o
         if (sp.head <= B2Q_THREADS) {
             const int64_t grid = b2q_flat_grid(ctx, sp.n8, B2Q_REDUCE_UNROLL, ctx->reduce_blocks_per_sm);
             b2q_timed_launch tl(ctx, B2Q_KIND_REDUCE_FLAT, 4.0 * (double)n, st);
-            reduce_flat_kernel<IS_MAX, B2Q_REDUCE_UNROLL, B2Q_REDUCE_LDPOL, true>
-                <<<(unsigned)grid, B2Q_THREADS, 0, st>>>(x, sp, slot, u, (float)n);
+            b2q_launch(ctx, reduce_flat_kernel<IS_MAX, B2Q_REDUCE_UNROLL, B2Q_REDUCE_LDPOL, true>, (unsigned)grid,
+                       B2Q_THREADS, st, x, sp, slot, u, (float)n);
             B2Q_LAUNCH_CHECK(ctx);
             return 0;
         }
@@ -353,9 +355,9 @@ static int launch_reduce(b2q_ctx* ctx, b2q_slot* slot, const float* x, int64_t o
     const unsigned grid = (unsigned)(groups * pl.S * pl.P);
     b2q_timed_launch tl(ctx, B2Q_KIND_OTHER, 4.0 * (double)n, st);
     if (pl.vec == 4 && inner % 8 == 0 && pl.part % 8 == 0 && (((uintptr_t)x) & 31) == 0 && n >= (1 << 20))
-        reduce_seg_kernel<IS_MAX, 8><<<grid, B2Q_THREADS, 0, st>>>(x, pl, ps, slot, u);
-    else if (pl.vec == 4) reduce_seg_kernel<IS_MAX, 4><<<grid, 128, 0, st>>>(x, pl, ps, slot, u);
-    else reduce_seg_kernel<IS_MAX, 1><<<grid, 128, 0, st>>>(x, pl, ps, slot, u);
+        b2q_launch(ctx, reduce_seg_kernel<IS_MAX, 8>, grid, B2Q_THREADS, st, x, pl, ps, slot, u);
+    else if (pl.vec == 4) b2q_launch(ctx, reduce_seg_kernel<IS_MAX, 4>, grid, 128, st, x, pl, ps, slot, u);
+    else b2q_launch(ctx, reduce_seg_kernel<IS_MAX, 1>, grid, 128, st, x, pl, ps, slot, u);
     B2Q_LAUNCH_CHECK(ctx);
     return 0;
 }

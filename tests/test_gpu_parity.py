@@ -372,7 +372,9 @@ def test_int8_export_feeds_an_integer_gemm(T):
     acc = T._int_mm(cx, cw.t().contiguous())                   # int32, exact
     got = acc.to(T.float64) * (float(sx) * float(sw))
     want = xq.to(T.float64) @ wq.to(T.float64).t()             # the fake-quant layer, in fp64 to remove order effects
-    assert T.allclose(got, want, rtol=1e-6, atol=1e-9)
+    # xq / wq are fl(code * step): each factor carries one float32 rounding, sums may cancel -> absolute bound on the row scale
+    scale = float(want.abs().max())
+    assert float((got - want).abs().max()) <= 1e-6 * scale
     # and the fp32 layer the training graph runs agrees with both within fp32 accumulation error
     fp32 = T.nn.functional.linear(xq, wq).to(T.float64)
-    assert T.allclose(fp32, want, rtol=1e-4, atol=1e-5)
+    assert float((fp32 - want).abs().max()) <= 1e-5 * scale

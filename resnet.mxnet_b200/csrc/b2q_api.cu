@@ -154,7 +154,7 @@ int b2q_threshold_update_f32(b2q_ctx* ctx, int mode, const float* stat, float* a
     UpdateArgs u;
     memset(&u, 0, sizeof(u));
     u.mode = mode; u.write_aux = 1; u.use_aux_as_scale = 1; u.p0 = p0; u.p1 = p1; u.aux = aux; u.clip_out = clip_out;
-    threshold_update_kernel<<<(unsigned)((groups + 127) / 128), 128, 0, (cudaStream_t)stream>>>(stat, (int)groups, u);
+    b2q_launch(ctx, threshold_update_kernel, (unsigned)((groups + 127) / 128), 128, (cudaStream_t)stream, stat, (int)groups, u);
     B2Q_LAUNCH_CHECK(ctx);
     return 0;
 }
@@ -302,7 +302,7 @@ int b2q_minmax_quant_finish_f32(b2q_ctx* ctx, int variant, const float* x, float
     b2q_slot* slot = b2q_take_slot(ctx);
     const float* scale_src = aux;
     UpdateArgs u = minmax_update(variant, is_weight, is_train, init, ema_decay, one_minus_decay, aux, slot, &scale_src);
-    threshold_update_kernel<<<(unsigned)((groups + 127) / 128), 128, 0, st>>>(stat, (int)groups, u);
+    b2q_launch(ctx, threshold_update_kernel, (unsigned)((groups + 127) / 128), 128, st, stat, (int)groups, u);
     B2Q_LAUNCH_CHECK(ctx);
     const bool clip = (variant == 1 && !is_weight);
     int eff_req = clip ? B2Q_REQ_WRITE : req;

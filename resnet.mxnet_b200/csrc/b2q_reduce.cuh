@@ -297,6 +297,7 @@ reduce_seg_kernel(const float* __restrict__ x, SegPlan pl, Prescale ps, b2q_slot
 
 // Stand-alone K3 (after a cross-rank allreduce of the statistic).
 static __global__ void threshold_update_kernel(const float* __restrict__ stat, int groups, UpdateArgs u) {
+    b2q_pdl_sync();
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g < groups) apply_update(u, g, stat[g]);
 }

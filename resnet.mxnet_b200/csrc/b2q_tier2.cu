@@ -37,6 +37,7 @@ struct EwIn {
 
 template <class Op>
 __global__ void __launch_bounds__(B2Q_THREADS) ew_kernel(Op op, int64_t n, b2q_slot* slot) {
+    b2q_pdl_sync();
     __shared__ double smem[32];
     __shared__ unsigned int s_ticket;
     op.setup();
@@ -94,7 +95,7 @@ static int launch_ew(b2q_ctx* ctx, Op op, int64_t n, cudaStream_t st) {
     int64_t cap = Op::REDUCES ? (int64_t)ctx->num_sms * 16 : (int64_t)0x7fffffff;   // reducing ops keep 4 partials per block
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
-    ew_kernel<Op><<<(unsigned)grid, B2Q_THREADS, 0, st>>>(op, n, b2q_take_slot(ctx));
+    b2q_launch(ctx, ew_kernel<Op>, (unsigned)grid, B2Q_THREADS, st, op, n, b2q_take_slot(ctx));
     B2Q_LAUNCH_CHECK(ctx);
     return 0;
 }

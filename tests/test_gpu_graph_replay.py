@@ -76,3 +76,55 @@ def test_weight_group_graph_replay_tracks_new_data():
             assert torch.equal(auxs[i].view(torch.int32), auxrs[i].view(torch.int32)), (scale, i)
             assert torch.equal(ys[i].view(torch.int32), yrs[i].view(torch.int32)), (scale, i)
     group.close()
+
+
+def test_tuning_options_never_change_results():
+    """`pdl` (programmatic dependent launch), `deferred`, `reverse`, `fast_div` and the grid knobs are performance options:
+    a forward + backward chain of several operators must give the same bits whatever they are set to."""
+    import torch
+    import b200quant
+    from b200quant import _lib
+    ctx = _lib.context(0)
+    gen = torch.Generator(device="cuda").manual_seed(17)
+    xs = [torch.randn(s, device="cuda", generator=gen) * 3 for s in [(8, 64, 28, 28), (4, 16, 7, 7), (3, 5, 11)]]
+    dys = [torch.randn_like(x) for x in xs]
+    w = torch.randn(64, 32, 3, 3, device="cuda", generator=gen) * 0.05
+
+    def chain():
+        outs = []
+        for op_type, attrs in (("Quantization_int8_V2", dict(quant_mode="minmax", is_weight="False")),
+                               ("ClipGrad_Quantization_int8", dict(quant_mode="minmax", is_weight="False")),
+                               ("GDRQ_PY", dict(nbits="8", group_size="-1", is_weight="False")),
+                               ("GDRQ_PY", dict(nbits="4", group_size="4", is_weight="False"))):
+            for x, dy in zip(xs, dys):
+                if op_type == "GDRQ_PY" and attrs["group_size"] != "-1" and (x.dim() < 2 or x.shape[1] % 4):
+                    continue
+                op = b200quant.get_prop(op_type)(**attrs).create_operator(None, None, None)
+                groups = 1 if attrs.get("group_size", "-1") == "-1" else x.shape[1] // 4
+                aux = torch.ones(groups, device="cuda")
+                y, dx = torch.zeros_like(x), torch.zeros_like(x)
+                op.forward(True, ["write"], [x], [y], [aux])
+                op.backward(["write"], [dy], [x], [y], [dx], [aux])
+                outs += [y, dx, aux]
+        opw = b200quant.get_prop("Quantization_int8_V2")(quant_mode="minmax", is_weight="True",
+                                                         is_weight_perchannel="True").create_operator(None, None, None)
+        wq, aw = torch.zeros_like(w), torch.ones(64, device="cuda")
+        opw.forward(True, ["write"], [w], [wq], [aw])
+        outs += [wq, aw]
+        torch.cuda.synchronize()
+        return [o.clone() for o in outs]
+
+    base = chain()
+    defaults = {k: ctx.get_option(k) for k in ("pdl", "deferred", "reverse", "fast_div", "blocks_per_sm",
+                                                "reduce_blocks_per_sm")}
+    try:
+        for key, value in (("pdl", 0), ("deferred", 0), ("reverse", 0), ("fast_div", 0), ("blocks_per_sm", 2),
+                           ("reduce_blocks_per_sm", 1)):
+            ctx.set_option(key, value)
+            got = chain()
+            ctx.set_option(key, defaults[key])
+            for a, b in zip(base, got):
+                assert torch.equal(a.view(torch.int32), b.view(torch.int32)), key
+    finally:
+        for k, v in defaults.items():
+            ctx.set_option(k, v)

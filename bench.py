@@ -553,11 +553,17 @@ def main():
     kinds = {1: "reduce_flat (max|x| + EMA update)", 2: "qdq_flat_hot (QDQ sweep)", 3: "bwd_flat (STE copy)",
              4: "bwd_flat (clip mask)", 5: "segmented/other"}
     kernels = {}
+    LARGE = 64e6   # algorithmic bytes: the tensors the ">= 70 % of HBM peak on large tensors" target is about
     for k, name in kinds.items():
         kms, kbytes, kn = ctx.timing_read(k)
         if kn:
             kernels[name] = {"launches": kn, "ms_total": kms, "alg_bytes_total": kbytes,
                              "achieved_gbs": kbytes / kms / 1e6, "frac_of_peak": kbytes / kms / 1e6 / peak_gbs}
+            lms, lbytes, ln = ctx.timing_read(k, min_bytes=LARGE)
+            if ln:
+                kernels[name]["large_tensors"] = {"min_alg_bytes": LARGE, "launches": ln, "ms_total": lms,
+                                                  "alg_bytes_total": lbytes, "achieved_gbs": lbytes / lms / 1e6,
+                                                  "frac_of_peak": lbytes / lms / 1e6 / peak_gbs}
     ctx.timing_read(0, reset=True)
     ctx.set_option("timing", 0)
     traffic, traffic_note = None, None

@@ -57,6 +57,10 @@ int64_t b2q_launch_count(b2q_ctx* ctx);
  * 5 segmented/other, 0 all): device milliseconds, ALGORITHMIC bytes (4, 8, 8, 12 B/element) and launch count;
  * reset!=0 clears the records.  Synchronises on the recorded events.  Not usable under stream capture.      */
 int b2q_timing_read(b2q_ctx* ctx, int kind, double* total_ms, double* total_bytes, int64_t* count, int reset);
+/* the same, restricted to launches whose algorithmic bytes lie in [min_bytes, max_bytes) (max_bytes <= 0: no upper
+ * bound): lets a benchmark quote large tensors apart from the launch-bound small ones                          */
+int b2q_timing_read_range(b2q_ctx* ctx, int kind, double min_bytes, double max_bytes, double* total_ms,
+                          double* total_bytes, int64_t* count, int reset);
 
 /* ---- primitives ---------------------------------------------------------------------------------
  * K1/K2  b2q_absmax_f32    stat[g] = max |x|          replaces mx.nd.abs -> mx.nd.max

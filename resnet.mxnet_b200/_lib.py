@@ -31,6 +31,8 @@ _CTX_FUNCS = {
     "b2q_get_option": [ctypes.c_char_p, ctypes.POINTER(_I)],
     "b2q_timing_read": [_I, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                         ctypes.POINTER(_L), _I],
+    "b2q_timing_read_range": [_I, ctypes.c_double, ctypes.c_double, ctypes.POINTER(ctypes.c_double),
+                              ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_L), _I],
     "b2q_absmax_f32": [_P, _L, _L, _L, _P, _P],
     "b2q_meanabs_f32": [_P, _L, _L, _L, _P, _P],
     "b2q_threshold_update_f32": [_I, _P, _P, _P, _L, _F, _F, _P],
@@ -159,10 +161,12 @@ class Context(object):
         self.call("b2q_get_option", key.encode(), ctypes.byref(v))
         return v.value
 
-    def timing_read(self, kind=0, reset=False):
-        """(device ms, algorithmic bytes, launches) recorded since the last reset for one kernel kind."""
+    def timing_read(self, kind=0, reset=False, min_bytes=0.0, max_bytes=0.0):
+        """(device ms, algorithmic bytes, launches) recorded since the last reset for one kernel kind, optionally only
+        the launches whose algorithmic bytes lie in [min_bytes, max_bytes)."""
         ms, by, n = ctypes.c_double(0), ctypes.c_double(0), _L(0)
-        self.call("b2q_timing_read", int(kind), ctypes.byref(ms), ctypes.byref(by), ctypes.byref(n), int(reset))
+        self.call("b2q_timing_read_range", int(kind), float(min_bytes), float(max_bytes), ctypes.byref(ms),
+                  ctypes.byref(by), ctypes.byref(n), int(reset))
         return ms.value, by.value, n.value
 
     def host_sync(self):

@@ -89,13 +89,15 @@ int b2q_set_option(b2q_ctx* ctx, const char* key, int value) {
     return 0;
 }
 
-int b2q_timing_read(b2q_ctx* ctx, int kind, double* total_ms, double* total_bytes, int64_t* count, int reset) {
+int b2q_timing_read_range(b2q_ctx* ctx, int kind, double min_bytes, double max_bytes, double* total_ms,
+                          double* total_bytes, int64_t* count, int reset) {
     B2Q_CTX(ctx);
     B2Q_REQUIRE(kind >= 0 && kind < B2Q_NKINDS, "bad kind");
     double ms = 0.0, bytes = 0.0;
     int64_t n = 0;
     for (const b2q_timing_rec& r : ctx->recs) {
         if (kind != 0 && r.kind != kind) continue;
+        if (r.bytes < min_bytes || (max_bytes > 0.0 && r.bytes >= max_bytes)) continue;
         B2Q_CHECK_CUDA(cudaEventSynchronize(r.e1));
         float t = 0.f;
         B2Q_CHECK_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
@@ -109,6 +111,10 @@ int b2q_timing_read(b2q_ctx* ctx, int kind, double* total_ms, double* total_byte
         ctx->recs.clear();
     }
     return 0;
+}
+
+int b2q_timing_read(b2q_ctx* ctx, int kind, double* total_ms, double* total_bytes, int64_t* count, int reset) {
+    return b2q_timing_read_range(ctx, kind, 0.0, 0.0, total_ms, total_bytes, count, reset);
 }
 
 int b2q_get_option(b2q_ctx* ctx, const char* key, int* value) {

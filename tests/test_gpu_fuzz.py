@@ -97,3 +97,39 @@ def test_bad_arguments_raise():
     with pytest.raises(B2QError):        # C ABI argument check surfaces with the library's message
         K.qdq(x, torch.empty_like(x), torch.ones(1, device="cuda"), 127, 99, "write")
     op.forward(True, ["null"], [x], [torch.empty_like(x)], [torch.ones(1, device="cuda")])   # null req is legal
+
+
+@pytest.mark.parametrize("op_type", ["Quantization_int8_V2", "ClipGrad_Quantization_int8", "GDRQ_PY"])
+def test_guard_regions_around_medium_tensors(op_type):
+    """Out-of-range WRITES of the vectorised paths: tensors of 2^16 + k elements placed at every float offset 0..8 inside
+    buffers whose surroundings hold a canary; forward and backward must leave every canary untouched and match the
+    oracle bit for bit (compute-sanitizer is not available on the GPU pool, this is the bounds check we run instead)."""
+    import torch
+    rng = np.random.default_rng(31)
+    canary = 12345.678
+    pad = 64
+    for k in (0, 1, 7, 8, 9, 31, 255):
+        n = (1 << 16) + k
+        x = (rng.standard_normal(n) * 2).astype(F)
+        dy = rng.standard_normal(n).astype(F)
+        for offset in (0, 1, 3, 8):
+            if op_type == "GDRQ_PY":
+                op, ref = _ops(op_type, nbits=8, group_size=-1, is_weight=False, lamda=0.01, ktimes=3)
+            else:
+                op, ref = _ops(op_type, quant_mode="minmax", is_weight=False)
+            bufs = [torch.full((n + 2 * pad + 16,), canary, device="cuda") for _ in range(4)]
+            lo = pad + offset
+            xd, yd, gd, dd = (b[lo:lo + n] for b in bufs)
+            xd.copy_(torch.from_numpy(x))
+            gd.copy_(torch.from_numpy(dy))
+            aux_d, aux_r = [torch.ones(1, device="cuda")], [np.ones(1, F)]
+            yr, dr = np.zeros(n, F), np.zeros(n, F)
+            op.forward(True, ["write"], [xd], [yd], aux_d)
+            ref.forward(True, ["write"], [x], [yr], aux_r)
+            op.backward(["write"], [gd], [xd], [yd], [dd], aux_d)
+            ref.backward(["write"], [dy], [x], [yr], [dr], aux_r)
+            assert bits_equal(aux_d[0].cpu().numpy(), aux_r[0]), (k, offset)
+            assert bits_equal(yd.cpu().numpy(), yr), (k, offset)
+            assert bits_equal(dd.cpu().numpy(), dr), (k, offset)
+            for b in bufs:
+                assert bool((b[:lo] == canary).all()) and bool((b[lo + n:] == canary).all()), (k, offset)

@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--full-model-multi", action="store_true",
+                    help="also run the whole-network context leg data parallel when launched on several GPUs")
     ap.add_argument("--no-full-model", action="store_true",
                     help="skip the context leg that trains the whole ResNet-50 (library convolutions + these operators)")
     ap.add_argument("--profile", action="store_true",
@@ -192,20 +194,29 @@ CPU_SAMPLE = [("act", (256, 64, 56, 56)), ("act", (256, 256, 14, 14)), ("act", (
               ("weight", (512, 512, 3, 3)), ("weight", (64, 3, 7, 7))]
 
 
-def full_model_leg(torch, device, batch, steps=8, warmup=3):
+def full_model_leg(torch, device, batch, steps=8, warmup=3, world=1, rank=0):
     """Context only (not the metric): one SGD step of the whole ResNet-50 int8-QAT network of symbol/resnet_int8.py --
     cuDNN/cuBLAS convolutions, BatchNorm and pooling from torch, every conv/FC input and weight through this package's
-    Quantization_int8_V2 nodes -- to show what share of a training step the quantization path is."""
-    from b200quant.harness import ResNetInt8
+    Quantization_int8_V2 nodes -- to show what share of a training step the quantization path is.  With world > 1
+    (--full-model-multi) it is the data-parallel training the reference runs through Module + KVStore (train.py:34-35):
+    activation thresholds through the fused peer-memory exchange, gradients through DistributedDataParallel."""
+    from b200quant.harness import ResNetInt8, quant_nodes
     torch.manual_seed(11)
     model = ResNetInt8().to(device)
+    net, ex = model, None
+    if world > 1:
+        from b200quant.dist import attach_peer_exchange
+        ex = attach_peer_exchange([m.op for m in quant_nodes(model)], device)
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[device.index], broadcast_buffers=False,
+                                                        gradient_as_bucket_view=True)
     opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
-    x = torch.randn(batch, 3, 224, 224, device=device)
-    y = torch.randint(0, 1000, (batch,), device=device)
+    g = torch.Generator(device=device).manual_seed(100 + rank)
+    x = torch.randn(batch, 3, 224, 224, device=device, generator=g)
+    y = torch.randint(0, 1000, (batch,), device=device, generator=g)
 
     def train_step():
         opt.zero_grad(set_to_none=True)
-        loss = torch.nn.functional.cross_entropy(model(x), y)
+        loss = torch.nn.functional.cross_entropy(net(x), y)
         loss.backward()
         opt.step()
         return loss
@@ -220,8 +231,25 @@ def full_model_leg(torch, device, batch, steps=8, warmup=3):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
-    return {"images_per_sec": batch / (ms / 1e3), "ms_per_step": ms, "batch": batch, "steps": steps,
-            "loss": float(loss), "conv_math": "torch/cuDNN fp32 (TF32 %s)" % ("on" if torch.backends.cudnn.allow_tf32 else "off"),
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        # every rank must hold the same thresholds after a data-parallel step
+        aux = torch.cat([a.flatten() for m in quant_nodes(model) for a in m.aux_list()])
+        lo, hi = aux.clone(), aux.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        same = bool(torch.equal(lo, hi))
+        torch.cuda.synchronize()
+        dist.barrier()
+        ex.close()
+    else:
+        same = None
+    return {"images_per_sec": world * batch / (ms / 1e3), "ms_per_step": ms, "batch": batch, "n_gpus": world,
+            "steps": steps, "thresholds_identical_across_ranks": same,
+            "loss": float(loss.detach()), "conv_math": "torch/cuDNN fp32 (TF32 %s)" % ("on" if torch.backends.cudnn.allow_tf32 else "off"),
             "note": "whole ResNet-50 int8-QAT SGD step, eager torch autograd; convolutions/BN are library code, "
                     "quantization nodes are this package's (108 nodes); context for the metric, not the metric"}
 
@@ -347,9 +375,10 @@ def main():
     fn, batch, op_type = WORKLOADS[args.workload]
     batch = args.batch or batch
     full_model = None
-    if world == 1 and not args.no_full_model and not args.profile and args.workload == "resnet50_int8":
+    if (world == 1 or args.full_model_multi) and not args.no_full_model and not args.profile \
+            and args.workload == "resnet50_int8":
         try:   # context leg, run first while the device memory is still free
-            full_model = full_model_leg(torch, device, batch)
+            full_model = full_model_leg(torch, device, batch, world=world, rank=rank)
         except Exception as e:  # pragma: no cover
             full_model = {"images_per_sec": None, "error": str(e).splitlines()[0][:200]}
         import gc

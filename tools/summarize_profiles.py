@@ -129,8 +129,11 @@ if __name__ == "__main__":
     os.makedirs(PROF, exist_ok=True)
     launches(tag)
     full(tag)
+    # only what the visit being summarised produced: gpurun_out/ is scratch and keeps files of earlier visits
+    ref = os.path.join(OUT, "launches.csv")
+    newest = os.path.getmtime(ref) if os.path.exists(ref) else 0.0
     for f in ("bench_ours.json", "bench_reference.json", "microbench.log", "l2_probe.json"):
         p = os.path.join(OUT, f)
-        if os.path.exists(p) and os.path.getsize(p):
+        if os.path.exists(p) and os.path.getsize(p) and abs(os.path.getmtime(p) - newest) < 3600:
             open(os.path.join(PROF, tag + "_" + f), "w").write(open(p).read())
     print("profiles/: " + ", ".join(sorted(os.listdir(PROF))))

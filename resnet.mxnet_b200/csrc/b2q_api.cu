@@ -70,6 +70,7 @@ static int* option_slot(b2q_ctx* ctx, const char* key) {
     if (!strcmp(key, "blocks_per_sm")) return &ctx->blocks_per_sm;
     if (!strcmp(key, "reduce_blocks_per_sm")) return &ctx->reduce_blocks_per_sm;
     if (!strcmp(key, "peer_reduce_blocks_per_sm")) return &ctx->peer_reduce_blocks_per_sm;
+    if (!strcmp(key, "reduce_deferred_blocks_per_sm")) return &ctx->reduce_deferred_blocks_per_sm;
     if (!strcmp(key, "deferred")) return &ctx->deferred;
     if (!strcmp(key, "pdl")) return &ctx->pdl;
     if (!strcmp(key, "reverse")) return &ctx->reverse;
@@ -82,7 +83,8 @@ int b2q_set_option(b2q_ctx* ctx, const char* key, int value) {
     B2Q_REQUIRE(ctx && key, "null argument");
     int* p = option_slot(ctx, key);
     B2Q_REQUIRE(p != nullptr, "unknown option");
-    if (p == &ctx->blocks_per_sm || p == &ctx->reduce_blocks_per_sm || p == &ctx->peer_reduce_blocks_per_sm)
+    if (p == &ctx->blocks_per_sm || p == &ctx->reduce_blocks_per_sm || p == &ctx->peer_reduce_blocks_per_sm ||
+        p == &ctx->reduce_deferred_blocks_per_sm)
         B2Q_REQUIRE(value >= 1 && value <= 65536, "blocks_per_sm out of range");
     if (p == &ctx->reduce_blocks_per_sm) B2Q_REQUIRE(value <= B2Q_MAX_PIECES / 256, "too many reduction blocks");
     *p = value;

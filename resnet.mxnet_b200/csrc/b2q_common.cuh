@@ -50,7 +50,7 @@ struct b2q_ctx {
     int blocks_per_sm = 4096;        // flat QDQ / backward sweeps: grid = min(tiles, SMs x this); the sweep shows one
                                      // 16 KB tile per block (no grid-stride loop) is fastest: dynamic balance over SMs
     int reduce_blocks_per_sm = 4;    // flat reductions that finalise in their last block (partials are re-read)
-    int reduce_deferred_blocks_per_sm = 16;   // flat reductions with deferred update (one atomicMax per block)
+    int reduce_deferred_blocks_per_sm = 64;   // flat reductions with deferred update (one atomicMax per block)
     int pdl = 1;                              // programmatic dependent launch between consecutive whole-tensor kernels
     int peer_reduce_blocks_per_sm = 8;        // max reductions of the peer-memory exchange (atomicMax + ticket per block)
     int deferred = 1;                // consumer-side threshold update in the fused whole-tensor forward

@@ -114,8 +114,8 @@ int b2q_host_release(b2q_ctx* ctx);  // b2q_host.cu
 // waits for the predecessor to complete and flush before touching memory, then lets its own successor do the same).
 // It hides the launch latency and prologue of ~300 back-to-back kernels per step; ordering and results are unchanged.
 template <typename... KArgs, typename... Args>
-static inline void b2q_launch(const b2q_ctx* ctx, void (*kernel)(KArgs...), unsigned grid, unsigned block,
-                              cudaStream_t st, Args&&... args) {
+static inline void b2q_launch(b2q_ctx* ctx, void (*kernel)(KArgs...), unsigned grid, unsigned block,
+                              cudaStream_t st, const Args&... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid, 1, 1);
     cfg.blockDim = dim3(block, 1, 1);
@@ -125,7 +125,13 @@ static inline void b2q_launch(const b2q_ctx* ctx, void (*kernel)(KArgs...), unsi
     attr.val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = ctx->pdl ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);   // error picked up by B2Q_LAUNCH_CHECK
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, args...);
+    if (e == cudaErrorNotSupported && cfg.numAttrs) {   // a driver without dependent launches: plain launches from now on
+        (void)cudaGetLastError();
+        ctx->pdl = 0;
+        cfg.numAttrs = 0;
+        cudaLaunchKernelEx(&cfg, kernel, args...);
+    }   // any other error is picked up by B2Q_LAUNCH_CHECK
 }
 
 static inline b2q_slot* b2q_take_slot(b2q_ctx* ctx) {

@@ -254,12 +254,26 @@ def full_model_leg(torch, device, batch, steps=8, warmup=3, world=1, rank=0):
                     "quantization nodes are this package's (108 nodes); context for the metric, not the metric"}
 
 
-def cpu_reference_step(sample_state):
+def cpu_reference_step(sample_state, op_type="Quantization_int8_V2"):
+    """One forward + backward of the sample tensors through the C restatement of the workload's operator."""
     from oracle import c_oracle as co
+    if op_type == "GDRQ_PY":   # the attributes of make_op: nbits 8 -> 255 levels, ktimes 3, lamda 0.001
+        for s in sample_state:
+            co.gdrq_fwd(s["x"], s["y"], s["aux"], s["w"], False, True, 255.0, 3.0, 0.001)
+        for s in reversed(sample_state):
+            if s["w"]:
+                co.ste_bwd(s["dy"], s["dx"])
+            else:
+                co.gdrq_bwd(s["x"], s["dy"], s["dx"], s["aux"])
+        return
+    variant = 1 if op_type == "ClipGrad_Quantization_int8" else 0
     for s in sample_state:
-        co.minmax_quant_fwd(0, s["x"], s["y"], s["aux"], s["w"], False, True, False, 0.99)
+        co.minmax_quant_fwd(variant, s["x"], s["y"], s["aux"], s["w"], False, True, False, 0.99)
     for s in reversed(sample_state):
-        co.ste_bwd(s["dy"], s["dx"])
+        if variant == 1 and not s["w"]:
+            co.clipgrad_bwd(s["x"], s["dy"], s["dx"], s["aux"])
+        else:
+            co.ste_bwd(s["dy"], s["dx"])
 
 
 def cpu_reference_prepare():
@@ -275,14 +289,14 @@ def cpu_reference_prepare():
     return st, sum(numel(s) for _, s in CPU_SAMPLE)
 
 
-def cpu_baseline(total_elems, batch, steps=2, warmup=1):
+def cpu_baseline(total_elems, batch, steps=2, warmup=1, op_type="Quantization_int8_V2"):
     from oracle import c_oracle as co
     st, sample_elems = cpu_reference_prepare()
     for _ in range(warmup):
-        cpu_reference_step(st)
+        cpu_reference_step(st, op_type)
     t0 = time.perf_counter()
     for _ in range(steps):
-        cpu_reference_step(st)
+        cpu_reference_step(st, op_type)
     dt = (time.perf_counter() - t0) / steps
     full = dt * total_elems / sample_elems
     return dict(value=batch / full, unit=UNIT, cores=co.num_threads(), kind="port",
@@ -297,23 +311,26 @@ def main_reference(args):
     if rank != 0:
         return 0
     from b200quant.workloads import WORKLOADS, summary
-    fn, batch, _ = WORKLOADS[args.workload]
+    fn, batch, op_type = WORKLOADS[args.workload]
+    if op_type == "GDRQ_Fold_BN":
+        raise SystemExit("the fold-BN workload is a parity case (tests/test_gpu_configs.py), not a bench line")
     batch = args.batch or batch
     sm = summary(fn(batch))
     total = sm["act_elems"] + sm["weight_elems"]
     from oracle import c_oracle as co
     st, sample_elems = cpu_reference_prepare()
     for _ in range(max(1, min(args.warmup, 2))):
-        cpu_reference_step(st)
+        cpu_reference_step(st, op_type)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_reference_step(st)
+        cpu_reference_step(st, op_type)
     dt = (time.perf_counter() - t0) / args.steps
     full = dt * total / sample_elems
     value = batch / full
     sample = ("each step = fwd+bwd of %s (%d of %d elements), time scaled by element count"
               % (", ".join("x".join(map(str, s)) for _, s in CPU_SAMPLE), sample_elems, total))
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+    line = {"impl": "reference",
+            "metric": METRIC if args.workload == "resnet50_int8" else args.workload + "_quant_path_images_per_sec", "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": full * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "%s quant path (fwd+bwd of all %d nodes), batch %d" %
@@ -656,9 +673,9 @@ def main():
         except Exception as e:  # pragma: no cover - e.g. not enough lockable host memory
             line["e2e"] = {"value": None, "unit": UNIT, "error": str(e).splitlines()[0][:200]}
 
-    if rank == 0 and world == 1 and not args.no_cpu and op_type == "Quantization_int8_V2":
+    if rank == 0 and world == 1 and not args.no_cpu:
         try:
-            line["cpu_baseline"] = cpu_baseline(total_elems, batch)
+            line["cpu_baseline"] = cpu_baseline(total_elems, batch, op_type=op_type)
         except Exception as e:  # pragma: no cover
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "error": str(e).splitlines()[0][:200]}
 

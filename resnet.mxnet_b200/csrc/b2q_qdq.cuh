@@ -135,6 +135,23 @@ template <int CLIP, int UNROLL, int LDPOL, int STPOL, bool DEFERRED>
 __global__ void __launch_bounds__(B2Q_THREADS)
 qdq_flat_hot_kernel(const float* __restrict__ x, float* __restrict__ y, FlatSplit sp, QdqArgs a, int reverse,
                     DeferredUpdate d, int clip_with_fresh) {
+    const float* xb = x + sp.head;
+    float* yb = y + sp.head;
+    const int64_t tile = (int64_t)B2Q_THREADS * UNROLL;
+    const int64_t ntiles = (sp.n8 + tile - 1) / tile;
+    f8 v[UNROLL];
+    if (DEFERRED) {
+        // The fused forward launches this kernel right behind its reduction, which only READS x and has itself waited
+        // for whatever produced x before letting us start: the first tile can be requested before the dependency wait,
+        // so its HBM latency overlaps the reduction's last wave.  (Only x: the statistic and y come after the wait.)
+        const int64_t t0 = reverse ? (ntiles - 1 - (int64_t)blockIdx.x) : (int64_t)blockIdx.x;
+        const int64_t base0 = t0 * tile + threadIdx.x;
+#pragma unroll
+        for (int k = 0; k < UNROLL; ++k) {
+            const int64_t i = base0 + (int64_t)k * B2Q_THREADS;
+            if ((int64_t)blockIdx.x < ntiles && i < sp.n8) v[k] = ld_f8<LDPOL>(xb + 8 * i);
+        }
+    }
     b2q_pdl_sync();
     float T, Tc;
     if (DEFERRED) {
@@ -168,18 +185,15 @@ qdq_flat_hot_kernel(const float* __restrict__ x, float* __restrict__ y, FlatSpli
     }
     const bool needs_pos = (CLIP != B2Q_CLIP_NONE && CLIP != B2Q_CLIP_PACT);
     const QScale s = make_qscale(T, a.qlevel, a.fast != 0 && !(needs_pos && !(Tc >= 0.f)));
-    const float* xb = x + sp.head;
-    float* yb = y + sp.head;
-    const int64_t tile = (int64_t)B2Q_THREADS * UNROLL;
-    const int64_t ntiles = (sp.n8 + tile - 1) / tile;
     for (int64_t tt = blockIdx.x; tt < ntiles; tt += gridDim.x) {
         const int64_t t = reverse ? (ntiles - 1 - tt) : tt;
         const int64_t base = t * tile + threadIdx.x;
-        f8 v[UNROLL];
+        if (!DEFERRED || tt != (int64_t)blockIdx.x) {
 #pragma unroll
-        for (int k = 0; k < UNROLL; ++k) {
-            const int64_t i = base + (int64_t)k * B2Q_THREADS;
-            if (i < sp.n8) v[k] = ld_f8<LDPOL>(xb + 8 * i);
+            for (int k = 0; k < UNROLL; ++k) {
+                const int64_t i = base + (int64_t)k * B2Q_THREADS;
+                if (i < sp.n8) v[k] = ld_f8<LDPOL>(xb + 8 * i);
+            }
         }
 #pragma unroll
         for (int k = 0; k < UNROLL; ++k) {

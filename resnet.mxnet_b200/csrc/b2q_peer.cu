@@ -176,12 +176,12 @@ template <int CLIP, int UNROLL, int LDPOL, int STPOL>
 __global__ void __launch_bounds__(B2Q_THREADS)
 qdq_peer_kernel(const float* __restrict__ x, float* __restrict__ y, FlatSplit sp, PeerBoxes pb, const b2q_slot* slot,
                 UpdateArgs u, float qlevel, int fast, int reverse, int clip_with_fresh) {
-    b2q_pdl_sync();
     const float* xb = x + sp.head;
     float* yb = y + sp.head;
     const int64_t tile = (int64_t)B2Q_THREADS * UNROLL;
     const int64_t ntiles = (sp.n8 + tile - 1) / tile;
-    // first tile's loads go out before the mailbox is read: the gather's L2 round trip hides behind the HBM latency
+    // The first tile's loads go out before the dependency wait and before the mailbox is read: the preceding kernel (this
+    // call's reduction) only READS x and has itself waited for x's producer, so the HBM latency overlaps its last wave.
     f8 v[UNROLL];
     int64_t tt = blockIdx.x;
     {
@@ -193,6 +193,7 @@ qdq_peer_kernel(const float* __restrict__ x, float* __restrict__ y, FlatSplit sp
             if (tt < ntiles && i < sp.n8) v[k] = ld_f8<LDPOL>(xb + 8 * i);
         }
     }
+    b2q_pdl_sync();
     const float a_old = slot->scale[0];
     const float stat = peer_gather(pb);
     float fresh, next;

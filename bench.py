@@ -291,6 +291,7 @@ def cpu_reference_prepare():
 
 def cpu_baseline(total_elems, batch, steps=2, warmup=1, op_type="Quantization_int8_V2"):
     from oracle import c_oracle as co
+    co.use_all_host_threads()   # whatever OMP_NUM_THREADS the launcher exported (torchrun sets it to 1)
     st, sample_elems = cpu_reference_prepare()
     for _ in range(warmup):
         cpu_reference_step(st, op_type)
@@ -318,6 +319,7 @@ def main_reference(args):
     sm = summary(fn(batch))
     total = sm["act_elems"] + sm["weight_elems"]
     from oracle import c_oracle as co
+    co.use_all_host_threads()   # the reference arm gets every host thread, also under torchrun (OMP_NUM_THREADS=1)
     st, sample_elems = cpu_reference_prepare()
     for _ in range(max(1, min(args.warmup, 2))):
         cpu_reference_step(st, op_type)

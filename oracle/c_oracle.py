@@ -48,6 +48,21 @@ def num_threads():
     return int(load().b2qo_num_threads())
 
 
+def set_num_threads(n):
+    """Thread count of the OpenMP loops (launchers such as torchrun export OMP_NUM_THREADS=1 to their workers)."""
+    load().b2qo_set_num_threads(int(n))
+    return num_threads()
+
+
+def use_all_host_threads():
+    import os
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:  # pragma: no cover
+        n = os.cpu_count() or 1
+    return set_num_threads(n)
+
+
 def minmax_quant_fwd(variant, x, y, aux, is_weight, per_channel, is_train, init, ema_decay, req="write"):
     rows, cols = _rc(x.shape)
     rc = load().b2qo_minmax_quant_fwd(variant, _p(x), _p(y), _p(aux), rows, cols, int(is_weight), int(per_channel),

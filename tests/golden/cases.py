@@ -199,6 +199,71 @@ CASES = [
     dict(id="qil_v3", op_type="QIL_V3_PY", attrs=dict(is_weight="True", fix_gamma="True", nbits="4"),
          inputs=[("unit", (4, 3, 3, 3)), ("const", (1,), -2.0), ("const", (1,), -0.3), ("const", (1,), 1.0)],
          aux_init=[], steps=[(T, W, True)]),
+    # ---- second batch: FC shapes, eval-first / add / delay combinations, grouped convolution, other bit widths --------
+    dict(id="qi8v2_fc_weight_perchannel", op_type="Quantization_int8_V2",
+         attrs=_qi8(is_weight=True, is_weight_perchannel=True, delay_quant=0),
+         inputs=[("normal", (10, 33))], aux_init=[1.0],
+         steps=[(T, W, True), (T, A, True), (E, W, False)]),
+    dict(id="qi8v2_fc_act", op_type="Quantization_int8_V2",
+         attrs=_qi8(is_weight=False, is_weight_perchannel=False, delay_quant=0, ema_decay=0.9),
+         inputs=[("relu", (7, 33))], aux_init=[1.0],
+         steps=[(T, W, True), (T, W, True), (T, W, True), (E, A, False)]),
+    dict(id="qi8v2_weight_delay", op_type="Quantization_int8_V2",
+         attrs=_qi8(is_weight=True, is_weight_perchannel=False, delay_quant=1),
+         inputs=[("normal", (4, 2, 3, 3))], aux_init=[1.0],
+         steps=[(T, W, True), (E, W, False), (T, W, True)]),
+    dict(id="clipgrad_fc_weight_eval_first", op_type="ClipGrad_Quantization_int8",
+         attrs=_qi8(is_weight=True, is_weight_perchannel=False, delay_quant=0),
+         inputs=[("normal", (12, 17))], aux_init=[0.75],
+         steps=[(E, W, False), (T, W, True), (E, W, False)]),
+    dict(id="clipgrad_weight_perchannel_eval_first", op_type="ClipGrad_Quantization_int8",
+         attrs=_qi8(is_weight=True, is_weight_perchannel=True, delay_quant=0),
+         inputs=[("normal", (5, 3, 3, 3))], aux_init=[0.5],
+         steps=[(E, W, False), (T, A, True)]),
+    dict(id="clipgrad_act_add_req", op_type="ClipGrad_Quantization_int8",   # the op writes with [:]= whatever req says
+         attrs=_qi8(is_weight=False, is_weight_perchannel=False, delay_quant=0),
+         inputs=[("normal", (3, 5, 4, 4))], aux_init=[1.0],
+         steps=[(T, A, True), (T, A, True), (E, A, True)]),
+    dict(id="gdrq_weight_fixalpha", op_type="GDRQ_PY",
+         attrs=dict(nbits="8", group_size="-1", is_weight="True", lamda="0.001", delay_quant="0",
+                    fix_alpha="True", ktimes="3"),
+         inputs=[("normal", (6, 4, 3, 3))], aux_init=[0.3],
+         steps=[(T, W, True), (E, A, True)]),
+    dict(id="gdrq_act_delay2_add", op_type="GDRQ_PY",
+         attrs=dict(nbits="6", group_size="-1", is_weight="False", lamda="0.05", delay_quant="2",
+                    fix_alpha="False", ktimes="2"),
+         inputs=[("relu", (3, 4, 6, 6))], aux_init=[2.0],
+         steps=[(T, W, True), (T, A, True), (T, W, True), (E, W, True)]),
+    dict(id="gdrq_weight_grouped_delay", op_type="GDRQ_PY",
+         attrs=dict(nbits="3", group_size="4", is_weight="True", lamda="0.001", delay_quant="1",
+                    fix_alpha="False", ktimes="3"),
+         inputs=[("normal", (8, 2, 3, 3))], aux_init=[0.5],
+         steps=[(T, W, True), (T, W, True), (E, W, False)]),
+    dict(id="gdrq_fc_act_grouped", op_type="GDRQ_PY",
+         attrs=dict(nbits="8", group_size="8", is_weight="False", lamda="0.001", delay_quant="0",
+                    fix_alpha="False", ktimes="3"),
+         inputs=[("normal", (5, 24))], aux_init=[1.0],
+         steps=[(T, W, True), (T, W, True)]),
+    dict(id="foldbn_grouped_conv_stride2", op_type="GDRQ_Fold_BN",
+         attrs=_fold(is_weight_perchannel=True, delay_quant=0, num_filter=6, num_group=2, kernel=(3, 3),
+                     stride=(2, 2), pad=(1, 1), quantize_flag=True),
+         inputs=_fold_inputs(2, 4, 9, 9, 6, 2, 3, 2, 1), aux_init=[1.0, 1.0],
+         steps=[(T, W, True), (T, W, True), (T, W, True)]),
+    dict(id="clip_relu_4bit", op_type="CLIP_RELU_PY", attrs=dict(nbits="4", threshold="6.0"),
+         inputs=[("normal", (3, 5, 5))], aux_init=[],
+         steps=[(T, W, True), (E, A, True)], input_gain=4.0),
+    dict(id="quant_ste_4bit", op_type="QUANT_STE_PY", attrs=dict(nbits="4"),
+         inputs=[("uniform", (9, 13))], aux_init=[],
+         steps=[(T, W, True), (E, W, True)]),
+    dict(id="pact_8bit", op_type="PACT_PY", attrs=dict(nbits="8"),
+         inputs=[("relu", (4, 3, 5, 5)), ("const", (1,), 0.8)], aux_init=[],
+         steps=[(T, W, True)]),
+    dict(id="dorefa_2bit", op_type="DoReFa_PY", attrs=dict(nbits="2"),
+         inputs=[("normal", (5, 4, 3, 3))], aux_init=[],
+         steps=[(T, W, True)]),
+    dict(id="wnq_8bit_perchannel_fc", op_type="WNQ_PY", attrs=dict(nbits="8", is_perchannel="True"),
+         inputs=[("normal", (7, 19))], aux_init=[],
+         steps=[(T, W, True), (T, W, True)]),
 ]
 
 CASE_BY_ID = {c["id"]: c for c in CASES}

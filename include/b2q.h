@@ -43,6 +43,11 @@ const char* b2q_last_error(void);
 int b2q_create(int device, b2q_ctx** out);
 int b2q_destroy(b2q_ctx* ctx);
 int b2q_num_sms(b2q_ctx* ctx);
+/* cudaStreamSynchronize(stream) on ctx's device.  The library never synchronises by itself; this is for hosts whose
+ * scheduler cannot see the library's launches (MXNet's engine: a CustomOp callback must not return before its kernels
+ * are done, python/mxnet/operator.py [upstream]) -- the MXNet-side operator wrapper calls it with the legacy default
+ * stream (0) after forward / backward, see INTEGRATION.md section 3.                                                */
+int b2q_stream_synchronize(b2q_ctx* ctx, void* stream);
 /* run-time knobs for benchmarking sweeps: "blocks_per_sm" (grid = SMs x this), "reverse" (QDQ sweep walks
  * descending addresses to reuse what the reduction left in L2), "fast_div" (reciprocal fast path on/off),
  * "peer_reduce_blocks_per_sm" (grid of the max reduction in the peer-memory exchange), "pdl" (programmatic dependent

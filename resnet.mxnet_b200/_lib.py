@@ -27,6 +27,7 @@ MASK_OPEN, MASK_ABS_LE, MASK_LT = 1, 2, 3
 _CTX_FUNCS = {
     "b2q_destroy": [],
     "b2q_num_sms": [],
+    "b2q_stream_synchronize": [_P],
     "b2q_set_option": [ctypes.c_char_p, _I],
     "b2q_get_option": [ctypes.c_char_p, ctypes.POINTER(_I)],
     "b2q_timing_read": [_I, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),

@@ -64,6 +64,12 @@ int b2q_destroy(b2q_ctx* ctx) {
 
 int b2q_num_sms(b2q_ctx* ctx) { return ctx ? ctx->num_sms : -1; }
 
+int b2q_stream_synchronize(b2q_ctx* ctx, void* stream) {
+    B2Q_CTX(ctx);
+    B2Q_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+}
+
 int64_t b2q_launch_count(b2q_ctx* ctx) { return ctx ? ctx->launches : -1; }
 
 static int* option_slot(b2q_ctx* ctx, const char* key) {

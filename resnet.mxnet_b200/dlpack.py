@@ -103,12 +103,27 @@ def as_buffer(obj, write=False):
     raise TypeError("cannot view %r as a DLPack tensor" % type(obj))
 
 
+FOREIGN_DEVICES = set()   # devices whose legacy default stream got launches for arrays torch does not own
+
+
 def current_stream(buf):
     """CUDA stream to launch on for ``buf``'s device: torch's current stream when torch owns the memory,
-    the legacy default stream (0) otherwise (MXNet: the shim synchronises)."""
+    the legacy default stream (0) otherwise (MXNet: ``operator.register`` wraps forward / backward so that they
+    synchronise that stream before returning to the engine)."""
     if torch is not None and isinstance(buf.keep, torch.Tensor) and buf.on_device:
         return _raw_stream(buf.device_id)
+    if buf.on_device:
+        FOREIGN_DEVICES.add(buf.device_id)
     return 0
+
+
+def sync_foreign():
+    """Wait for the default-stream launches made for non-torch arrays (no-op when there were none)."""
+    if not FOREIGN_DEVICES:
+        return
+    from . import _lib
+    while FOREIGN_DEVICES:
+        _lib.context(FOREIGN_DEVICES.pop()).call("b2q_stream_synchronize", 0)
 
 
 def _raw_stream(device_id):

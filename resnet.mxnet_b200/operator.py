@@ -22,11 +22,35 @@ if HAVE_MXNET:  # pragma: no cover
     CustomOp = _mx.operator.CustomOp
     CustomOpProp = _mx.operator.CustomOpProp
 
+    def _synced(method):
+        """MXNet's engine cannot see the library's launches: do not hand control back before they are done."""
+        import functools
+
+        @functools.wraps(method)
+        def call(self, *args, **kwargs):
+            try:
+                return method(self, *args, **kwargs)
+            finally:
+                from .dlpack import sync_foreign
+                sync_foreign()
+        call.__b2q_syncs__ = True
+        return call
+
     def register(reg_name):
         mx_deco = _mx.operator.register(reg_name)
 
         def deco(prop_cls):
             REGISTRY[reg_name] = prop_cls
+            make = prop_cls.create_operator
+
+            def create_operator(self, ctx, in_shapes, in_dtypes):
+                op = make(self, ctx, in_shapes, in_dtypes)
+                cls = type(op)
+                if not getattr(cls.forward, "__b2q_syncs__", False):
+                    cls.forward = _synced(cls.forward)
+                    cls.backward = _synced(cls.backward)
+                return op
+            prop_cls.create_operator = create_operator
             return mx_deco(prop_cls)
         return deco
 else:

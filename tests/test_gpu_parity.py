@@ -378,3 +378,31 @@ def test_int8_export_feeds_an_integer_gemm(T):
     # and the fp32 layer the training graph runs agrees with both within fp32 accumulation error
     fp32 = T.nn.functional.linear(xq, wq).to(T.float64)
     assert float((fp32 - want).abs().max()) <= 1e-5 * scale
+
+
+def test_foreign_dlpack_arrays_and_default_stream_sync(T):
+    """Arrays torch does not own (anything exporting __dlpack__, i.e. what mx.nd hands over) are viewed zero-copy, the
+    kernels go to the legacy default stream, and dlpack.sync_foreign() -- what the MXNet-side wrapper calls before a
+    CustomOp callback returns -- waits for them through b2q_stream_synchronize."""
+    from b200quant import dlpack
+
+    class Foreign(object):
+        def __init__(self, t):
+            self.t = t
+
+        def __dlpack__(self, **kw):
+            return self.t.__dlpack__()
+
+    rng = np.random.default_rng(21)
+    x = (rng.standard_normal((6, 16, 14, 14)) * 2).astype(F)
+    op, ref = make("Quantization_int8_V2", quant_mode="minmax", is_weight=False)
+    xd, yd, ad = dev(T, x), dev(T, np.zeros_like(x)), dev(T, np.ones(1, F))
+    T.cuda.synchronize()
+    dlpack.FOREIGN_DEVICES.clear()
+    op.forward(True, ["write"], [Foreign(xd)], [Foreign(yd)], [Foreign(ad)])
+    assert dlpack.FOREIGN_DEVICES == {xd.device.index}
+    dlpack.sync_foreign()
+    assert not dlpack.FOREIGN_DEVICES
+    yr, ar = np.zeros_like(x), [np.ones(1, F)]
+    ref.forward(True, ["write"], [x], [yr], ar)
+    assert bits_equal(yd.cpu().numpy(), yr) and bits_equal(ad.cpu().numpy(), ar[0])

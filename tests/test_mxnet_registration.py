@@ -64,6 +64,8 @@ for name, cls in op.registered.items():
     prop = cls(**%r.get(name, {}))
     inst = prop.create_operator(None, None, None)
     assert isinstance(inst, CustomOp), name
+    # the engine cannot see the library's launches: forward / backward synchronise before returning
+    assert getattr(type(inst).forward, "__b2q_syncs__", False) and getattr(type(inst).backward, "__b2q_syncs__", False), name
 print(",".join(sorted(op.registered)))
 '''
 

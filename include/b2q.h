@@ -51,7 +51,10 @@ int b2q_stream_synchronize(b2q_ctx* ctx, void* stream);
 /* run-time knobs for benchmarking sweeps: "blocks_per_sm" (grid = SMs x this), "reverse" (QDQ sweep walks
  * descending addresses to reuse what the reduction left in L2), "fast_div" (reciprocal fast path on/off),
  * "peer_reduce_blocks_per_sm" (grid of the max reduction in the peer-memory exchange), "pdl" (programmatic dependent
- * launch between consecutive whole-tensor kernels on/off), "timing" (see b2q_timing_read).
+ * launch between consecutive whole-tensor kernels on/off), "timing" (see b2q_timing_read), "resident" (single-launch
+ * forward for tensors that fit on chip), "peer_mode" (1: ticket-free exchange kernels, 0: the first-generation ones),
+ * "peer_timeout_ms", "host_ste_copy" (host-buffer straight-through backward copied host to host instead of through the
+ * GPU), "dorefa_tanh_max" (DoReFa: element-wise max of |tanh| instead of tanhf(max|w|)).
  * Results never depend on them. */
 int b2q_set_option(b2q_ctx* ctx, const char* key, int value);
 int b2q_get_option(b2q_ctx* ctx, const char* key, int* value);
@@ -118,6 +121,10 @@ int b2q_export_int8_f32(b2q_ctx* ctx, const float* x, int8_t* codes, float* step
 
 /* K5  straight-through backward: in_grad (req) out_grad      quant_ops.py:41-42, GDRQ.py:126        */
 int b2q_ste_bwd_f32(b2q_ctx* ctx, const float* dy, float* dx, int64_t n, int req, void* stream);
+
+/* in_grad[i][:] = 0 for the inputs that get no gradient (symbol/fold_bn_v1_gdrq.py:124-125): a memset on the caller's
+ * stream.                                                                                              */
+int b2q_zero_f32(b2q_ctx* ctx, float* x, int64_t n, void* stream);
 
 /* K6  masked backward, one pass:  dx (req) dy * mask(x, thr[g])
  * mask_mode B2Q_MASK_OPEN   [x > -T][x < T]   clip_grad_quantization_int8.py:61-67
@@ -203,6 +210,12 @@ int b2q_qil_bwd_f32(b2q_ctx* ctx, int variant, const float* x, const float* dy, 
                     const float* p1, float* dp0, float* dp1, int64_t n, int req, int req_p0, int req_p1,
                     void* stream);
 
+/* Exhaustive self tests of the two numerical shortcuts in the second-tier kernels; *failures = number of inputs on which
+ * the shortcut differs from the reference arithmetic (must be 0).  which = 1: code / L by reciprocal + two FMAs versus
+ * IEEE division, every integer |code| <= 4 L, L = 2^nbits - 1, nbits = 1..16.  which = 2: tanhf is odd and monotonic
+ * non-decreasing over all finite positive floats (so max|tanh(w)| == tanhf(max|w|), DoReFa_PY).  Synchronous.     */
+int b2q_selftest(b2q_ctx* ctx, int which, int64_t* failures);
+
 /* ---- multi-tensor: every weight of a network in two launches (forward) / one launch (backward) ---------
  * The weight tensors of a network are ~1% of a step's bytes but, launched one by one (3 launches each), ~7% of its
  * time.  A plan is built once from the (stable) parameter pointers; b2q_multi_weight_quant_fwd_f32 then runs the
@@ -246,6 +259,11 @@ int b2q_multi_weight_ste_bwd_f32(b2q_ctx* ctx, b2q_multi_plan* plan, void* strea
  * of calls; the sequence number itself is kept on the device (so a CUDA graph can replay the pair), the `sequence`
  * argument is informational.  A peer that never arrives makes the kernel trap after ~20 s instead of hanging.   */
 int b2q_peer_mailbox_bytes(void);
+/* The wait for a peer's statistic is bounded by time (option "peer_timeout_ms", default 600 000): when it expires the
+ * sweep uses NaN as the statistic (threshold and output turn NaN), records the sequence number and the first missing
+ * rank in its mailbox and carries on -- the CUDA context stays usable.  b2q_peer_status reads that record (0 = no
+ * timeout so far); it copies device to host and therefore synchronises with the device.                            */
+int b2q_peer_status(b2q_ctx* ctx, const void* own_mailbox, uint32_t* timeout_sequence, uint32_t* timeout_rank);
 int b2q_peer_mailbox_create(b2q_ctx* ctx, void** mailbox, void* ipc_handle_out /* 64 bytes */);
 int b2q_peer_mailbox_open(b2q_ctx* ctx, const void* ipc_handle /* 64 bytes */, void** peer_ptr);
 int b2q_peer_mailbox_close(b2q_ctx* ctx, void* peer_ptr);

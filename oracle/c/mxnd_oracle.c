@@ -61,11 +61,17 @@ static void nd_abs(const float* x, float* y, size_t n) {
     for (ptrdiff_t i = 0; i < (ptrdiff_t)n; ++i) y[i] = fabsf(x[i]);
 }
 
+/* NaN propagates (np.max in quant_oracle.py, torch.max in the shim the golden vectors were generated over): the
+ * number of NaN elements is counted beside the maximum so the result does not depend on the visiting order */
 static float nd_max(const float* x, size_t n) {
     float m = -INFINITY;
-#pragma omp parallel for schedule(static) reduction(max : m)
-    for (ptrdiff_t i = 0; i < (ptrdiff_t)n; ++i) m = x[i] > m ? x[i] : m;
-    return m;
+    long long nans = 0;
+#pragma omp parallel for schedule(static) reduction(max : m) reduction(+ : nans)
+    for (ptrdiff_t i = 0; i < (ptrdiff_t)n; ++i) {
+        nans += (x[i] != x[i]);
+        m = x[i] > m ? x[i] : m;
+    }
+    return nans ? NAN : m;
 }
 
 static float nd_mean(const float* x, size_t n) {
@@ -132,8 +138,12 @@ static void nd_max_rows(const float* x, float* out, size_t rows, size_t cols) {
 #pragma omp parallel for schedule(static)
     for (ptrdiff_t r = 0; r < (ptrdiff_t)rows; ++r) {
         float m = -INFINITY;
-        for (size_t c = 0; c < cols; ++c) m = x[r * cols + c] > m ? x[r * cols + c] : m;
-        out[r] = m;
+        int nans = 0;
+        for (size_t c = 0; c < cols; ++c) {
+            nans |= (x[r * cols + c] != x[r * cols + c]);
+            m = x[r * cols + c] > m ? x[r * cols + c] : m;
+        }
+        out[r] = nans ? NAN : m;
     }
 }
 static void nd_broadcast_rows(const float* v, float* y, size_t rows, size_t cols) {

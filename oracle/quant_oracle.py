@@ -68,6 +68,12 @@ def mx_sub(a, b):
         return (fl(a) - fl(b)).astype(F)
 
 
+def mx_sign(x):
+    """mshadow_op::sign [upstream]: a < 0 ? -1 : (a > 0 ? 1 : 0) -- so sign(0) = 0 and sign(NaN) = 0 (np.sign gives NaN)."""
+    x = fl(x)
+    return np.where(x > 0, F(1), np.where(x < 0, F(-1), F(0))).astype(F)
+
+
 def mx_clip(x, lo, hi):
     x = fl(x)
     lo = F(lo)
@@ -103,6 +109,28 @@ def qdq(x, q):
     """fl(roundf(fl(x/q)) * q) and the integer-valued codes."""
     codes = mx_round(mx_div(x, q))
     return mx_mul(codes, q), codes
+
+
+def clip_by_mode(mode, x, t):
+    """The six clipping expressions of the reference, numbered like include/b2q.h's B2Q_CLIP_*:
+    0 none; 1 mx.nd.clip(x, -t, t) (quant clip_grad...py:48, GDRQ.py:79, fold_bn_v1_gdrq.py:67);
+    2 where(|x| <= t, x, t*sign(x)) (GDRQ.py:109); 3 mx.nd.clip(x, 0, t) (GDRQ.py:202);
+    4 where(x < t, x, t) (PACT.py:125); 5 where(|x| < t, x, t*sign(x)) (PACT.py:193)."""
+    x = fl(x)
+    t = F(t)
+    if mode == 0:
+        return x
+    if mode == 1:
+        return mx_clip(x, -t, t)
+    if mode == 2:
+        return np.where(np.abs(x) <= t, x, mx_mul(t, mx_sign(x))).astype(F)
+    if mode == 3:
+        return mx_clip(x, F(0), t)
+    if mode == 4:
+        return np.where(x < t, x, t).astype(F)
+    if mode == 5:
+        return np.where(np.abs(x) < t, x, mx_mul(t, mx_sign(x))).astype(F)
+    raise ValueError(mode)
 
 
 def assign(dst, req, src):
@@ -389,7 +417,7 @@ class GDRQ_PY(_Op):
         else:                                                              # :88-118
             r, shape = self._grouped_view(data)
             rabs = np.abs(r)
-            rsign = np.sign(r).astype(F)
+            rsign = mx_sign(r)
             if self.fix_alpha is False:
                 threshold = mx_mul(F(self.ktimes), mx_mean(rabs, axis=tuple(range(1, r.ndim))))  # :98-100
                 self._alpha_update(alpha, threshold)
@@ -474,7 +502,7 @@ class PACT_PY(_Op):
 
     def _clip(self, x, gamma):
         if self.two_sided:                                                 # :191-193
-            return np.abs(x) < gamma, mx_mul(gamma, np.sign(x).astype(F))
+            return np.abs(x) < gamma, mx_mul(gamma, mx_sign(x))
         return x < gamma, np.broadcast_to(gamma, x.shape)                  # :125
 
     def forward(self, is_train, req, in_data, out_data, aux):
@@ -494,7 +522,7 @@ class PACT_PY(_Op):
         dx = np.where(cond, dy, F(0)).astype(F)
         dother = np.where(cond, F(0), dy).astype(F)
         if self.two_sided:  # d(gamma_b * sign(x)) / d gamma_b = sign(x)
-            dother = mx_mul(dother, np.sign(x).astype(F))
+            dother = mx_mul(dother, mx_sign(x))
         dgamma = mx_sum(dother).reshape(1)
         self.assign(in_grad[0], req[0], dx)
         self.assign(in_grad[1], req[1], dgamma)
@@ -529,7 +557,7 @@ class DoReFa_PY(_Op):
         # d o / d (2v) = -t / (2v)^2 ; d(2v)/dv = 2
         d2v = mx_sum(mx_mul(g, mx_div(-t, mx_mul(two_v, two_v))))
         dv = mx_mul(F(2), d2v)
-        dt = mx_add(dt, mx_mul(mx_mul((np.abs(t) == v).astype(F), dv), np.sign(t).astype(F)))
+        dt = mx_add(dt, mx_mul(mx_mul((np.abs(t) == v).astype(F), dv), mx_sign(t)))
         dx = mx_mul(dt, mx_sub(F(1), mx_mul(t, t)))
         self.assign(in_grad[0], req[0], dx)
 
@@ -587,7 +615,7 @@ class _QILBase(_Op):
 
     def _transform(self, x, pp, cp, a, b):
         xabs = np.abs(x)
-        sgn = np.sign(x).astype(F)
+        sgn = mx_sign(x)
         inter = ((xabs >= pp).astype(F) * (xabs <= cp).astype(F)).astype(F)
         lin = mx_add(mx_mul(a, xabs), b)
         out = mx_add(mx_mul(sgn, (xabs > cp).astype(F)), mx_mul(mx_mul(sgn, lin), inter))
@@ -667,7 +695,7 @@ class QIL_V3_PY(_QILBase):
         distance = np.exp(ed).astype(F)                                    # :51
         cp = mx_add(pp, distance)                                          # :52
         xabs = np.abs(x)
-        sgn = np.sign(x).astype(F)
+        sgn = mx_sign(x)
         inter = ((xabs >= pp).astype(F) * (xabs <= cp).astype(F)).astype(F)  # :56
         lin = mx_div(mx_sub(xabs, pp), distance)                           # :59
         output = mx_add(mx_mul(sgn, (xabs > cp).astype(F)), mx_mul(mx_mul(sgn, lin), inter))  # :58-59

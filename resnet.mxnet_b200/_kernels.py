@@ -85,12 +85,32 @@ def assign(dst, req, src):
 
 
 def zero_(dst):
-    """in_grad[i][:] = 0 (fold_bn_v1_gdrq.py:124-125)."""
-    import torch
-    if isinstance(dst, torch.Tensor):
-        dst.zero_()
-    else:  # pragma: no cover (MXNet NDArray)
+    """in_grad[i][:] = 0 (fold_bn_v1_gdrq.py:124-125): a memset on the array's stream."""
+    d = as_buffer(dst, write=True)
+    if d.on_device:
+        _lib.context(d.device_id).call("b2q_zero_f32", d.ptr, d.numel, current_stream(d))
+    else:
         dst[:] = 0
+
+
+def scratch_like(ref, n=1, dtype_name="float32"):
+    """Small device scratch array next to ``ref``, allocated by whichever framework owns ``ref``: torch for torch
+    tensors, ``mx.nd.empty(ctx=ref.context)`` for MXNet NDArrays (they have no ``.device``), and for any other DLPack
+    exporter a torch tensor on the same CUDA device (torch only supplies the memory)."""
+    try:
+        import torch
+    except ImportError:  # pragma: no cover
+        torch = None
+    if torch is not None and isinstance(ref, torch.Tensor):
+        return torch.empty(n, dtype=getattr(torch, dtype_name), device=ref.device)
+    if hasattr(ref, "context") and hasattr(ref, "to_dlpack_for_write"):   # mx.nd.NDArray
+        import mxnet as mx
+        return mx.nd.empty((n,), ctx=ref.context, dtype=dtype_name)
+    b = as_buffer(ref)
+    if torch is None:  # pragma: no cover
+        raise _lib.B2QError("cannot allocate scratch memory for %r without torch or mxnet" % type(ref))
+    dev = torch.device("cuda", b.device_id) if b.on_device else torch.device("cpu")
+    return torch.empty(n, dtype=getattr(torch, dtype_name), device=dev)
 
 
 def minmax_quant_fwd(variant, x, y, aux, is_weight, per_channel, is_train, init, ema_decay, req):
@@ -342,8 +362,9 @@ def export_int8(x, thr, qlevel, clip_mode, view=None):
     outer, groups, inner = view if view is not None else (1, 1, xb.numel)
     on_dev, dev = _same_place(xb, tb)
     require_device(on_dev, "export_int8")
-    codes = torch.empty(xb.shape, dtype=torch.int8, device=x.device)
-    steps = torch.empty(groups, dtype=torch.float32, device=x.device)
+    dev = x.device if isinstance(x, torch.Tensor) else torch.device("cuda", xb.device_id)
+    codes = torch.empty(xb.shape, dtype=torch.int8, device=dev)
+    steps = torch.empty(groups, dtype=torch.float32, device=dev)
     _lib.context(dev).call("b2q_export_int8_f32", xb.ptr, codes.data_ptr(), steps.data_ptr(), outer, groups, inner,
                            tb.ptr, _f32(qlevel), int(clip_mode), current_stream(xb))
     return codes, steps

@@ -40,6 +40,9 @@ _CTX_FUNCS = {
     "b2q_qdq_f32": [_P, _P, _L, _L, _L, _P, _P, _F, _I, _I, _I, _P, _P, _P, _F, _P],
     "b2q_export_int8_f32": [_P, _P, _P, _L, _L, _L, _P, _F, _I, _P],
     "b2q_ste_bwd_f32": [_P, _P, _L, _I, _P],
+    "b2q_zero_f32": [_P, _L, _P],
+    "b2q_selftest": [_I, ctypes.POINTER(_L)],
+    "b2q_peer_status": [_P, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)],
     "b2q_mask_bwd_f32": [_P, _P, _P, _L, _L, _L, _P, _F, _I, _I, _P],
     "b2q_minmax_quant_fwd_f32": [_I, _P, _P, _P, _L, _L, _I, _I, _I, _I, _F, _F, _I, _P],
     "b2q_minmax_quant_stat_f32": [_P, _L, _L, _I, _P, _P],

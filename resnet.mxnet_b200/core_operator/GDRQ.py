@@ -39,8 +39,7 @@ class GDRQ_PY(CustomOp):
             x, alpha = in_data[0], aux[0]
             view = K._gdrq_view(tuple(x.shape), self.group_size, False)
             if self._stat is None:
-                import torch
-                self._stat = torch.empty(view[1], dtype=torch.float32, device=x.device)
+                self._stat = K.scratch_like(x, view[1])
             K.meanabs(x, self._stat, view)
             if self.sync is None:   # peer exchange attached but this call is outside its fused case (delay_quant)
                 from ..dist import ThresholdSync

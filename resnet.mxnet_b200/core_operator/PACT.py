@@ -9,8 +9,7 @@ from ..operator import CustomOp, CustomOpProp, py_literal, register
 
 
 def _scratch_like(ref, n=1):
-    import torch
-    return torch.empty(n, dtype=torch.float32, device=ref.device)
+    return K.scratch_like(ref, n)
 
 
 class DoReFa_PY(CustomOp):

@@ -82,6 +82,11 @@ static int* option_slot(b2q_ctx* ctx, const char* key) {
     if (!strcmp(key, "reverse")) return &ctx->reverse;
     if (!strcmp(key, "fast_div")) return &ctx->fast_div;
     if (!strcmp(key, "timing")) return &ctx->timing;
+    if (!strcmp(key, "dorefa_tanh_max")) return &ctx->dorefa_tanh_max;
+    if (!strcmp(key, "host_ste_copy")) return &ctx->host_ste_copy;
+    if (!strcmp(key, "resident")) return &ctx->resident;
+    if (!strcmp(key, "peer_mode")) return &ctx->peer_mode;
+    if (!strcmp(key, "peer_timeout_ms")) return &ctx->peer_timeout_ms;
     return nullptr;
 }
 
@@ -191,6 +196,14 @@ int b2q_ste_bwd_f32(b2q_ctx* ctx, const float* dy, float* dx, int64_t n, int req
     B2Q_REQUIRE(dy && dx && n >= 1, "bad argument");
     if (dy == dx && req != B2Q_REQ_ADD) return 0;  // in-place identity
     return launch_bwd_mask<0>(ctx, nullptr, dy, dx, 1, 1, n, nullptr, 0.f, req, (cudaStream_t)stream);
+}
+
+int b2q_zero_f32(b2q_ctx* ctx, float* x, int64_t n, void* stream) {
+    B2Q_CTX(ctx);
+    B2Q_REQUIRE(x != nullptr && n >= 0, "bad argument");
+    if (n == 0) return 0;
+    B2Q_CHECK_CUDA(cudaMemsetAsync(x, 0, sizeof(float) * (size_t)n, (cudaStream_t)stream));
+    return 0;
 }
 
 int b2q_mask_bwd_f32(b2q_ctx* ctx, const float* x, const float* dy, float* dx, int64_t outer, int64_t groups,

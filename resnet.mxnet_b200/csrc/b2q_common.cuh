@@ -32,7 +32,8 @@ struct b2q_slot {
 #define B2Q_KIND_BWD_STE 3
 #define B2Q_KIND_BWD_MASK 4
 #define B2Q_KIND_OTHER 5
-#define B2Q_NKINDS 6
+#define B2Q_KIND_FUSED_FWD 6   // single-launch forward of a resident tensor (12 B/element algorithmic)
+#define B2Q_NKINDS 7
 
 struct b2q_timing_rec {
     int kind;
@@ -57,9 +58,16 @@ struct b2q_ctx {
     int reverse = 1;                 // QDQ sweep walks descending addresses when the tensor exceeds reverse_min_bytes
     long long reverse_min_bytes = 96ll << 20;
     int fast_div = 1;
+    int dorefa_tanh_max = 0;         // 1: DoReFa takes max|tanh(w)| element-wise instead of tanhf(max|w|) (same float)
+    int host_ste_copy = 1;           // host-buffer straight-through backward: copy host to host, no PCIe round trip
+    int resident = 1;                // single-launch forward for tensors that fit on chip (shared memory + L2)
+    long long resident_max_bytes = 72ll << 20;
+    int peer_mode = 1;               // 1: ticket-free reduction, the sweep's first block publishes to the peers; 0: r1 kernels
+    int peer_timeout_ms = 600000;    // how long a sweep waits for a peer's statistic before it gives up (NaN output + flag)
     int timing = 0;
     std::vector<b2q_timing_rec> recs;
     std::vector<cudaEvent_t> event_pool;
+    bool rows_cta_optin[2] = {false, false};   // > 48 KB dynamic shared memory enabled for rows_cta_kernel<max / sum>
     void* host_state = nullptr;     // staging buffers + streams of the host-buffer entry points (b2q_host.cu)
 };
 
@@ -113,6 +121,28 @@ int b2q_host_release(b2q_ctx* ctx);  // b2q_host.cu
 // previous kernel of the stream drains its last wave (every kernel launched this way starts with b2q_pdl_sync(), which
 // waits for the predecessor to complete and flush before touching memory, then lets its own successor do the same).
 // It hides the launch latency and prologue of ~300 back-to-back kernels per step; ordering and results are unchanged.
+template <typename... KArgs, typename... Args>
+static inline void b2q_launch_smem(b2q_ctx* ctx, void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem,
+                                   cudaStream_t st, const Args&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(block, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr = {};
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = ctx->pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, args...);
+    if (e == cudaErrorNotSupported && cfg.numAttrs) {
+        (void)cudaGetLastError();
+        ctx->pdl = 0;
+        cfg.numAttrs = 0;
+        cudaLaunchKernelEx(&cfg, kernel, args...);
+    }
+}
+
 template <typename... KArgs, typename... Args>
 static inline void b2q_launch(b2q_ctx* ctx, void (*kernel)(KArgs...), unsigned grid, unsigned block,
                               cudaStream_t st, const Args&... args) {
@@ -191,6 +221,44 @@ __device__ __forceinline__ void b2q_pdl_sync() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
+// ---- bulk asynchronous copies (TMA engine, no tensor map) + mbarrier completion ------------------------------------------
+// cp.async.bulk moves a contiguous, 16-byte aligned range global -> shared without occupying the threads or their
+// registers; the mbarrier it signals counts the bytes that have landed.  Used where a tile is read more than once from
+// shared memory (weight rows: statistic pass + QDQ pass; the resident single-launch forward).
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_fence_init() {   // make the initialised barrier visible to the async proxy
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 // "Last block finishes" ticket: a release atomic (+ an acquire fence in the one block that draws `last`) instead of
 // __threadfence() + atomicAdd.  __threadfence() is a sequentially consistent fence that also invalidates the SM's whole
 // L1 (MEMBAR.SC.GPU + CCTL.IVALL) in every block; the release orders the block's earlier writes (partials, atomicMax)
@@ -203,9 +271,25 @@ __device__ __forceinline__ unsigned int b2q_take_ticket(unsigned int* ticket, un
     return t;
 }
 
+// max / min that PROPAGATE NaN (PTX max.NaN / min.NaN, one FMNMX like fmaxf / fminf, which drop it).  The reference's
+// comparison-based mx.nd.clip passes a NaN input through and max(|x|) of a tensor holding a NaN is NaN (NumPy oracle
+// and the torch-backed shim agree): a diverged network must produce NaN, not be silently quantised.  On the fast QDQ
+// path a NaN that survives the clip fails the safety test, so the word is redone with the reference arithmetic.
+__device__ __forceinline__ float fmax_nan(float a, float b) {
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+
+__device__ __forceinline__ float fmin_nan(float a, float b) {
+    float r;
+    asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    for (int o = 16; o > 0; o >>= 1) v = fmax_nan(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
 
@@ -252,6 +336,7 @@ struct UpdateArgs {
     float* scale_out;  // [groups] threshold to scale with
     float* clip_out;   // [groups] threshold to clip with (may be null)
     float* stat_out;   // [groups] raw statistic (may be null)
+    unsigned int* seq_counter;   // peer exchange: call counter advanced once per reduction (deferred kernels only)
 };
 
 // Pure part of the update: from the old aux value and the reduced statistic to (batch threshold, new aux).

@@ -10,8 +10,12 @@
 // waits (stream-side, never the host) for the calls whose space it is about to overwrite.  Every call returns after
 // enqueueing; b2q_host_sync() waits for all of them.  Calls that touch the same host aux array must be separated by
 // b2q_host_sync().
+#include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "b2q_common.cuh"
@@ -36,7 +40,87 @@ struct HostStage {         // what one call works on
     cudaEvent_t h2d_done, comp_done, d2h_done;
 };
 
+// Host-to-host copies (the straight-through backward of a host caller: dx <- dy, both in host memory).  Moving the
+// bytes to the GPU and back would spend two PCIe transfers on an identity; a small pool of host threads copies them
+// instead -- no arithmetic happens on the CPU -- while the PCIe links keep serving the forward traffic.  A job may carry
+// CUDA events to wait for (device-to-host copies still landing in its source).
+struct CopyJob {
+    char* dst;
+    const char* src;
+    size_t bytes;
+    cudaEvent_t wait;     // may be null
+};
+
+class HostCopyPool {
+  public:
+    explicit HostCopyPool(int device) : device_(device) {
+        unsigned n = std::thread::hardware_concurrency();
+        if (const char* e = std::getenv("B2Q_HOST_COPY_THREADS")) n = (unsigned)std::atoi(e);
+        if (n < 1) n = 1;
+        if (n > 16) n = 16;
+        for (unsigned i = 0; i < n; ++i) workers_.emplace_back([this] { run(); });
+    }
+    ~HostCopyPool() {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (std::thread& t : workers_) t.join();
+    }
+    void submit(void* dst, const void* src, size_t bytes, cudaEvent_t wait) {
+        const size_t chunk = 8u << 20;
+        std::lock_guard<std::mutex> lk(m_);
+        for (size_t off = 0; off < bytes; off += chunk) {
+            q_.push_back({(char*)dst + off, (const char*)src + off, bytes - off < chunk ? bytes - off : chunk, wait});
+            ++pending_;
+        }
+        cv_.notify_all();
+    }
+    void wait() {
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [this] { return pending_ == 0; });
+    }
+    int threads() const { return (int)workers_.size(); }
+
+  private:
+    void run() {
+        cudaSetDevice(device_);
+        for (;;) {
+            CopyJob j;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [this] { return stop_ || !q_.empty(); });
+                if (q_.empty()) return;
+                j = q_.front();
+                q_.pop_front();
+            }
+            if (j.wait) cudaEventSynchronize(j.wait);
+            std::memcpy(j.dst, j.src, j.bytes);
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                if (--pending_ == 0) done_.notify_all();
+            }
+        }
+    }
+    int device_;
+    std::vector<std::thread> workers_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    std::deque<CopyJob> q_;
+    size_t pending_ = 0;
+    bool stop_ = false;
+};
+
+struct PendingHostWrite {   // a device-to-host copy that may still be landing in [ptr, ptr + bytes)
+    const char* ptr;
+    size_t bytes;
+    cudaEvent_t done;
+};
+
 struct HostState {
+    HostCopyPool* pool = nullptr;
+    std::vector<PendingHostWrite> landing;
     float* a = nullptr;    // ring: staged inputs
     float* b = nullptr;    // ring: second input (dy) or output
     float* c = nullptr;    // ring: output of two-input ops (allocated on first use)
@@ -71,10 +155,23 @@ static int host_init(b2q_ctx* ctx) {
     return 0;
 }
 
+static void note_landing(HostState* hs, const void* ptr, size_t bytes, cudaEvent_t done) {
+    if (hs->landing.size() > 256) {   // drop the copies that have finished
+        std::vector<PendingHostWrite> keep;
+        for (const PendingHostWrite& w : hs->landing)
+            if (cudaEventQuery(w.done) == cudaErrorNotReady) keep.push_back(w);
+        (void)cudaGetLastError();
+        hs->landing.swap(keep);
+    }
+    hs->landing.push_back({(const char*)ptr, bytes, done});
+}
+
 static int host_sync_all(HostState* hs) {
     B2Q_CHECK_CUDA(cudaStreamSynchronize(hs->h2d));
     B2Q_CHECK_CUDA(cudaStreamSynchronize(hs->comp));
     B2Q_CHECK_CUDA(cudaStreamSynchronize(hs->d2h));
+    if (hs->pool) hs->pool->wait();
+    hs->landing.clear();
     for (HostSeg& s : hs->inflight) hs->events.push_back(s.done);
     hs->inflight.clear();
     hs->head = 0;
@@ -158,6 +255,7 @@ int b2q_host_release(b2q_ctx* ctx) {
     if (hs->h2d) { cudaStreamSynchronize(hs->h2d); cudaStreamDestroy(hs->h2d); }
     if (hs->comp) { cudaStreamSynchronize(hs->comp); cudaStreamDestroy(hs->comp); }
     if (hs->d2h) { cudaStreamSynchronize(hs->d2h); cudaStreamDestroy(hs->d2h); }
+    if (hs->pool) { hs->pool->wait(); delete hs->pool; hs->pool = nullptr; }
     cudaFree(hs->a); cudaFree(hs->b); cudaFree(hs->c); cudaFree(hs->aux);
     for (HostSeg& s : hs->inflight) cudaEventDestroy(s.done);
     for (cudaEvent_t e : hs->events) cudaEventDestroy(e);
@@ -199,12 +297,33 @@ int b2q_minmax_quant_fwd_host_f32(b2q_ctx* ctx, int variant, const float* host_x
     hs->events.push_back(e);
     B2Q_CHECK_CUDA(cudaMemcpyAsync(host_y, s.b, sizeof(float) * n, cudaMemcpyDeviceToHost, hs->d2h));
     B2Q_CHECK_CUDA(cudaMemcpyAsync(host_aux, s.aux, sizeof(float) * naux, cudaMemcpyDeviceToHost, hs->d2h));
-    return finish(hs, s);
+    rc = finish(hs, s);
+    note_landing(hs, host_y, sizeof(float) * n, s.d2h_done);
+    return rc;
 }
 
 int b2q_ste_bwd_host_f32(b2q_ctx* ctx, const float* host_dy, float* host_dx, int64_t n) {
     B2Q_CTX(ctx);
     B2Q_REQUIRE(host_dy && host_dx && n >= 1, "bad argument");
+    if (host_dy == host_dx) return 0;
+    if (ctx->host_ste_copy) {
+        // dx <- dy between two host buffers: an identity has no business crossing PCIe twice.  Copied by the host copy
+        // pool (asynchronous like every host-buffer call; b2q_host_sync() waits for it), after any device-to-host copy
+        // that is still landing in dy (e.g. dy is the output of an earlier forward call).
+        int rc = host_init(ctx);
+        if (rc) return rc;
+        HostState* hs = host_state(ctx);
+        if (!hs->pool) hs->pool = new HostCopyPool(ctx->device);
+        const char* lo = (const char*)host_dy;
+        const char* hi = lo + sizeof(float) * (size_t)n;
+        cudaEvent_t wait = nullptr;
+        for (size_t i = hs->landing.size(); i-- > 0;) {   // newest first: events on the d2h stream complete in order
+            const PendingHostWrite& w = hs->landing[i];
+            if (w.ptr < hi && lo < w.ptr + w.bytes) { wait = w.done; break; }
+        }
+        hs->pool->submit(host_dx, host_dy, sizeof(float) * (size_t)n, wait);
+        return 0;
+    }
     HostStage s;
     int rc = take_stage(ctx, n, false, &s);
     if (rc) return rc;

@@ -77,10 +77,10 @@ mt_absmax_kernel(const MtTensor* __restrict__ tensors, const MtItem* __restrict_
             const long long n4 = (it.b - it.a) >> 2;
             for (long long i = threadIdx.x; i < n4; i += blockDim.x) {
                 const float4 v = p[i];
-                m = fmaxf(fmaxf(m, fabsf(v.x)), fmaxf(fabsf(v.y), fmaxf(fabsf(v.z), fabsf(v.w))));
+                m = fmax_nan(fmax_nan(m, fabsf(v.x)), fmax_nan(fabsf(v.y), fmax_nan(fabsf(v.z), fabsf(v.w))));
             }
         } else {
-            for (long long i = it.a + threadIdx.x; i < it.b; i += blockDim.x) m = fmaxf(m, fabsf(base[i]));
+            for (long long i = it.a + threadIdx.x; i < it.b; i += blockDim.x) m = fmax_nan(m, fabsf(base[i]));
         }
         const float r = (float)block_reduce<true>((double)m, smem);
         if (threadIdx.x == 0) atomicMax(stat + t.gbase + it.group, tag | __float_as_uint(r));
@@ -89,7 +89,7 @@ mt_absmax_kernel(const MtTensor* __restrict__ tensors, const MtItem* __restrict_
         for (long long row = it.a + wid; row < it.b; row += nw) {
             const float* p = t.x + row * t.cols;
             float m = 0.f;
-            for (long long c = lane; c < t.cols; c += 32) m = fmaxf(m, fabsf(p[c]));
+            for (long long c = lane; c < t.cols; c += 32) m = fmax_nan(m, fabsf(p[c]));
             m = warp_max(m);
             if (lane == 0) stat[t.gbase + row] = tag | __float_as_uint(m);
         }

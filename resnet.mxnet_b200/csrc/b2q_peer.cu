@@ -41,6 +41,8 @@ struct PeerState {
                                     // every block of that kernel has read it (they read it before taking a ticket)
     unsigned int seq;               // sequence number of the call in flight, for the sweep
     unsigned long long local_max;   // (seq << 32 | bits): running local max|x| of the call in flight
+    unsigned int timeout_seq;       // != 0: a sweep gave up waiting for a peer at this sequence number (its output is NaN)
+    unsigned int timeout_rank;      // the first rank whose statistic was missing
 };
 
 struct PeerBoxes {
@@ -162,7 +164,12 @@ __device__ __forceinline__ float peer_gather(const PeerBoxes& pb) {
         while ((unsigned int)(m >> 32) != seq) {
             __nanosleep(64 + 8 * (threadIdx.x >> 5));
             m = ld_sys_u64(p);
-            if (++spins > B2Q_PEER_SPIN_LIMIT) __trap();   // a peer never arrived: fail loudly instead of hanging
+            if (++spins > B2Q_PEER_SPIN_LIMIT) {           // a peer never arrived (~20 s): NaN statistic + flag, no trap
+                pb.state->timeout_seq = seq;
+                pb.state->timeout_rank = (unsigned int)lane;
+                m = ((unsigned long long)seq << 32) | 0x7fc00000ull;
+                break;
+            }
         }
         v = __uint_as_float((unsigned int)(m & 0xffffffffull));
     }
@@ -233,9 +240,168 @@ qdq_peer_kernel(const float* __restrict__ x, float* __restrict__ y, FlatSplit sp
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// peer_mode 1 (default): no ticket chain at all.
+//   kernel 1  the ordinary deferred reduction of the single-GPU forward (reduce_flat_kernel<.., FINALIZE=false>: one tagged
+//             atomicMax per block, or fp64 partial sums; block 0 snapshots the old aux and advances the call counter).
+//   kernel 2  qdq_peer2_kernel: its blocks are resident behind the reduction (programmatic dependent launch) with their
+//             first tile already requested.  Block 0 reads the reduced statistic (max: the tagged word; mean: combines
+//             the partials in a fixed order) and stores (sequence << 32 | bits) into every rank's mailbox -- one lane
+//             per destination, 8-byte system-scope stores over NVLink.  In every block warp 0 alone looks the statistic up
+//             (the SM's cached line, else the mailbox: one lane per rank) and hands it to the block through shared
+//             memory, so the mailbox line sees one poller per block instead of one per warp.
+// The wait is bounded by TIME (option peer_timeout_ms, default 10 minutes, %globaltimer): on expiry the sweep records
+// (sequence, missing rank) in the mailbox state, uses NaN as the statistic -- the output and the threshold turn NaN,
+// loudly -- and the context stays alive; b2q_peer_status() reports it to the host.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ float peer_gather_warp0(const PeerBoxes& pb, unsigned int seq, unsigned long long timeout_ns) {
+    // called by warp 0 of a block (all 32 lanes)
+    unsigned int smid;
+    asm("mov.u32 %0, %%smid;" : "=r"(smid));
+    unsigned long long* mine = pb.resolved + (size_t)(smid % B2Q_PEER_MAX_SMS) * 16;   // 128 bytes apart
+    unsigned long long w;
+    asm volatile("ld.global.ca.u64 %0, [%1];" : "=l"(w) : "l"(mine) : "memory");
+    if ((unsigned int)(w >> 32) == seq) return __uint_as_float((unsigned int)(w & 0xffffffffull));   // warp-uniform
+    const int lane = threadIdx.x & 31;
+    float v = 0.f;
+    bool late = false;
+    if (lane < pb.world) {
+        const unsigned long long* p = pb.box[pb.rank] + (size_t)(seq & 1u) * B2Q_PEER_MAX_RANKS + lane;
+        unsigned long long m = ld_sys_u64(p);
+        if ((unsigned int)(m >> 32) != seq) {
+            const unsigned long long t0 = global_ns();
+            unsigned int ns = 32;
+            while (true) {
+                __nanosleep(ns);
+                m = ld_sys_u64(p);
+                if ((unsigned int)(m >> 32) == seq) break;
+                if (ns < 1024) ns += ns;                       // back off: a peer that is late is usually very late
+                if (global_ns() - t0 > timeout_ns) { late = true; break; }
+            }
+        }
+        v = late ? __int_as_float(0x7fc00000) : __uint_as_float((unsigned int)(m & 0xffffffffull));
+    }
+    const unsigned int late_mask = __ballot_sync(0xffffffffu, late);
+    v = warp_max(v);                                           // NaN-propagating
+    if (late_mask) {
+        if (lane == 0) {
+            pb.state->timeout_seq = seq;
+            pb.state->timeout_rank = (unsigned int)(__ffs(late_mask) - 1);
+        }
+        return v;   // NaN; not cached, so that every block reports the same
+    }
+    if (lane == 0) *mine = ((unsigned long long)seq << 32) | __float_as_uint(v);
+    return v;
+}
+
+template <int CLIP, int UNROLL, int LDPOL, int STPOL>
+__global__ void __launch_bounds__(B2Q_THREADS)
+qdq_peer2_kernel(const float* __restrict__ x, float* __restrict__ y, FlatSplit sp, PeerBoxes pb, b2q_slot* slot,
+                 UpdateArgs u, float qlevel, int fast, int reverse, int clip_with_fresh, int is_max, int n_partials,
+                 float count, unsigned long long timeout_ns) {
+    __shared__ float s_stat;
+    __shared__ double s_red[32];
+    const float* xb = x + sp.head;
+    float* yb = y + sp.head;
+    const int64_t tile = (int64_t)B2Q_THREADS * UNROLL;
+    const int64_t ntiles = (sp.n8 + tile - 1) / tile;
+    f8 v[UNROLL];
+    int64_t tt = blockIdx.x;
+    {   // first tile: requested before the dependency wait (the reduction in front of us only reads x)
+        const int64_t t = reverse ? (ntiles - 1 - tt) : tt;
+        const int64_t base = t * tile + threadIdx.x;
+#pragma unroll
+        for (int k = 0; k < UNROLL; ++k) {
+            const int64_t i = base + (int64_t)k * B2Q_THREADS;
+            if (tt < ntiles && i < sp.n8) v[k] = ld_f8<LDPOL>(xb + 8 * i);
+        }
+    }
+    b2q_pdl_sync();
+    const unsigned int seq = pb.state->seq;   // advanced by this call's reduction (block 0), stable during this kernel
+    if (blockIdx.x == 0) {   // publish this rank's statistic to every rank (own mailbox included)
+        float mine;
+        if (is_max) {
+            const unsigned long long word = slot->max64;
+            mine = __uint_as_float((unsigned int)(word & 0xffffffffull));
+            if (threadIdx.x == 0) slot->epoch = (unsigned int)(word >> 32);   // consume the tag
+        } else {
+            double acc = 0.0;
+            for (int i = threadIdx.x; i < n_partials; i += blockDim.x) acc += slot->partial[i];
+            const double tot = block_reduce<false>(acc, s_red);
+            if (threadIdx.x == 0) s_stat = __fdiv_rn((float)tot, count);
+            __syncthreads();
+            mine = s_stat;
+            __syncthreads();
+        }
+        if ((int)threadIdx.x < pb.world) {
+            const unsigned long long word = ((unsigned long long)seq << 32) | __float_as_uint(mine);
+            st_sys_u64(pb.box[threadIdx.x] + (size_t)(seq & 1u) * B2Q_PEER_MAX_RANKS + pb.rank, word);
+        }
+        if (threadIdx.x == 0) pb.state->done = seq;   // keeps the r1 kernels' counter (peer_mode 0) in step
+    }
+    if (threadIdx.x < 32) {
+        const float g = peer_gather_warp0(pb, seq, timeout_ns);
+        if (threadIdx.x == 0) s_stat = g;
+    }
+    __syncthreads();
+    const float stat = s_stat;
+    const float a_old = slot->scale[0];
+    float fresh, next;
+    compute_update(u.mode, u.p0, u.p1, a_old, stat, fresh, next);
+    const float T = next;
+    const float Tc = clip_with_fresh ? fresh : T;   // fold_bn_v1_gdrq.py:67 clips with the batch threshold
+    if (blockIdx.x == 0 && threadIdx.x == 0) u.aux[0] = next;
+    const QScale s = make_qscale(T, qlevel, fast != 0 && !(CLIP != B2Q_CLIP_NONE && !(Tc >= 0.f)));
+    for (; tt < ntiles; tt += gridDim.x) {
+        const int64_t t = reverse ? (ntiles - 1 - tt) : tt;
+        const int64_t base = t * tile + threadIdx.x;
+        if (tt != (int64_t)blockIdx.x) {
+#pragma unroll
+            for (int k = 0; k < UNROLL; ++k) {
+                const int64_t i = base + (int64_t)k * B2Q_THREADS;
+                if (i < sp.n8) v[k] = ld_f8<LDPOL>(xb + 8 * i);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < UNROLL; ++k) {
+            const int64_t i = base + (int64_t)k * B2Q_THREADS;
+            if (i < sp.n8) {
+                f8 o;
+                qdq8<CLIP>(v[k], o, Tc, s);
+                st_f8<STPOL>(yb + 8 * i, o);
+            }
+        }
+    }
+    if (blockIdx.x == 0) {
+        const int64_t tid = threadIdx.x;
+        int64_t idx = -1;
+        if (tid < sp.head) idx = tid;
+        else if (tid - sp.head < sp.tail) idx = sp.head + 8 * sp.n8 + (tid - sp.head);
+        if (idx >= 0) {
+            y[idx] = __fmul_rn(quant_code_exact(clip_value(CLIP, x[idx], Tc), s.q), s.q);
+        }
+    }
+}
+
 extern "C" {
 
 int b2q_peer_mailbox_bytes(void) { return B2Q_PEER_BYTES; }
+
+int b2q_peer_status(b2q_ctx* ctx, const void* own_mailbox, uint32_t* timeout_sequence, uint32_t* timeout_rank) {
+    B2Q_CTX(ctx);
+    B2Q_REQUIRE(own_mailbox && timeout_sequence, "null argument");
+    PeerState st;
+    B2Q_CHECK_CUDA(cudaMemcpy(&st, (const char*)own_mailbox + B2Q_PEER_BOX_BYTES, sizeof(st), cudaMemcpyDeviceToHost));
+    *timeout_sequence = st.timeout_seq;
+    if (timeout_rank) *timeout_rank = st.timeout_rank;
+    return 0;
+}
 
 int b2q_peer_mailbox_create(b2q_ctx* ctx, void** mailbox, void* ipc_handle_out) {
     B2Q_CTX(ctx);
@@ -296,6 +462,34 @@ static int peer_quant_fwd(b2q_ctx* ctx, bool is_max, int upd_mode, float p0, flo
     static_assert(sizeof(PeerState) <= B2Q_PEER_STATE_BYTES, "mailbox state area");
     pb.resolved = (unsigned long long*)((char*)mailboxes[rank] + B2Q_PEER_BOX_BYTES + B2Q_PEER_STATE_BYTES);
     b2q_slot* slot = b2q_take_slot(ctx);
+    if (ctx->peer_mode == 1) {
+        UpdateArgs ur;
+        memset(&ur, 0, sizeof(ur));
+        ur.aux = aux;                       // the deferred reduction snapshots the old threshold into slot->scale[0]
+        ur.seq_counter = &pb.state->seq;
+        int np = 0;
+        int rc = is_max ? launch_reduce_deferred<true>(ctx, slot, x, n, ur, st, &np)
+                        : launch_reduce_deferred<false>(ctx, slot, x, n, ur, st, &np);
+        if (rc) return rc;
+        B2Q_REQUIRE(np > 0, "peer path needs equally aligned float32 buffers");
+        UpdateArgs u;
+        memset(&u, 0, sizeof(u));
+        u.mode = upd_mode;
+        u.write_aux = 1; u.use_aux_as_scale = 1; u.p0 = p0; u.p1 = p1; u.aux = aux;
+        const int64_t grid = b2q_flat_grid(ctx, sp.n8, B2Q_QDQ_UNROLL);
+        const int rev = (ctx->reverse && n * 4 > ctx->reverse_min_bytes) ? 1 : 0;
+        const bool stream_out = n * 4 > B2Q_STREAM_BYTES;
+        const unsigned long long timeout_ns = (unsigned long long)(ctx->peer_timeout_ms > 0 ? ctx->peer_timeout_ms : 1) * 1000000ull;
+        b2q_timed_launch tl(ctx, B2Q_KIND_QDQ_HOT, 8.0 * (double)n, st);
+#define B2Q_PEER2_SWEEP(C, S) b2q_launch(ctx, qdq_peer2_kernel<C, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, S>, (unsigned)grid, B2Q_THREADS, st, \
+            x, y, sp, pb, slot, u, qlevel, ctx->fast_div, rev, clip_with_fresh, is_max ? 1 : 0, np, (float)n, timeout_ns)
+#define B2Q_PEER2_SWEEP_S(C) do { if (stream_out) B2Q_PEER2_SWEEP(C, 1); else B2Q_PEER2_SWEEP(C, B2Q_QDQ_STPOL); } while (0)
+        if (clip_mode == B2Q_CLIP_SYM) B2Q_PEER2_SWEEP_S(B2Q_CLIP_SYM); else B2Q_PEER2_SWEEP_S(B2Q_CLIP_NONE);
+#undef B2Q_PEER2_SWEEP_S
+#undef B2Q_PEER2_SWEEP
+        B2Q_LAUNCH_CHECK(ctx);
+        return 0;
+    }
     {
         const int64_t grid = b2q_flat_grid(ctx, sp.n8, B2Q_REDUCE_UNROLL, is_max ? ctx->peer_reduce_blocks_per_sm : ctx->reduce_blocks_per_sm);
         b2q_timed_launch tl(ctx, B2Q_KIND_REDUCE_FLAT, 4.0 * (double)n, st);

@@ -82,13 +82,15 @@ __device__ __forceinline__ float clip_value(int clip, float x, float T) {
 }
 
 // Clip on the fast path: min/max forms that equal the reference's comparison-based clips for non-NaN inputs and a
-// non-negative threshold (NaN inputs fail the safety test and are redone exactly; the caller disables the fast path
-// when the threshold is negative).
+// non-negative threshold.  The NaN-PROPAGATING min/max are used (fminf/fmaxf would turn a NaN input into -T or 0), so a
+// NaN input reaches the safety test, fails it, and the word is redone with clip_value + the reference arithmetic
+// (mx.nd.clip passes NaN through; where(|x|<=a, x, a*sign(x)) gives a*0).  The caller disables the fast path when the
+// threshold is negative.
 template <int CLIP>
 __device__ __forceinline__ float clip_fast(float x, float T) {
-    if (CLIP == B2Q_CLIP_SYM || CLIP == B2Q_CLIP_WHERE_LE || CLIP == B2Q_CLIP_WHERE_LT) return fminf(fmaxf(x, -T), T);
-    if (CLIP == B2Q_CLIP_ZERO_T) return fminf(fmaxf(x, 0.f), T);
-    if (CLIP == B2Q_CLIP_PACT) return fminf(x, T);
+    if (CLIP == B2Q_CLIP_SYM || CLIP == B2Q_CLIP_WHERE_LE || CLIP == B2Q_CLIP_WHERE_LT) return fmin_nan(fmax_nan(x, -T), T);
+    if (CLIP == B2Q_CLIP_ZERO_T) return fmin_nan(fmax_nan(x, 0.f), T);
+    if (CLIP == B2Q_CLIP_PACT) return fmin_nan(x, T);
     return x;
 }
 
@@ -290,23 +292,27 @@ qdq_seg_hot_kernel(const float* __restrict__ x, float* __restrict__ y, SegPlan p
     const float Tc = a.clip_thr ? __ldg(a.clip_thr + pc.g) : T;
     const bool needs_pos = (CLIP != B2Q_CLIP_NONE && CLIP != B2Q_CLIP_PACT);
     const QScale s = make_qscale(T, a.qlevel, a.fast != 0 && !(needs_pos && !(Tc >= 0.f)));
-    for (int64_t o = pc.o0; o < pc.o1; ++o) {
-        const int64_t off = (o * pl.groups + pc.g) * pl.inner;
-        const float* xb = x + off;
-        float* yb = y + off;
-        const int64_t end = pc.i1 >> 3;
-        for (int64_t i0 = (pc.i0 >> 3) + threadIdx.x; i0 < end; i0 += 2 * (int64_t)blockDim.x) {
-            const int64_t i1 = i0 + blockDim.x;
-            f8 v0, v1;
-            v0 = ld_f8<B2Q_QDQ_LDPOL>(xb + 8 * i0);
-            if (i1 < end) v1 = ld_f8<B2Q_QDQ_LDPOL>(xb + 8 * i1);
-            f8 r;
-            qdq8<CLIP>(v0, r, Tc, s);
-            st_f8<1>(yb + 8 * i0, r);
-            if (i1 < end) {
-                qdq8<CLIP>(v1, r, Tc, s);
-                st_f8<1>(yb + 8 * i1, r);
-            }
+    // the piece's (row, word) space flattened into one index, two 256-bit words in flight per thread
+    const unsigned wpr = (unsigned)((pc.i1 - pc.i0) >> 3);
+    const unsigned total = (unsigned)(pc.o1 - pc.o0) * wpr;
+    for (unsigned w0 = threadIdx.x; w0 < total; w0 += 2 * blockDim.x) {
+        const unsigned w1 = w0 + blockDim.x;
+        const unsigned o0 = w0 / wpr, i0 = w0 - o0 * wpr;
+        const int64_t off0 = ((pc.o0 + o0) * pl.groups + pc.g) * pl.inner + pc.i0 + 8 * (int64_t)i0;
+        int64_t off1 = 0;
+        f8 v0, v1;
+        v0 = ld_f8<B2Q_QDQ_LDPOL>(x + off0);
+        if (w1 < total) {
+            const unsigned o1 = w1 / wpr, i1 = w1 - o1 * wpr;
+            off1 = ((pc.o0 + o1) * pl.groups + pc.g) * pl.inner + pc.i0 + 8 * (int64_t)i1;
+            v1 = ld_f8<B2Q_QDQ_LDPOL>(x + off1);
+        }
+        f8 r;
+        qdq8<CLIP>(v0, r, Tc, s);
+        st_f8<1>(y + off0, r);
+        if (w1 < total) {
+            qdq8<CLIP>(v1, r, Tc, s);
+            st_f8<1>(y + off1, r);
         }
     }
 }
@@ -462,13 +468,123 @@ rows_fused_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t ro
     }
 }
 
+// Long rows (1024 <= inner <= B2Q_ROWS_CTA_MAX_INNER, e.g. 512x512x3x3: 4608 per out-channel): one CTA per row.  The
+// row is staged ONCE in shared memory -- by a single bulk asynchronous copy (TMA engine, mbarrier completion) when it is
+// 16-byte aligned, by cooperative loads otherwise -- and both passes read it from there, so every weight byte crosses
+// L2 once and a 512-row tensor spreads over all SMs instead of 64 eight-warp blocks streaming 18 KB per warp twice.
+#define B2Q_ROWS_CTA_MIN_INNER 1024
+#define B2Q_ROWS_CTA_MAX_INNER 49152   // 192 KB of dynamic shared memory (opt-in above 48 KB)
+
+template <bool IS_MAX>
+__global__ void __launch_bounds__(B2Q_THREADS)
+rows_cta_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t rows, int64_t inner, Prescale ps,
+                FoldBias fb, UpdateArgs u, QdqArgs a, int clip_with_fresh) {
+    extern __shared__ __align__(128) float s_row[];
+    __shared__ double s_red[32];
+    __shared__ float s_stat;
+    __shared__ __align__(8) unsigned long long s_bar;
+    b2q_pdl_sync();
+    const int64_t row = blockIdx.x;
+    const float* xb = x + row * inner;
+    float* yb = y + row * inner;
+    const int n = (int)inner;
+    const bool bulk = ((((uintptr_t)xb) & 15) == 0) && ((n & 3) == 0);
+    if (bulk) {
+        if (threadIdx.x == 0) {
+            mbar_init(&s_bar, 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&s_bar, (unsigned)n * 4u);
+            bulk_g2s(s_row, xb, (unsigned)n * 4u, &s_bar);
+        }
+        mbar_wait(&s_bar, 0);
+    } else {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) s_row[i] = xb[i];
+        __syncthreads();
+    }
+    const float f = ps.gamma ? prescale_factor(ps, row) : 1.f;
+    double acc = 0.0;
+    float m = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {   // consecutive threads, consecutive words: conflict free
+        float v = s_row[i];
+        if (ps.gamma) {
+            v = __fmul_rn(v, f);
+            s_row[i] = v;                                  // the second pass reads the folded weight
+        }
+        acc1<IS_MAX>(acc, m, v);
+    }
+    const double tot = block_reduce<IS_MAX>(IS_MAX ? (double)m : acc, s_red);
+    if (threadIdx.x == 0) s_stat = IS_MAX ? (float)tot : __fdiv_rn((float)tot, (float)inner);
+    __syncthreads();
+    const float stat = s_stat;
+    const float a_old = u.aux ? u.aux[row] : 0.f;
+    float fresh, next;
+    compute_update(u.mode, u.p0, u.p1, a_old, stat, fresh, next);
+    __syncthreads();   // every thread has read aux[row] before thread 0 overwrites it
+    if (threadIdx.x == 0) {
+        if (u.write_aux && u.aux) u.aux[row] = next;
+        if (fb.bias) {
+            const float den = __fsqrt_rn(__fadd_rn(ps.var[row], ps.eps));
+            fb.bias[row] = __fsub_rn(fb.beta[row], __fdiv_rn(__fmul_rn(fb.mean[row], ps.gamma[row]), den));
+        }
+    }
+    if (a.req == B2Q_REQ_NULL) return;
+    const float after = u.write_aux ? next : a_old;
+    const float T = u.use_aux_as_scale ? after : fresh;
+    const float Tc = clip_with_fresh ? fresh : T;
+    const QScale qs = make_qscale(T, a.qlevel, a.fast != 0);
+    const bool add = (a.req == B2Q_REQ_ADD);
+    const bool vec_out = ((((uintptr_t)yb) & 15) == 0) && ((n & 3) == 0);
+    if (vec_out) {
+        const float4* s4 = reinterpret_cast<const float4*>(s_row);
+        float4* y4 = reinterpret_cast<float4*>(yb);
+        for (int i = threadIdx.x; i < (n >> 2); i += blockDim.x) {
+            const float4 v = s4[i];
+            float4 r;
+            float c;
+            r.x = qdq_generic(a, v.x, Tc, qs, c); r.y = qdq_generic(a, v.y, Tc, qs, c);
+            r.z = qdq_generic(a, v.z, Tc, qs, c); r.w = qdq_generic(a, v.w, Tc, qs, c);
+            if (add) {
+                const float4 old = y4[i];
+                r.x = __fadd_rn(old.x, r.x); r.y = __fadd_rn(old.y, r.y); r.z = __fadd_rn(old.z, r.z); r.w = __fadd_rn(old.w, r.w);
+            }
+            y4[i] = r;
+        }
+    } else {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            float c;
+            float r = qdq_generic(a, s_row[i], Tc, qs, c);
+            if (add) r = __fadd_rn(yb[i], r);
+            yb[i] = r;
+        }
+    }
+}
+
 // Eligible: weights viewed as (1, rows, inner) with short rows.  *done = 0 -> caller uses reduce + sweep.
 template <bool IS_MAX>
 [[maybe_unused]] static int launch_rows_fused(b2q_ctx* ctx, const float* x, float* y, int64_t rows, int64_t inner,
                                               Prescale ps, FoldBias fb, UpdateArgs u, QdqArgs a, int clip_with_fresh,
                                               cudaStream_t st, int* done) {
     *done = 0;
-    if (inner > B2Q_ROWS_FUSED_MAX_INNER || rows < 2 || a.codes != nullptr || u.stat_out != nullptr) return 0;
+    if (rows < 2 || a.codes != nullptr || u.stat_out != nullptr) return 0;
+    if (inner >= B2Q_ROWS_CTA_MIN_INNER && inner <= B2Q_ROWS_CTA_MAX_INNER && rows <= 0x7fffffff) {
+        const size_t smem = (size_t)inner * sizeof(float);
+        bool& optin_done = IS_MAX ? ctx->rows_cta_optin[0] : ctx->rows_cta_optin[1];   // per device (per ctx)
+        if (smem > 48 * 1024 && !optin_done) {
+            B2Q_CHECK_CUDA(cudaFuncSetAttribute(rows_cta_kernel<IS_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                B2Q_ROWS_CTA_MAX_INNER * (int)sizeof(float)));
+            optin_done = true;
+        }
+        b2q_timed_launch tl(ctx, B2Q_KIND_OTHER, 8.0 * (double)(rows * inner), st);
+        b2q_launch_smem(ctx, rows_cta_kernel<IS_MAX>, (unsigned)rows, B2Q_THREADS, smem, st, x, y, rows, inner, ps, fb, u, a,
+                        clip_with_fresh);
+        B2Q_LAUNCH_CHECK(ctx);
+        *done = 1;
+        return 0;
+    }
+    if (inner > B2Q_ROWS_FUSED_MAX_INNER) return 0;
     const int nw = B2Q_THREADS / 32;
     const unsigned grid = (unsigned)((rows + nw - 1) / nw);
     b2q_timed_launch tl(ctx, B2Q_KIND_OTHER, 8.0 * (double)(rows * inner), st);

@@ -33,15 +33,15 @@ static inline FlatSplit b2q_flat_split(const void* p, int64_t n) {
 
 template <bool IS_MAX>
 __device__ __forceinline__ void acc1(double& a, float& m, float v) {
-    if (IS_MAX) m = fmaxf(m, fabsf(v)); else a += (double)fabsf(v);
+    if (IS_MAX) m = fmax_nan(m, fabsf(v)); else a += (double)fabsf(v);
 }
 
 template <bool IS_MAX>
 __device__ __forceinline__ void acc8(double& a, float& m, const f8& r) {
     if (IS_MAX) {
-        const float m0 = fmaxf(fabsf(r.v[0]), fabsf(r.v[1])), m1 = fmaxf(fabsf(r.v[2]), fabsf(r.v[3]));
-        const float m2 = fmaxf(fabsf(r.v[4]), fabsf(r.v[5])), m3 = fmaxf(fabsf(r.v[6]), fabsf(r.v[7]));
-        m = fmaxf(m, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+        const float m0 = fmax_nan(fabsf(r.v[0]), fabsf(r.v[1])), m1 = fmax_nan(fabsf(r.v[2]), fabsf(r.v[3]));
+        const float m2 = fmax_nan(fabsf(r.v[4]), fabsf(r.v[5])), m3 = fmax_nan(fabsf(r.v[6]), fabsf(r.v[7]));
+        m = fmax_nan(m, fmax_nan(fmax_nan(m0, m1), fmax_nan(m2, m3)));
     } else {
         // double accumulation: every float32 -> double conversion and each pair sum below 2^53 ulps is exact
         const double s0 = (double)fabsf(r.v[0]) + (double)fabsf(r.v[1]);
@@ -99,6 +99,8 @@ reduce_flat_kernel(const float* __restrict__ x, FlatSplit sp, b2q_slot* slot, Up
                 slot->partial[blockIdx.x] = r;
             }
             if (blockIdx.x == 0 && u.aux) slot->scale[0] = u.aux[0];   // snapshot of the old threshold
+            // peer exchange: this call's sequence number (one thread of the whole grid; kernels of a stream are ordered)
+            if (blockIdx.x == 0 && u.seq_counter) *u.seq_counter = *u.seq_counter + 1u;
         }
         return;
     }
@@ -117,7 +119,7 @@ reduce_flat_kernel(const float* __restrict__ x, FlatSplit sp, b2q_slot* slot, Up
     float m = 0.f;
     for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
         double p = __ldcg(&slot->partial[i]);
-        if (IS_MAX) m = fmaxf(m, (float)p); else a += p;
+        if (IS_MAX) m = fmax_nan(m, (float)p); else a += p;
     }
     double tot = block_reduce<IS_MAX>(IS_MAX ? (double)m : a, smem);
     if (threadIdx.x == 0) {
@@ -203,33 +205,43 @@ reduce_seg_kernel(const float* __restrict__ x, SegPlan pl, Prescale ps, b2q_slot
     const SegPiece pc = seg_piece(pl);
     double acc = 0.0;
     float mx = 0.f;
-    for (int64_t o = pc.o0; o < pc.o1; ++o) {
+    if (VEC == 8) {
+        // 256-bit loads, four in flight per thread, over the piece's (row, word) space FLATTENED into one index: short
+        // rows (gs = 1 on 56x56 maps: 392 words per row) would otherwise leave most lanes of every iteration idle
+        const unsigned wpr = (unsigned)((pc.i1 - pc.i0) >> 3);                    // words per row in this piece
+        const unsigned total = (unsigned)(pc.o1 - pc.o0) * wpr;
+        for (unsigned w0 = threadIdx.x; w0 < total; w0 += 4 * blockDim.x) {
+            f8 v[4];
+            float fk[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const unsigned w = w0 + k * blockDim.x;
+                if (w < total) {
+                    const unsigned o = w / wpr, i = w - o * wpr;
+                    const int64_t row = (pc.o0 + o) * pl.groups + pc.g;
+                    v[k] = ld_f8<0>(x + row * pl.inner + pc.i0 + 8 * (int64_t)i);
+                    fk[k] = ps.gamma ? prescale_factor(ps, row) : 1.f;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[k].v[e] = 0.f;
+                    fk[k] = 1.f;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (ps.gamma) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[k].v[e] = __fmul_rn(v[k].v[e], fk[k]);
+                }
+                acc8<IS_MAX>(acc, mx, v[k]);
+            }
+        }
+    }
+    for (int64_t o = pc.o0; VEC != 8 && o < pc.o1; ++o) {
         const int64_t row = o * pl.groups + pc.g;
         const float* base = x + row * pl.inner;
         const float f = ps.gamma ? prescale_factor(ps, row) : 1.f;
-        if (VEC == 8) {   // 256-bit loads, four in flight per thread (same inner loop as the flat kernel)
-            const int64_t end = pc.i1 >> 3;
-            for (int64_t i = (pc.i0 >> 3) + threadIdx.x; i < end; i += 4 * (int64_t)blockDim.x) {
-                f8 v[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int64_t j = i + (int64_t)k * blockDim.x;
-                    if (j < end) v[k] = ld_f8<0>(base + 8 * j);
-                    else {
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) v[k].v[e] = 0.f;
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (ps.gamma) {
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) v[k].v[e] = __fmul_rn(v[k].v[e], f);
-                    }
-                    acc8<IS_MAX>(acc, mx, v[k]);
-                }
-            }
-        } else if (VEC == 4) {
+        if (VEC == 4) {
             const float4* b4 = reinterpret_cast<const float4*>(base);
             const int64_t end = pc.i1 >> 2;
             for (int64_t i = (pc.i0 >> 2) + threadIdx.x; i < end; i += 4 * (int64_t)blockDim.x) {
@@ -274,7 +286,7 @@ reduce_seg_kernel(const float* __restrict__ x, SegPlan pl, Prescale ps, b2q_slot
             float m = 0.f;
             for (int l = 0; l < SP; ++l) {
                 const double q = __ldcg(&slot->partial[gg * SP + l]);
-                if (IS_MAX) m = fmaxf(m, (float)q); else a += q;
+                if (IS_MAX) m = fmax_nan(m, (float)q); else a += q;
             }
             apply_update(u, (int)gg, IS_MAX ? m : __fdiv_rn((float)a, count));
         }
@@ -285,7 +297,7 @@ reduce_seg_kernel(const float* __restrict__ x, SegPlan pl, Prescale ps, b2q_slot
             float m = 0.f;
             for (int l = lane; l < SP; l += 32) {
                 double q = __ldcg(&slot->partial[gg * SP + l]);
-                if (IS_MAX) m = fmaxf(m, (float)q); else a += q;
+                if (IS_MAX) m = fmax_nan(m, (float)q); else a += q;
             }
             if (IS_MAX) m = warp_max(m); else a = warp_sum(a);
             if (lane == 0) apply_update(u, (int)gg, IS_MAX ? m : __fdiv_rn((float)a, count));

@@ -118,7 +118,29 @@ class PeerThresholdExchange(object):
                       float(np.float32(p0)), float(np.float32(p1)), float(np.float32(qlevel)), self._boxes, self.rank,
                       self.world, current_stream(xb))
 
+    def status(self):
+        """(sequence, rank) of the first exchange in which this rank gave up waiting for a peer's statistic (option
+        ``peer_timeout_ms``; the affected outputs and thresholds are NaN), or None.  Synchronises with the device."""
+        import ctypes
+        seq, rk = ctypes.c_uint32(0), ctypes.c_uint32(0)
+        self.ctx.call("b2q_peer_status", self._own, ctypes.byref(seq), ctypes.byref(rk))
+        return (int(seq.value), int(rk.value)) if seq.value else None
+
+    def check(self):
+        st = self.status()
+        if st is not None:
+            from . import _lib
+            raise _lib.B2QError("rank %d waited longer than peer_timeout_ms for the statistic of rank %d in exchange %d; "
+                                "thresholds and outputs from that call on are NaN" % (self.rank, st[1], st[0]))
+
     def close(self):
+        if self._own is not None:
+            try:
+                self.check()
+            finally:
+                self._close()
+
+    def _close(self):
         for p in self._opened:
             self.ctx.call("b2q_peer_mailbox_close", p)
         self._opened = []

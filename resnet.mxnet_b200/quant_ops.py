@@ -38,10 +38,15 @@ class Quantization_int8(CustomOp):
         reduce -> allreduce(max) -> update + QDQ, so every rank applies the same threshold."""
         if self.peer is not None and is_train and not self.is_weight and req in ("write", "inplace"):
             self.peer.quantize(self.VARIANT, x, y, aux, first, self.ema_decay)
-        elif self.sync is not None and is_train and not self.is_weight:
+            return
+        if self.peer is not None and self.sync is None and is_train and not self.is_weight:
+            # a peer exchange is attached but this call is outside its fused case (req='add'): the threshold must still
+            # be the max over ranks, so go through the NCCL exchange instead of silently using the local statistic
+            from .dist import ThresholdSync
+            self.sync = ThresholdSync(getattr(self.peer, "group", None))
+        if self.sync is not None and is_train and not self.is_weight:
             if self._stat is None:
-                import torch
-                self._stat = torch.empty(1, dtype=torch.float32, device=x.device)
+                self._stat = K.scratch_like(x, 1)
             K.minmax_quant_stat(x, self._stat, False)
             self.sync(self._stat)
             K.minmax_quant_finish(self.VARIANT, x, y, aux, self._stat, False, False, True, first, self.ema_decay, req)

@@ -78,3 +78,38 @@ def test_foldbn_pieces(per_channel):
         co.foldbn_weight_fwd(ins[1], wq, bias, aux_c[1], ins[3], ins[4], ins[5], ins[6], 1e-5, per_channel, True, True)
         assert bits_equal(aux_c[0], aux_r[0]) and bits_equal(aux_c[1], aux_r[1])
         assert bits_equal(xq, ref.data_q) and bits_equal(wq, ref.weight_q) and bits_equal(bias, ref.bias)
+
+
+def _same_or_nan(a, b):
+    na, nb = np.isnan(a), np.isnan(b)
+    return np.array_equal(na, nb) and np.array_equal(a.view(np.uint32)[~na], b.view(np.uint32)[~nb])
+
+
+@pytest.mark.parametrize("kind", ["zeros", "nan", "inf", "denormal", "outlier"])
+@pytest.mark.parametrize("variant,name", [(0, "Quantization_int8_V2"), (1, "ClipGrad_Quantization_int8")])
+@pytest.mark.parametrize("is_weight,per_channel", [(False, False), (True, False), (True, True)])
+def test_minmax_ops_edge_inputs(variant, name, is_weight, per_channel, kind):
+    """all-zero / NaN / Inf / denormal / outlier inputs: the C restatement used for the full-size GPU
+    parity tests must carry NaN and Inf exactly like the NumPy oracle (max|x| of a tensor holding NaN is NaN)."""
+    rng = np.random.default_rng(23)
+    shape = (6, 5, 3, 3)
+    x = rng.standard_normal(shape).astype(F)
+    flat = x.reshape(-1)
+    if kind == "zeros":
+        flat[:] = 0
+    elif kind == "nan":
+        flat[100] = np.nan
+    elif kind == "inf":
+        flat[100] = -np.inf
+    elif kind == "denormal":
+        flat *= F(1e-41)
+    else:
+        flat[100] = F(3e30)
+    ref = qo.create(name, quant_mode="minmax", is_weight=str(is_weight), is_weight_perchannel=str(per_channel))
+    naux = shape[0] if per_channel else 1
+    aux_c, aux_r = np.ones(naux, F), np.ones(naux, F)
+    yc, yr = np.zeros(shape, F), np.zeros(shape, F)
+    with np.errstate(all="ignore"):
+        co.minmax_quant_fwd(variant, x, yc, aux_c, is_weight, per_channel, True, not is_weight, 0.99)
+        ref.forward(True, ["write"], [x], [yr], [aux_r])
+    assert _same_or_nan(aux_c, aux_r) and _same_or_nan(yc, yr)

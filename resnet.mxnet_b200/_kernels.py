@@ -362,9 +362,9 @@ def export_int8(x, thr, qlevel, clip_mode, view=None):
     outer, groups, inner = view if view is not None else (1, 1, xb.numel)
     on_dev, dev = _same_place(xb, tb)
     require_device(on_dev, "export_int8")
-    dev = x.device if isinstance(x, torch.Tensor) else torch.device("cuda", xb.device_id)
-    codes = torch.empty(xb.shape, dtype=torch.int8, device=dev)
-    steps = torch.empty(groups, dtype=torch.float32, device=dev)
+    tdev = x.device if isinstance(x, torch.Tensor) else torch.device("cuda", xb.device_id)
+    codes = torch.empty(xb.shape, dtype=torch.int8, device=tdev)
+    steps = torch.empty(groups, dtype=torch.float32, device=tdev)
     _lib.context(dev).call("b2q_export_int8_f32", xb.ptr, codes.data_ptr(), steps.data_ptr(), outer, groups, inner,
                            tb.ptr, _f32(qlevel), int(clip_mode), current_stream(xb))
     return codes, steps

@@ -61,12 +61,13 @@ struct b2q_ctx {
     int dorefa_tanh_max = 0;         // 1: DoReFa takes max|tanh(w)| element-wise instead of tanhf(max|w|) (same float)
     int host_ste_copy = 1;           // host-buffer straight-through backward: copy host to host, no PCIe round trip
     int resident = 1;                // single-launch forward for tensors that fit on chip (shared memory + L2)
-    long long resident_max_bytes = 72ll << 20;
+    int resident_max_mb = 72;        // largest tensor (MB) that takes the single-launch resident forward
     int peer_mode = 1;               // 1: ticket-free reduction, the sweep's first block publishes to the peers; 0: r1 kernels
     int peer_timeout_ms = 600000;    // how long a sweep waits for a peer's statistic before it gives up (NaN output + flag)
     int timing = 0;
     std::vector<b2q_timing_rec> recs;
     std::vector<cudaEvent_t> event_pool;
+    bool resident_optin[4] = {false, false, false, false};   // > 48 KB dynamic shared memory for fused_resident_kernel<..>
     bool rows_cta_optin[2] = {false, false};   // > 48 KB dynamic shared memory enabled for rows_cta_kernel<max / sum>
     void* host_state = nullptr;     // staging buffers + streams of the host-buffer entry points (b2q_host.cu)
 };

@@ -306,21 +306,27 @@ struct DorefaMax {
     __device__ void finalize(const double*, float m) { vmax[0] = m; }
 };
 
-__global__ void dorefa_vmax_kernel(const float* __restrict__ absmax, float* __restrict__ vmax) {
-    b2q_pdl_sync();
-    vmax[0] = fabsf(tanhf(absmax[0]));
-}
-
 struct DorefaFwd {
     static const int NIN = 1;
     static const bool REDUCES = false;
     const float* x; float* y; const float* vmax; float L; int add_;
+    const float* absmax;   // != nullptr: vmax = tanhf(absmax[0]) is derived here (every thread; thread 0 of block 0 stores it)
     float two_v; LevelDiv ld;
     __host__ __device__ const float* in0() const { return x; }
     __host__ __device__ const float* in1() const { return nullptr; }
     __host__ __device__ float* out() const { return y; }
     __host__ __device__ int add() const { return add_; }
-    __device__ void setup() { two_v = __fmul_rn(2.f, vmax[0]); ld = make_level_div(L); }
+    __device__ void setup() {
+        float v;
+        if (absmax) {
+            v = fabsf(tanhf(absmax[0]));
+            if (blockIdx.x == 0 && threadIdx.x == 0) const_cast<float*>(vmax)[0] = v;
+        } else {
+            v = vmax[0];
+        }
+        two_v = __fmul_rn(2.f, v);
+        ld = make_level_div(L);
+    }
     __device__ float apply(float a, float, int64_t, double*, float&) {
         const float t = tanhf(a);
         const float o = __fadd_rn(__fdiv_rn(t, two_v), 0.5f);                      // PACT.py:49
@@ -556,7 +562,9 @@ __global__ void selftest_div_level_kernel(unsigned long long* bad) {
     if (local) atomicAdd(bad, local);
 }
 
-__global__ void selftest_tanh_kernel(unsigned long long* bad) {
+// mode 2: count of violations; mode 3: largest x (bit pattern) with tanhf(next(x)) < tanhf(x); mode 4: largest x with
+// tanhf(-x) != -tanhf(x)
+__global__ void selftest_tanh_kernel(unsigned long long* bad, int mode) {
     // all finite positive floats: tanhf(next(x)) >= tanhf(x) and tanhf(-x) == -tanhf(x)
     unsigned long long local = 0;
     const unsigned int last = 0x7f7fffffu;
@@ -564,22 +572,28 @@ __global__ void selftest_tanh_kernel(unsigned long long* bad) {
          b += (unsigned long long)gridDim.x * blockDim.x) {
         const float x = __uint_as_float((unsigned int)b), xn = __uint_as_float((unsigned int)b + 1u);
         const float t = tanhf(x), tn = tanhf(xn);
-        if (!(tn >= t)) ++local;
-        if (__float_as_uint(tanhf(-x)) != (__float_as_uint(t) ^ 0x80000000u)) ++local;
+        const bool inv = !(tn >= t);
+        const bool odd = __float_as_uint(tanhf(-x)) != (__float_as_uint(t) ^ 0x80000000u);
+        if (mode == 2) local += (inv ? 1 : 0) + (odd ? 1 : 0);
+        else if ((mode == 3 && inv) || (mode == 4 && odd)) local = b > local ? b : local;
     }
-    if (local) atomicAdd(bad, local);
+    if (local) {
+        if (mode == 2) atomicAdd(bad, local);
+        else atomicMax(bad, local);
+    }
 }
 
 extern "C" {
 
 int b2q_selftest(b2q_ctx* ctx, int which, int64_t* failures) {
     B2Q_CTX(ctx);
-    B2Q_REQUIRE(failures != nullptr && (which == 1 || which == 2), "which: 1 level division, 2 tanhf monotonic/odd");
+    B2Q_REQUIRE(failures != nullptr && which >= 1 && which <= 4,
+                "which: 1 level division, 2 tanhf monotonic/odd (count), 3 / 4 where (bit pattern of the largest x)");
     unsigned long long* d = nullptr;
     B2Q_CHECK_CUDA(cudaMalloc(&d, sizeof(unsigned long long)));
     B2Q_CHECK_CUDA(cudaMemset(d, 0, sizeof(unsigned long long)));
     if (which == 1) selftest_div_level_kernel<<<ctx->num_sms, 256>>>(d);
-    else selftest_tanh_kernel<<<ctx->num_sms * 8, 256>>>(d);
+    else selftest_tanh_kernel<<<ctx->num_sms * 8, 256>>>(d, which);
     unsigned long long h = 0;
     cudaError_t e = cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost);
     cudaFree(d);
@@ -689,6 +703,7 @@ int b2q_dorefa_fwd_f32(b2q_ctx* ctx, const float* x, float* y, float* vmax_out, 
     B2Q_CTX(ctx);
     B2Q_REQUIRE(x && y && vmax_out && n >= 1, "bad argument");
     cudaStream_t st = (cudaStream_t)stream;
+    const float* absmax = nullptr;
     if (ctx->dorefa_tanh_max) {   // element-wise max of |tanh(w)| (PACT.py:48 as written)
         DorefaMax mop = {x, vmax_out};
         int rc = launch_ew(ctx, mop, n, 4.0, st);
@@ -700,11 +715,11 @@ int b2q_dorefa_fwd_f32(b2q_ctx* ctx, const float* x, float* y, float* vmax_out, 
         u.stat_out = slot->scale;
         int rc = launch_reduce<true>(ctx, slot, x, 1, 1, n, kNoPrescale, u, st);
         if (rc) return rc;
-        b2q_launch(ctx, dorefa_vmax_kernel, 1u, 1u, st, (const float*)slot->scale, vmax_out);
-        B2Q_LAUNCH_CHECK(ctx);
+        absmax = slot->scale;
     }
-    if (req == B2Q_REQ_NULL) return 0;
-    DorefaFwd op = {x, y, vmax_out, qlevel, req == B2Q_REQ_ADD, 0.f, {}};
+    // req == null still has to leave vmax behind for the backward: the sweep runs without an output
+    DorefaFwd op = {x, req == B2Q_REQ_NULL ? nullptr : y, vmax_out, qlevel, req == B2Q_REQ_ADD, absmax, 0.f, {}};
+    if (req == B2Q_REQ_NULL && absmax == nullptr) return 0;
     return launch_ew(ctx, op, n, 8.0, st);
 }
 

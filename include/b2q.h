@@ -212,8 +212,11 @@ int b2q_qil_bwd_f32(b2q_ctx* ctx, int variant, const float* x, const float* dy, 
 
 /* Exhaustive self tests of the two numerical shortcuts in the second-tier kernels; *failures = number of inputs on which
  * the shortcut differs from the reference arithmetic (must be 0).  which = 1: code / L by reciprocal + two FMAs versus
- * IEEE division, every integer |code| <= 4 L, L = 2^nbits - 1, nbits = 1..16.  which = 2: tanhf is odd and monotonic
- * non-decreasing over all finite positive floats (so max|tanh(w)| == tanhf(max|w|), DoReFa_PY).  Synchronous.     */
+ * IEEE division, every integer |code| <= 4 L, L = 2^nbits - 1, nbits = 1..16.  which = 2: the facts behind DoReFa_PY's
+ * max|tanh(w)| = max(tanhf(max|w|), max of tanhf over the elements in a 129-ulp window around |w| = 0.6): tanhf is odd,
+ * monotonic non-decreasing over all finite positive floats outside that window, and the window's values lie between
+ * tanhf of its lowest float and tanhf of the first float above it.  which = 3 / 4 (diagnostic): bit pattern of the
+ * largest x with tanhf(next(x)) < tanhf(x) / with tanhf(-x) != -tanhf(x), 0 if none.  Synchronous.              */
 int b2q_selftest(b2q_ctx* ctx, int which, int64_t* failures);
 
 /* ---- multi-tensor: every weight of a network in two launches (forward) / one launch (backward) ---------

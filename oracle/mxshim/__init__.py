@@ -9,6 +9,7 @@ their results can be recorded as golden vectors (``tests/golden/generate.py``) w
     mx.nd.{abs,max,mean,sum,round,clip,sign,where,reshape,swapaxes,sqrt,tanh,exp,power,zeros_like,
            ones_like,Convolution,array}                  mx.nd.NDArray (operators, indexing, asnumpy,
                                                          reshape, broadcast_like, attach_grad/grad/backward)
+    mx.sym (oracle/mxshim/sym.py): a symbolic graph recorder for the reference's graph builders
 
 Arrays are torch CPU float32 tensors (torch supplies IEEE float32 elementwise arithmetic and the autograd
 the PACT/DoReFa/QIL ops replay).  The MXNet numerics it encodes are the [upstream] assumptions listed in
@@ -166,6 +167,25 @@ class NDArray(object):
 
     def broadcast_like(self, other):
         return NDArray(self._t.expand_as(_t(other)))
+
+    @property
+    def ndim(self):
+        return self._t.dim()
+
+    def expand_dims(self, axis):
+        return NDArray(self._t.unsqueeze(axis))
+
+    def __isub__(self, o):
+        with torch.no_grad():
+            self._t -= _t(o)
+        return self
+
+    def __itruediv__(self, o):
+        with torch.no_grad():
+            self._t /= _t(o)
+        return self
+
+    __idiv__ = __itruediv__
 
     # -- autograd ----------------------------------------------------------------------------
     def attach_grad(self):
@@ -352,8 +372,26 @@ def install():
     ag = types.ModuleType("mxnet.autograd")
     ag.record = _record
     init = types.ModuleType("mxnet.init")
-    init.Initializer = type("Initializer", (), {})
+
+    class Initializer(object):
+        """[upstream python/mxnet/initializer.py]: ``dumps()`` is what ends up in a variable's ``__init__`` attribute."""
+
+        def __init__(self, **kwargs):
+            self._kwargs = kwargs
+
+        def dumps(self):
+            import json
+            return json.dumps([self.__class__.__name__.lower(), self._kwargs])
+
+    class Constant(Initializer):
+        def __init__(self, value):
+            super(Constant, self).__init__(value=value)
+
+    init.Initializer, init.Constant = Initializer, Constant
+    from . import sym as _sym
+    _sym.set_registries(REGISTRY)
     mx.nd, mx.ndarray, mx.operator, mx.autograd, mx.init = nd, nd, op, ag, init
+    mx.sym = mx.symbol = _sym
     sys.modules.update({"mxnet": mx, "mxnet.nd": nd, "mxnet.operator": op, "mxnet.autograd": ag,
-                        "mxnet.init": init})
+                        "mxnet.init": init, "mxnet.sym": _sym, "mxnet.symbol": _sym})
     return mx

@@ -60,7 +60,11 @@ struct b2q_ctx {
     int fast_div = 1;
     int dorefa_tanh_max = 0;         // 1: DoReFa takes max|tanh(w)| element-wise instead of tanhf(max|w|) (same float)
     int host_ste_copy = 1;           // host-buffer straight-through backward: copy host to host, no PCIe round trip
-    int resident = 1;                // single-launch forward for tensors that fit on chip (shared memory + L2)
+    int resident = 0;                // single-launch forward for tensors that fit on chip (shared memory + L2).  OFF by
+                                     // default: on B200 the 126 MB L2 already serves the sweep of a <= 51 MB tensor (ncu in
+                                     // step: 3.6 MB of DRAM reads for a 51.4 MB tensor), so the kernel saves no traffic,
+                                     // and its barrier latency chain costs more than two PDL-chained launches
+                                     // (profiles/r02b_resident_ab.md)
     int resident_max_mb = 72;        // largest tensor (MB) that takes the single-launch resident forward
     int peer_mode = 1;               // 1: ticket-free reduction, the sweep's first block publishes to the peers; 0: r1 kernels
     int peer_timeout_ms = 600000;    // how long a sweep waits for a peer's statistic before it gives up (NaN output + flag)

@@ -181,7 +181,7 @@ template <bool IS_MAX>
                                                   UpdateArgs u, float qlevel, int clip_mode, int clip_with_fresh,
                                                   cudaStream_t st, int* done) {
     *done = 0;
-    if (!ctx->resident || n * 4 > ((int64_t)ctx->resident_max_mb << 20) || n < 4096) return 0;
+    if (!ctx->resident || n * 4 > ((int64_t)ctx->resident_max_mb << 20) || n < (1 << 20)) return 0;
     if (!(clip_mode == B2Q_CLIP_NONE || clip_mode == B2Q_CLIP_SYM) || u.stat_out != nullptr) return 0;
     FlatSplit sp = b2q_flat_split(x, n);
     if (!same_misalignment(x, y) || sp.head > B2Q_THREADS || sp.n8 < 1) return 0;

@@ -38,12 +38,12 @@ __device__ __forceinline__ float div_level(float c, const LevelDiv& d) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Generic flat "elementwise + up to 2 sums + 1 max" kernel over 256-bit words.  Op provides
+// Generic flat "elementwise + up to 2 sums + 2 maxima" kernel over 256-bit words.  Op provides
 //   static const int NIN (1: x, 2: x and dy);  static const bool REDUCES;
 //   const float* in0() / in1();  float* out() (nullptr: nothing is written);  int add() (req == add)
 //   __device__ void setup();                                     (per-thread scalars from device memory)
-//   __device__ float apply(float a, float b, int64_t i, double* s, float& m);   (returns the output value)
-//   __device__ void finalize(const double* s, float m);          (last block, thread 0)
+//   __device__ float apply(float a, float b, int64_t i, double* s, float* m);   (returns the output value; s[2], m[2])
+//   __device__ void finalize(const double* s, const float* m);   (last block, thread 0)
 // Same structure as the hot sweeps: head scalars until 32-byte alignment, two 256-bit loads per input in flight per
 // thread, one 256-bit store per word, tail scalars; reducing ops run a capped grid-stride grid and finish in the block
 // that draws the last ticket.
@@ -51,7 +51,7 @@ __device__ __forceinline__ float div_level(float c, const LevelDiv& d) {
 #define B2Q_EW_UNROLL 2
 
 template <class Op>
-__device__ __forceinline__ void ew_scalar(Op& op, int64_t i, double* s, float& m) {
+__device__ __forceinline__ void ew_scalar(Op& op, int64_t i, double* s, float* m) {
     const float a = op.in0()[i];
     const float b = (Op::NIN == 2) ? op.in1()[i] : 0.f;
     const float r = op.apply(a, b, i, s, m);
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(B2Q_THREADS) ew_kernel(Op op, FlatSplit sp, in
     __shared__ unsigned int s_ticket;
     op.setup();
     double s[2] = {0.0, 0.0};
-    float m = 0.f;
+    float m[2] = {0.f, 0.f};
     if (VEC) {
         const float* xa = op.in0() + sp.head;
         const float* xb = (Op::NIN == 2) ? op.in1() + sp.head : nullptr;
@@ -110,31 +110,38 @@ __global__ void __launch_bounds__(B2Q_THREADS) ew_kernel(Op op, FlatSplit sp, in
         for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) ew_scalar(op, i, s, m);
     }
     if (!Op::REDUCES) return;
-    double r[3];
+    double r[4];
     r[0] = block_reduce<false>(s[0], smem);
     r[1] = block_reduce<false>(s[1], smem);
-    r[2] = block_reduce<true>((double)m, smem);
+    r[2] = block_reduce<true>((double)m[0], smem);
+    r[3] = block_reduce<true>((double)m[1], smem);
     if (gridDim.x == 1) {
-        if (threadIdx.x == 0) op.finalize(r, (float)r[2]);
+        if (threadIdx.x == 0) {
+            const float fm[2] = {(float)r[2], (float)r[3]};
+            op.finalize(r, fm);
+        }
         return;
     }
     if (threadIdx.x == 0) {
-        for (int k = 0; k < 3; ++k) slot->partial[3 * blockIdx.x + k] = r[k];
+        for (int k = 0; k < 4; ++k) slot->partial[4 * blockIdx.x + k] = r[k];
         s_ticket = b2q_take_ticket(&slot->ticket, gridDim.x - 1);
     }
     __syncthreads();
     if (s_ticket != gridDim.x - 1) return;
     double a[2] = {0.0, 0.0};
-    float mm = 0.f;
+    float mm[2] = {0.f, 0.f};
     for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
-        a[0] += __ldcg(&slot->partial[3 * i + 0]);
-        a[1] += __ldcg(&slot->partial[3 * i + 1]);
-        mm = fmax_nan(mm, (float)__ldcg(&slot->partial[3 * i + 2]));
+        a[0] += __ldcg(&slot->partial[4 * i + 0]);
+        a[1] += __ldcg(&slot->partial[4 * i + 1]);
+        mm[0] = fmax_nan(mm[0], (float)__ldcg(&slot->partial[4 * i + 2]));
+        mm[1] = fmax_nan(mm[1], (float)__ldcg(&slot->partial[4 * i + 3]));
     }
     double t[2];
     t[0] = block_reduce<false>(a[0], smem);
     t[1] = block_reduce<false>(a[1], smem);
-    const float tm = (float)block_reduce<true>((double)mm, smem);
+    float tm[2];
+    tm[0] = (float)block_reduce<true>((double)mm[0], smem);
+    tm[1] = (float)block_reduce<true>((double)mm[1], smem);
     if (threadIdx.x == 0) {
         op.finalize(t, tm);
         slot->ticket = 0;
@@ -148,7 +155,7 @@ static int launch_ew(b2q_ctx* ctx, Op op, int64_t n, double alg_bytes_per_elem, 
     bool vec = sp.head <= B2Q_THREADS;
     if (Op::NIN == 2) vec = vec && same_misalignment(op.in0(), op.in1());
     if (op.out()) vec = vec && same_misalignment(op.in0(), op.out());
-    const int64_t cap = Op::REDUCES ? (int64_t)ctx->num_sms * 16 : (int64_t)0x7fffffff;   // 3 partials per block
+    const int64_t cap = Op::REDUCES ? (int64_t)ctx->num_sms * 16 : (int64_t)0x7fffffff;   // 4 partials per block
     b2q_timed_launch tl(ctx, B2Q_KIND_OTHER, alg_bytes_per_elem * (double)n, st);
     if (vec) {
         const int64_t tile = (int64_t)B2Q_THREADS * B2Q_EW_UNROLL;
@@ -180,13 +187,13 @@ struct WnqFwd {
     __host__ __device__ float* out() const { return y; }
     __host__ __device__ int add() const { return add_; }
     __device__ void setup() { m0 = m[0]; ld = make_level_div(L); }
-    __device__ float apply(float a, float, int64_t i, double*, float&) {
+    __device__ float apply(float a, float, int64_t i, double*, float*) {
         const float mm = PER_CHANNEL ? m[i / cols] : m0;
         const float normed = __fdiv_rn(a, mm);                                     // WNQ.py:62
         const float code = roundf(__fmul_rn(normed, L));
         return __fmul_rn(div_level(code, ld), mm);                                 // :63
     }
-    __device__ void finalize(const double*, float) {}
+    __device__ void finalize(const double*, const float*) {}
 };
 
 // sum_g( dy * x * [|x| != m_g] ) over the (1, groups, cols) view, then max_abs_grad = -sum / m   (:73 / :83)
@@ -253,14 +260,14 @@ struct WnqBwdApply {
     __host__ __device__ float* out() const { return dx; }
     __host__ __device__ int add() const { return add_; }
     __device__ void setup() { m0 = m[0]; g0 = mgrad[0]; }
-    __device__ float apply(float a, float b, int64_t i, double*, float&) {
+    __device__ float apply(float a, float b, int64_t i, double*, float*) {
         const int64_t g = PER_CHANNEL ? i / cols : 0;
         const float mm = PER_CHANNEL ? m[g] : m0, mg = PER_CHANNEL ? mgrad[g] : g0;
         const float ax = fabsf(a);
         const float nm = (ax != mm) ? 1.f : 0.f, im = (ax == mm) ? 1.f : 0.f;
         return __fadd_rn(__fmul_rn(b, nm), __fmul_rn(mg, im));                     // :85
     }
-    __device__ void finalize(const double*, float) {}
+    __device__ void finalize(const double*, const float*) {}
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -276,23 +283,48 @@ struct PactBwd {
     __host__ __device__ float* out() const { return dx; }
     __host__ __device__ int add() const { return add_; }
     __device__ void setup() { g = gamma[0]; }
-    __device__ float apply(float xv, float d, int64_t, double* s, float&) {
+    __device__ float apply(float xv, float d, int64_t, double* s, float*) {
         const bool cond = two_sided ? (fabsf(xv) < g) : (xv < g);
         float other = cond ? 0.f : d;
         if (two_sided) other = __fmul_rn(other, mx_sign(xv));
         s[0] += (double)other;
         return cond ? d : 0.f;
     }
-    __device__ void finalize(const double* s, float) { put_scalar(dgamma, (float)s[0], req_gamma); }
+    __device__ void finalize(const double* s, const float*) { put_scalar(dgamma, (float)s[0], req_gamma); }
 };
 
 // ------------------------------------------------------------------------------------------------
 // DoReFa_PY  (core/operator/PACT.py:44-50, 76-77)
-// max|tanh(w)| is taken as tanhf(max|w|): tanhf is odd and monotonic non-decreasing over every positive float on this
-// toolchain (b2q_selftest(2) checks all 2^31 of them), so the two are the same float and the first pass is the plain
-// max|w| reduction at HBM speed instead of a second tanh per element.  Option "dorefa_tanh_max"=1 restores the
+// max|tanh(w)| without a tanh per element: tanhf is odd and monotonic non-decreasing over the positive floats EXCEPT at
+// the switch between its two branches -- on this toolchain exactly one adjacent pair, tanhf(0x3f199999) >
+// tanhf(0x3f19999a) (|x| = 0.6, b2q_selftest(3)).  So the first pass takes max|w| (m0) and, for the few elements whose
+// |w| lies in a 129-ulp window W around that point, max tanhf(|w|) (m1, evaluated only there); max|tanh(w)| =
+// max(tanhf(m0), m1) exactly: outside W tanhf is monotonic, and every value in W is below tanhf of the first float
+// above W (b2q_selftest(2) checks both facts over all 2^31 positive floats).  Option "dorefa_tanh_max"=1 restores the
 // element-wise max of tanh.
 // ------------------------------------------------------------------------------------------------
+#define B2Q_TANH_WINDOW_LO 0x3f199959u
+#define B2Q_TANH_WINDOW_HI 0x3f1999d9u
+
+struct DorefaAbsMax {
+    static const int NIN = 1;
+    static const bool REDUCES = true;
+    const float* x; float* vmax;
+    __host__ __device__ const float* in0() const { return x; }
+    __host__ __device__ const float* in1() const { return nullptr; }
+    __host__ __device__ float* out() const { return nullptr; }
+    __host__ __device__ int add() const { return 0; }
+    __device__ void setup() {}
+    __device__ float apply(float a, float, int64_t, double*, float* m) {
+        const float ax = fabsf(a);
+        m[0] = fmax_nan(m[0], ax);
+        const unsigned int b = __float_as_uint(ax);
+        if (b >= B2Q_TANH_WINDOW_LO && b <= B2Q_TANH_WINDOW_HI) m[1] = fmax_nan(m[1], tanhf(ax));
+        return 0.f;
+    }
+    __device__ void finalize(const double*, const float* m) { vmax[0] = fmax_nan(fabsf(tanhf(m[0])), m[1]); }
+};
+
 struct DorefaMax {
     static const int NIN = 1;
     static const bool REDUCES = true;
@@ -302,38 +334,27 @@ struct DorefaMax {
     __host__ __device__ float* out() const { return nullptr; }
     __host__ __device__ int add() const { return 0; }
     __device__ void setup() {}
-    __device__ float apply(float a, float, int64_t, double*, float& m) { m = fmax_nan(m, fabsf(tanhf(a))); return 0.f; }
-    __device__ void finalize(const double*, float m) { vmax[0] = m; }
+    __device__ float apply(float a, float, int64_t, double*, float* m) { m[0] = fmax_nan(m[0], fabsf(tanhf(a))); return 0.f; }
+    __device__ void finalize(const double*, const float* m) { vmax[0] = m[0]; }
 };
 
 struct DorefaFwd {
     static const int NIN = 1;
     static const bool REDUCES = false;
     const float* x; float* y; const float* vmax; float L; int add_;
-    const float* absmax;   // != nullptr: vmax = tanhf(absmax[0]) is derived here (every thread; thread 0 of block 0 stores it)
     float two_v; LevelDiv ld;
     __host__ __device__ const float* in0() const { return x; }
     __host__ __device__ const float* in1() const { return nullptr; }
     __host__ __device__ float* out() const { return y; }
     __host__ __device__ int add() const { return add_; }
-    __device__ void setup() {
-        float v;
-        if (absmax) {
-            v = fabsf(tanhf(absmax[0]));
-            if (blockIdx.x == 0 && threadIdx.x == 0) const_cast<float*>(vmax)[0] = v;
-        } else {
-            v = vmax[0];
-        }
-        two_v = __fmul_rn(2.f, v);
-        ld = make_level_div(L);
-    }
-    __device__ float apply(float a, float, int64_t, double*, float&) {
+    __device__ void setup() { two_v = __fmul_rn(2.f, vmax[0]); ld = make_level_div(L); }
+    __device__ float apply(float a, float, int64_t, double*, float*) {
         const float t = tanhf(a);
         const float o = __fadd_rn(__fdiv_rn(t, two_v), 0.5f);                      // PACT.py:49
         const float code = roundf(__fmul_rn(L, o));                               // quantizeK, :26-28
         return __fsub_rn(__fmul_rn(2.f, div_level(code, ld)), 1.f);                // :50
     }
-    __device__ void finalize(const double*, float) {}
+    __device__ void finalize(const double*, const float*) {}
 };
 
 struct DorefaBwdSum {  // d(2v) = sum( g * (-t / (2v)^2) ),  g = 2*dy
@@ -346,13 +367,13 @@ struct DorefaBwdSum {  // d(2v) = sum( g * (-t / (2v)^2) ),  g = 2*dy
     __host__ __device__ float* out() const { return nullptr; }
     __host__ __device__ int add() const { return 0; }
     __device__ void setup() { two_v = __fmul_rn(2.f, vmax[0]); sq = __fmul_rn(two_v, two_v); }
-    __device__ float apply(float a, float b, int64_t, double* s, float&) {
+    __device__ float apply(float a, float b, int64_t, double* s, float*) {
         const float t = tanhf(a);
         const float g = __fmul_rn(2.f, b);
         s[0] += (double)__fmul_rn(g, __fdiv_rn(-t, sq));
         return 0.f;
     }
-    __device__ void finalize(const double* s, float) { dv_out[0] = __fmul_rn(2.f, (float)s[0]); }
+    __device__ void finalize(const double* s, const float*) { dv_out[0] = __fmul_rn(2.f, (float)s[0]); }
 };
 
 struct DorefaBwdApply {
@@ -365,7 +386,7 @@ struct DorefaBwdApply {
     __host__ __device__ float* out() const { return dx; }
     __host__ __device__ int add() const { return add_; }
     __device__ void setup() { v = vmax[0]; two_v = __fmul_rn(2.f, v); dvv = dv[0]; }
-    __device__ float apply(float a, float b, int64_t, double*, float&) {
+    __device__ float apply(float a, float b, int64_t, double*, float*) {
         const float t = tanhf(a);
         const float g = __fmul_rn(2.f, b);
         float dt = __fdiv_rn(g, two_v);
@@ -373,7 +394,7 @@ struct DorefaBwdApply {
         dt = __fadd_rn(dt, __fmul_rn(__fmul_rn(ismax, dvv), mx_sign(t)));
         return __fmul_rn(dt, __fsub_rn(1.f, __fmul_rn(t, t)));
     }
-    __device__ void finalize(const double*, float) {}
+    __device__ void finalize(const double*, const float*) {}
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -418,7 +439,7 @@ struct QilFwd {
     __host__ __device__ float* out() const { return y; }
     __host__ __device__ int add() const { return add_; }
     __device__ void setup() { q = qil_params(variant, p0[0], p1[0]); ld = make_level_div(L); }
-    __device__ float apply(float xv, float, int64_t, double*, float&) {
+    __device__ float apply(float xv, float, int64_t, double*, float*) {
         const float ax = fabsf(xv), sg = mx_sign(xv);
         const float inter = __fmul_rn((ax >= q.pp) ? 1.f : 0.f, (ax <= q.cp) ? 1.f : 0.f);
         const float lin = VARIANT3 ? __fdiv_rn(__fsub_rn(ax, q.pp), q.distance)
@@ -427,7 +448,7 @@ struct QilFwd {
         const float code = roundf(__fmul_rn(out, L));
         return div_level(code, ld);
     }
-    __device__ void finalize(const double*, float) {}
+    __device__ void finalize(const double*, const float*) {}
 };
 
 struct QilBwd {
@@ -441,7 +462,7 @@ struct QilBwd {
     __host__ __device__ float* out() const { return dx; }
     __host__ __device__ int add() const { return add_; }
     __device__ void setup() { q = qil_params(variant, p0[0], p1[0]); dsq = __fmul_rn(q.distance, q.distance); }
-    __device__ float apply(float xv, float gy, int64_t, double* s, float&) {
+    __device__ float apply(float xv, float gy, int64_t, double* s, float*) {
         const float ax = fabsf(xv), sg = mx_sign(xv);
         const float inter = __fmul_rn((ax >= q.pp) ? 1.f : 0.f, (ax <= q.cp) ? 1.f : 0.f);
         const float g = __fmul_rn(__fmul_rn(gy, sg), inter);     // d out / d lin
@@ -457,7 +478,7 @@ struct QilBwd {
         }
         return d;
     }
-    __device__ void finalize(const double* s, float) {
+    __device__ void finalize(const double* s, const float*) {
         if (variant == 3) {
             put_scalar(dp0, __fmul_rn((float)s[0], q.pp), req_p0);
             put_scalar(dp1, __fmul_rn((float)s[1], q.distance), req_p1);
@@ -562,20 +583,30 @@ __global__ void selftest_div_level_kernel(unsigned long long* bad) {
     if (local) atomicAdd(bad, local);
 }
 
-// mode 2: count of violations; mode 3: largest x (bit pattern) with tanhf(next(x)) < tanhf(x); mode 4: largest x with
-// tanhf(-x) != -tanhf(x)
+// mode 2: violations of the facts DorefaAbsMax relies on: (a) tanhf(next(x)) >= tanhf(x) for every adjacent pair with
+//         both members OUTSIDE the window W, and across W's borders; (b) tanhf(W's lowest float) <= tanhf(x) <=
+//         tanhf(first float above W) for x in W; (c) tanhf(-x) == -tanhf(x).  mode 3: largest x (bit pattern) with tanhf(next(x)) < tanhf(x), anywhere;
+// mode 4: largest x with tanhf(-x) != -tanhf(x)
 __global__ void selftest_tanh_kernel(unsigned long long* bad, int mode) {
-    // all finite positive floats: tanhf(next(x)) >= tanhf(x) and tanhf(-x) == -tanhf(x)
     unsigned long long local = 0;
     const unsigned int last = 0x7f7fffffu;
+    const float above = tanhf(__uint_as_float(B2Q_TANH_WINDOW_HI + 1u));
+    const float bottom = tanhf(__uint_as_float(B2Q_TANH_WINDOW_LO));
     for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b < last;
          b += (unsigned long long)gridDim.x * blockDim.x) {
         const float x = __uint_as_float((unsigned int)b), xn = __uint_as_float((unsigned int)b + 1u);
         const float t = tanhf(x), tn = tanhf(xn);
         const bool inv = !(tn >= t);
         const bool odd = __float_as_uint(tanhf(-x)) != (__float_as_uint(t) ^ 0x80000000u);
-        if (mode == 2) local += (inv ? 1 : 0) + (odd ? 1 : 0);
-        else if ((mode == 3 && inv) || (mode == 4 && odd)) local = b > local ? b : local;
+        const bool in_w = b >= B2Q_TANH_WINDOW_LO && b <= B2Q_TANH_WINDOW_HI;
+        const bool next_in_w = b + 1 >= B2Q_TANH_WINDOW_LO && b + 1 <= B2Q_TANH_WINDOW_HI;
+        if (mode == 2) {
+            if (inv && !(in_w && next_in_w)) ++local;          // (a) an inversion may only join two members of W
+            if (in_w && !(t <= above && t >= bottom)) ++local; // (b): W's values lie between its bottom and what follows W
+            if (odd) ++local;                                  // (c)
+        } else if ((mode == 3 && inv) || (mode == 4 && odd)) {
+            local = b > local ? b : local;
+        }
     }
     if (local) {
         if (mode == 2) atomicAdd(bad, local);
@@ -703,23 +734,16 @@ int b2q_dorefa_fwd_f32(b2q_ctx* ctx, const float* x, float* y, float* vmax_out, 
     B2Q_CTX(ctx);
     B2Q_REQUIRE(x && y && vmax_out && n >= 1, "bad argument");
     cudaStream_t st = (cudaStream_t)stream;
-    const float* absmax = nullptr;
+    int rc;
     if (ctx->dorefa_tanh_max) {   // element-wise max of |tanh(w)| (PACT.py:48 as written)
         DorefaMax mop = {x, vmax_out};
-        int rc = launch_ew(ctx, mop, n, 4.0, st);
-        if (rc) return rc;
-    } else {                      // tanhf(max|w|): the same float (see DorefaMax), one tanh per element less
-        b2q_slot* slot = b2q_take_slot(ctx);
-        UpdateArgs u;
-        memset(&u, 0, sizeof(u));
-        u.stat_out = slot->scale;
-        int rc = launch_reduce<true>(ctx, slot, x, 1, 1, n, kNoPrescale, u, st);
-        if (rc) return rc;
-        absmax = slot->scale;
+        rc = launch_ew(ctx, mop, n, 4.0, st);
+    } else {                      // max|w| + the window around tanhf's non-monotonic step: the same float, no tanh pass
+        DorefaAbsMax mop = {x, vmax_out};
+        rc = launch_ew(ctx, mop, n, 4.0, st);
     }
-    // req == null still has to leave vmax behind for the backward: the sweep runs without an output
-    DorefaFwd op = {x, req == B2Q_REQ_NULL ? nullptr : y, vmax_out, qlevel, req == B2Q_REQ_ADD, absmax, 0.f, {}};
-    if (req == B2Q_REQ_NULL && absmax == nullptr) return 0;
+    if (rc || req == B2Q_REQ_NULL) return rc;
+    DorefaFwd op = {x, y, vmax_out, qlevel, req == B2Q_REQ_ADD, 0.f, {}};
     return launch_ew(ctx, op, n, 8.0, st);
 }
 

@@ -178,9 +178,8 @@ def GDRQ_fold_bn(name, data, quant_mod="minmax", is_weight_perchannel=False, del
     """Symbol builder of fold_bn_v1_gdrq.py:237-288 (needs MXNet): conv + BatchNorm_v1(output_mean_var) feeding
     the fold-BN custom op.  Quirks kept: ``delay_quant=0`` is hard-wired into the op (:279) and gamma/beta are
     declared with the *input* channel count (:263-266).  Under torch use ``b200quant.harness.FoldBNConv2d``."""
-    from .quant_ops import _need_mx
-    _need_mx()
-    import mxnet as mx
+    from ._mx import mx
+    mx.module()
     if is_weight_perchannel:
         assert quant_mod == "minmax", "currenet weight perchannel only support minmax node with weight"
     assert dict_shapes is not None, "please setting dict_shapes for infer shape"

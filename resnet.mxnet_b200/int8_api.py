@@ -11,10 +11,7 @@ These are graph builders and need MXNet's symbolic API; under torch use ``b200qu
 from .clip_grad_quantization_int8 import *  # noqa: F401,F403  (registers ClipGrad_Quantization_int8)
 from .quant_ops import _need_mx
 
-try:
-    import mxnet as mx
-except Exception:  # pragma: no cover
-    mx = None
+from ._mx import mx
 
 _OP = "ClipGrad_Quantization_int8"
 

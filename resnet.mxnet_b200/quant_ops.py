@@ -11,10 +11,7 @@ shapes as the reference (symbol/quant_ops.py:3-72); the arithmetic runs in libb2
 from . import _kernels as K
 from .operator import CustomOp, CustomOpProp, py_bool, register
 
-try:  # symbol builders need MXNet; the operators do not
-    import mxnet as mx
-except Exception:  # pragma: no cover
-    mx = None
+from ._mx import mx   # resolved at call time: the symbol builders need MXNet, the operators do not
 
 
 class Quantization_int8(CustomOp):
@@ -105,9 +102,7 @@ class QuantizationInt8Prop(_MinMaxProp):
 
 # ---- symbol builders (quant_ops.py:75-121); need MXNet's symbolic API --------------------------------------
 def _need_mx():
-    if mx is None or getattr(mx, "__is_b2q_shim__", False):
-        raise RuntimeError("quant_conv/quant_fc build mx.sym graphs and need MXNet; under torch use "
-                           "b200quant.harness.QuantConv2d / QuantLinear (same node and parameter names)")
+    return mx.module()
 
 
 def get_sym_output_channel(name, sym, data_shape=(1, 3, 224, 224)):

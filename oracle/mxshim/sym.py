@@ -242,6 +242,8 @@ _OPS = {
     "add_n": (None, [], "add_n"),           # variadic
     "Concat": (None, [], "concat"),         # variadic
     "_contrib_BroadcastScale": (["data", "scaler"], [], "broadcastscale"),
+    # fork-only C++ operators (source absent): input slots assumed to mirror the Python twins (minmax / alpha
+    # auxiliary, PACT's gamma an argument)
     "_contrib_Quantization_int8": (["data", "minmax"], ["minmax"], "quantization_int8"),
     "_contrib_GDRQ": (["data", "alpha"], ["alpha"], "gdrq"),
     "_contrib_PACT": (["data", "gamma"], [], "pact"),
@@ -302,8 +304,8 @@ def _make(op, args, kwargs, name, hint=None):
                 inputs.append(given[n]._heads[0])
             else:                                        # auto-created parameter / aux variable
                 inputs.append((_Node("null", "%s_%s" % (name, n), {}, [], is_aux=(n in aux_names)), 0))
-        for n in aux_names:                              # explicitly passed aux inputs keep their variable, flagged aux
-            if n in given and given[n]._heads[0][0].op == "null" and op in ("BatchNorm", "BatchNorm_v1"):
+        for n in aux_names:                              # a variable passed for an aux slot is an auxiliary state
+            if n in given and given[n]._heads[0][0].op == "null":
                 given[n]._heads[0][0].is_aux = True
     nout = 3 if (op in ("BatchNorm", "BatchNorm_v1") and _bool(attrs.get("output_mean_var"))) else 1
     return Symbol([(_Node(op, name, attrs, inputs, nout), 0)])

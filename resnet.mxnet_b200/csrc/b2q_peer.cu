@@ -275,14 +275,16 @@ __device__ __forceinline__ float peer_gather_warp0(const PeerBoxes& pb, unsigned
         const unsigned long long* p = pb.box[pb.rank] + (size_t)(seq & 1u) * B2Q_PEER_MAX_RANKS + lane;
         unsigned long long m = ld_sys_u64(p);
         if ((unsigned int)(m >> 32) != seq) {
+            // The common wait is 2-5 us (NVLink latency + the skew between two ranks' reductions): poll tightly for the
+            // first ~8 us (one warp per CTA polls, so the mailbox line is not swamped), then back off.
             const unsigned long long t0 = global_ns();
-            unsigned int ns = 32;
+            unsigned int polls = 0;
             while (true) {
-                __nanosleep(ns);
+                if (polls < 256) __nanosleep(20);
+                else __nanosleep(polls < 4096 ? 200 : 2000);
                 m = ld_sys_u64(p);
                 if ((unsigned int)(m >> 32) == seq) break;
-                if (ns < 1024) ns += ns;                       // back off: a peer that is late is usually very late
-                if (global_ns() - t0 > timeout_ns) { late = true; break; }
+                if ((++polls & 63u) == 0 && global_ns() - t0 > timeout_ns) { late = true; break; }
             }
         }
         v = late ? __int_as_float(0x7fc00000) : __uint_as_float((unsigned int)(m & 0xffffffffull));

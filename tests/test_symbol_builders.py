@@ -35,9 +35,11 @@ def ns():
     """this repository's builders over the shim (installed as ``mxnet`` for this module only)."""
     saved = {k: sys.modules.get(k) for k in ("mxnet", "mxnet.nd", "mxnet.operator", "mxnet.autograd", "mxnet.init",
                                              "mxnet.sym", "mxnet.symbol")}
-    import oracle.mxshim as shim
-    mx = shim.install()
     import torch
+    grad_mode = torch.is_grad_enabled()
+    import oracle.mxshim as shim          # importing the shim switches autograd off globally (MXNet semantics)
+    mx = shim.install()
+    torch.set_grad_enabled(grad_mode)     # the graph builders need no arrays: leave torch as the other tests expect it
     import b200quant
     from b200quant import fold_bn_v1_gdrq, graph_optimize_sym as go, int8_api, quant_ops
     mx.sym.set_registries(b200quant.REGISTRY)
@@ -115,20 +117,28 @@ def test_rewriter_graph_equals_the_reference_graph_with_python_twins(ns, name):
 
 def test_attach_quantizes_every_input_of_concat_pooling_and_adds_once_per_producer(ns):
     """graph_optimize.py:216-217,261-272: Concat / Pooling / add_n / elemwise_add inputs get data nodes; a producer that
-    feeds several quantized ops (pool0 -> conv1, conv2, add0; conv3 -> add0, addn0) is quantized ONCE."""
-    got = run_case(ns, gc.case_attach_all_ops)
-    custom = [n for n in got["nodes"] if n["op"] == "Custom"]
-    names = [n["name"] for n in custom]
-    assert len(names) == len(set(names))
-    by_name = {n["name"]: n for n in got["nodes"]}
-    for op_node, n_inputs in (("cat0", 2), ("pool0", 1), ("add0", 2), ("addn0", 2)):
-        ins = by_name[op_node]["inputs"]
-        assert len(ins) == n_inputs
-        for src, _ in ins:
-            assert by_name[src]["op"] == "Custom" and by_name[src]["attrs"]["op_type"] == "PACT_PY", (op_node, src)
-    consumers = [n["name"] for n in got["nodes"] if ["pool0", 0] in n["inputs"] and n["op"] != "Custom"]
-    assert consumers == []      # everything reads the quantized pool0, never the raw one
-    assert sum(1 for n in custom if n["inputs"][0] == ["pool0", 0]) == 1
+    feeds several quantized ops (pool0 -> conv1, conv2, add0; conv3 -> add0, addn0) is quantized ONCE.  A quantization
+    node carries the NAME of its producer (:168-195), so names repeat: the check works on node indices."""
+    ns.mx.sym.reset_names()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sym = gc.case_attach_all_ops(ns)
+    nodes = json.loads(sym.tojson())["nodes"]
+    quant = [i for i, n in enumerate(nodes) if n["op"] == "Custom"]
+    producers = [nodes[i]["inputs"][0][0] for i in quant]
+    assert len(producers) == len(set(producers))                     # one quantization node per producer
+    for i in quant:
+        assert nodes[i]["name"] == nodes[nodes[i]["inputs"][0][0]]["name"]
+    for i, n in enumerate(nodes):
+        if n["op"] in ("Concat", "Pooling", "add_n", "elemwise_add"):
+            for src, _, _ in n["inputs"]:
+                assert nodes[src]["op"] == "Custom" and nodes[src]["attrs"]["op_type"] == "PACT_PY", (n["name"], nodes[src])
+        if n["op"] in ("Convolution", "FullyConnected", "Deconvolution"):
+            data, weight = n["inputs"][0][0], n["inputs"][1][0]
+            assert nodes[data]["attrs"]["op_type"] == "PACT_PY" and nodes[weight]["attrs"]["op_type"] == "GDRQ_PY"
+    pool = [i for i, n in enumerate(nodes) if n["op"] == "Pooling"][0]
+    readers = [n for n in nodes if any(e[0] == pool for e in n["inputs"])]
+    assert len(readers) == 1 and readers[0]["op"] == "Custom"        # conv1, conv2 and add0 share that one node
 
 
 def test_reference_failure_modes_are_known_and_this_package_builds_the_node(ns):

@@ -167,6 +167,92 @@ class QuantLinear(_QuantLayer):
         return torch.nn.functional.linear(self.data_quant(x.flatten(1)), self.weight_quant(self.weight), self.bias)
 
 
+class QuantDeconv2d(_QuantLayer):
+    """``clipgrad_quant_deconv`` (symbol/int8_api.py:73-94): weight Variable ``<name>_weight`` of shape
+    (in_channels, num_filter, kh, kw), nodes ``<name>_weight`` / ``<name>_data``, then Deconvolution."""
+
+    def __init__(self, name, in_channels, kernel, stride, pad, num_filter, no_bias=True, quant_mod="minmax",
+                 delay_quant=0, is_weight_perchannel=False, ema_decay=0.99, style="int8_api"):
+        super(QuantDeconv2d, self).__init__()
+        self.stride, self.pad = tuple(stride), tuple(pad)
+        self.weight = nn.Parameter(torch.empty(in_channels, num_filter, kernel[0], kernel[1]))
+        nn.init.kaiming_normal_(self.weight, mode="fan_in", nonlinearity="relu")
+        self.bias = None if no_bias else nn.Parameter(torch.zeros(num_filter))
+        self._make_nodes(name, style, quant_mod, delay_quant, is_weight_perchannel, ema_decay)
+
+    def forward(self, x):
+        return torch.nn.functional.conv_transpose2d(self.data_quant(x), self.weight_quant(self.weight), self.bias,
+                                                    self.stride, self.pad)
+
+
+class _DataNodes(nn.Module):
+    """Activation-only wrappers of symbol/int8_api.py:96-117: ClipGrad data nodes in front of an add / concat, or alone."""
+
+    def _node(self, node_name, quant_mode, delay_quant, ema_decay):
+        q = Custom("ClipGrad_Quantization_int8", quant_mode=quant_mode, is_weight=False, is_weight_perchannel=False,
+                   ema_decay=ema_decay, delay_quant=delay_quant)
+        q.node_name = node_name
+        return q
+
+    def mx_names(self):
+        aux = {}
+        for mod in self.children():
+            if isinstance(mod, Custom):
+                for aname in mod.aux_names:
+                    if getattr(mod, aname, None) is not None:
+                        aux[mod.node_name + "_" + aname] = getattr(mod, aname)
+        return {}, aux
+
+
+class QuantData(_DataNodes):
+    """``clipgrad_quant_data`` (int8_api.py:96-99): node ``<name>_data``."""
+
+    def __init__(self, name, quant_mode="minmax", delay_quant=0, ema_decay=0.99):
+        super(QuantData, self).__init__()
+        self.data_quant = self._node(name + "_data", quant_mode, delay_quant, ema_decay)
+
+    def forward(self, x):
+        return self.data_quant(x)
+
+
+class QuantAdd(_DataNodes):
+    """``clipgrad_quant_add`` (int8_api.py:101-108): nodes ``<name>add_lhs_data`` / ``<name>add_rhs_data`` (no separator,
+    as in the reference), sum ``<name>_plus``."""
+
+    def __init__(self, name, quant_mode="minmax", delay_quant=0, ema_decay=0.99):
+        super(QuantAdd, self).__init__()
+        self.out_name = name + "_plus"
+        self.lhs_quant = self._node(name + "add_lhs_data", quant_mode, delay_quant, ema_decay)
+        self.rhs_quant = self._node(name + "add_rhs_data", quant_mode, delay_quant, ema_decay)
+
+    def forward(self, lhs, rhs):
+        return self.lhs_quant(lhs) + self.rhs_quant(rhs)
+
+
+class QuantConcat(_DataNodes):
+    """``clipgrad_quant_concat`` (int8_api.py:110-117): nodes ``<name>concat_{i}_data``, then concat along ``dim``."""
+
+    def __init__(self, name, num_inputs, dim=1, quant_mode="minmax", delay_quant=0, ema_decay=0.99):
+        super(QuantConcat, self).__init__()
+        self.dim = dim
+        self.out_name = name
+        self.quants = nn.ModuleList([self._node(name + "concat_{}_data".format(i), quant_mode, delay_quant, ema_decay)
+                                     for i in range(num_inputs)])
+
+    def mx_names(self):
+        aux = {}
+        for mod in self.quants:
+            for aname in mod.aux_names:
+                if getattr(mod, aname, None) is not None:
+                    aux[mod.node_name + "_" + aname] = getattr(mod, aname)
+        return {}, aux
+
+    def forward(self, inputs):
+        assert isinstance(inputs, (list, tuple)), "the input fo quantize concat must be a list"
+        assert len(inputs) == len(self.quants)
+        return torch.cat([q(x) for q, x in zip(self.quants, inputs)], dim=self.dim)
+
+
 def export_mx_params(model):
     """(arg_params, aux_params) name -> tensor maps in the reference's checkpoint naming (train.py:218,224-227),
     plus the per-op Python state the reference forgets to save (delay_quant countdown, first-batch init flag)."""
@@ -178,6 +264,12 @@ def export_mx_params(model):
             aux_params.update({k: v.detach() for k, v in x.items()})
             op_state[mod.weight_node_name] = mod.weight_quant.get_extra_state()
             op_state[mod.data_node_name] = mod.data_quant.get_extra_state()
+        elif isinstance(mod, _DataNodes):
+            _, x = mod.mx_names()
+            aux_params.update({k: v.detach() for k, v in x.items()})
+            for q in mod.modules():
+                if isinstance(q, Custom):
+                    op_state[q.node_name] = q.get_extra_state()
     return arg_params, aux_params, op_state
 
 

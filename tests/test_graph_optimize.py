@@ -110,3 +110,150 @@ def test_quant_attrs_schema_validates_reference_settings():
         validate({"quantize_op_name": "PACT", "attrs": {"group_size": "2"}})      # foreign attribute
     with pytest.raises(ValueError):
         validate({"quantize_op_name": "nope", "attrs": {}})
+
+
+# ---- graph-level rewriting (Concat / Pooling / adds), reference-semantics merge_bn, layer twins -------------------
+class GraphNet(nn.Module):
+    """pool0 feeds two convolutions AND the residual add; the branches are concatenated."""
+
+    def __init__(self):
+        super().__init__()
+        self.conv0 = nn.Conv2d(3, 8, 3, padding=1, bias=False)
+        self.bn0 = nn.BatchNorm2d(8)
+        self.pool = nn.MaxPool2d(2)
+        self.a = nn.Conv2d(8, 4, 1, bias=False)
+        self.b = nn.Conv2d(8, 4, 3, padding=1, bias=False)
+        self.c = nn.Conv2d(8, 8, 3, padding=1, bias=False)
+        self.bn1 = nn.BatchNorm2d(8)
+        self.up = nn.ConvTranspose2d(8, 4, 2, stride=2, bias=False)
+        self.fc = nn.Linear(4, 5)
+
+    def forward(self, x):
+        p = self.pool(torch.relu(self.bn0(self.conv0(x))))
+        cat = torch.cat([self.a(p), self.b(p)], 1)
+        y = self.c(self.bn1(cat)) + p
+        return self.fc(self.up(y).mean(dim=(2, 3)))
+
+
+PACT = {"quantize_op_name": "PACT", "init_value": 6.0, "attrs": {"nbits": "4"}}
+GDRQ_W = {"quantize_op_name": "GDRQ", "attrs": {"nbits": "4", "is_weight": "True"}}
+ALL_OPS = ("Convolution", "FullyConnected", "Deconvolution", "Concat", "Pooling", "add_n", "elemwise_add")
+
+
+def test_fx_rewriter_quantizes_concat_pooling_and_add_inputs_once_per_producer():
+    """core/graph_optimize.py:216-217,261-272 on a torch model: data nodes on every input of Concat / Pooling /
+    elemwise_add, named after their producer, shared by all consumers of that producer."""
+    import torch.fx as fx
+    from b200quant.graph_optimize import QuantNode, QuantizedWeightOp, attach_quantize_node
+    gm = attach_quantize_node(GraphNet(), GDRQ_W, PACT, quantized_op=ALL_OPS)
+    assert isinstance(gm, fx.GraphModule)
+    assert gm.quantized_op_counts == {"Convolution": 4, "FullyConnected": 1, "Deconvolution": 1, "Concat": 1, "Pooling": 1,
+                                      "add_n": 0, "elemwise_add": 1}
+    mods = dict(gm.named_modules())
+    nodes = {n.name: n for n in gm.graph.nodes}
+    qnodes = [n for n in gm.graph.nodes if n.op == "call_module" and isinstance(mods[n.target], QuantNode)]
+    producers = [n.args[0].name for n in qnodes]
+    assert len(producers) == len(set(producers))                               # one node per producer
+    assert all(mods[n.target].var_name == n.args[0].name for n in qnodes)       # named like the producer (:168-195)
+    assert len(nodes["pool_quant"].users) == 3                                  # a, b and the residual add share it
+    assert [a.name for a in nodes["cat"].args[0]] == ["a_quant", "b_quant"]
+    assert [a.name for a in nodes["add"].args] == ["c_quant", "pool_quant"]
+    assert nodes["pool"].args[0].name == "relu_quant"
+    for name in ("conv0", "a", "b", "c", "up", "fc"):
+        assert isinstance(mods[name], QuantizedWeightOp) and mods[name].weight_quant.var_name == name + "_weight"
+        assert mods[name].weight_quant.node.op_type == "GDRQ_PY"
+    # skip counts apply per operator kind, in graph order
+    gm2 = attach_quantize_node(GraphNet(), GDRQ_W, PACT, quantized_op=ALL_OPS,
+                               skip_quantize_counts={"Convolution": 1, "Pooling": 1})
+    mods2 = dict(gm2.named_modules())
+    assert isinstance(mods2["conv0"], nn.Conv2d) and isinstance(mods2["a"], QuantizedWeightOp)
+    assert "relu_quant" not in {n.name for n in gm2.graph.nodes}
+
+
+def test_merge_bn_follows_the_dataflow_and_the_reference_semantics():
+    """graph_optimize.py:37-112: only a BatchNorm in inference mode fed by a convolution is replaced, by a per-channel
+    scale and shift (the convolution's weights are untouched); the result equals the BatchNorm it replaces."""
+    from b200quant.graph_optimize import ChannelAffine, merge_bn
+    torch.manual_seed(3)
+    m = GraphNet().eval()
+    with torch.no_grad():
+        for bn in (m.bn0, m.bn1):
+            bn.running_mean.normal_()
+            bn.running_var.uniform_(0.5, 1.5)
+            bn.weight.uniform_(0.5, 1.5)
+            bn.bias.normal_()
+    x = torch.randn(2, 3, 8, 8)
+    want = m(x)
+    w0 = m.conv0.weight.detach().clone()
+    g = merge_bn(m)
+    mods = dict(g.named_modules())
+    assert isinstance(mods["bn0"], ChannelAffine)          # conv0 -> bn0
+    assert isinstance(mods["bn1"], nn.BatchNorm2d)         # fed by a concat, not by a convolution: left alone (:71)
+    assert mods["bn0"].gamma.shape == (1, 8, 1, 1)
+    assert torch.equal(mods["conv0"].weight, w0)
+    torch.testing.assert_close(g(x), want, rtol=1e-5, atol=1e-5)
+    # training-mode BatchNorm (batch statistics) is never folded; affine=False is handled
+    t = nn.Sequential(nn.Conv2d(3, 4, 1), nn.BatchNorm2d(4)).train()
+    assert isinstance(dict(merge_bn(t).named_modules())["1"], nn.BatchNorm2d)
+    e = nn.Sequential(nn.Conv2d(3, 4, 1), nn.BatchNorm2d(4, affine=False)).eval()
+    y = e(x)
+    torch.testing.assert_close(merge_bn(e)(x), y, rtol=1e-5, atol=1e-5)
+    with pytest.raises(AssertionError):
+        merge_bn(nn.Sequential(nn.Conv2d(3, 4, 1), nn.BatchNorm2d(5)).eval())
+
+
+def test_layer_twins_keep_the_int8_api_names():
+    """symbol/int8_api.py:73-117: deconv / data / add / concat wrappers -- node names, aux names, weight layout."""
+    from b200quant.harness import QuantAdd, QuantConcat, QuantData, QuantDeconv2d, export_mx_params
+    net = nn.ModuleDict(dict(up=QuantDeconv2d("up0", 8, (2, 2), (2, 2), (0, 0), 6), d=QuantData("in0", delay_quant=2),
+                             add=QuantAdd("res0"), cat=QuantConcat("cat0", 3)))
+    assert tuple(net["up"].weight.shape) == (8, 6, 2, 2)          # (in_channels, num_filter, kh, kw) (:82-84)
+    assert (net["up"].weight_node_name, net["up"].data_node_name) == ("up0_weight", "up0_data")
+    assert net["d"].data_quant.node_name == "in0_data" and net["d"].data_quant.op.delay_quant == 2
+    assert (net["add"].lhs_quant.node_name, net["add"].rhs_quant.node_name, net["add"].out_name) == \
+        ("res0add_lhs_data", "res0add_rhs_data", "res0_plus")
+    assert [q.node_name for q in net["cat"].quants] == ["cat0concat_0_data", "cat0concat_1_data", "cat0concat_2_data"]
+    assert all(q.op_type == "ClipGrad_Quantization_int8" and not q.op.is_weight for q in net["cat"].quants)
+    _, _, state = export_mx_params(net)
+    assert state["in0_data"]["delay_quant"] == 2 and "res0add_lhs_data" in state
+
+
+@pytest.mark.gpu
+def test_fx_rewritten_model_and_layer_twins_train():
+    from b200quant.graph_optimize import attach_quantize_node, export_quant_params
+    from b200quant.harness import QuantAdd, QuantConcat, QuantData, QuantDeconv2d, export_mx_params
+    torch.manual_seed(1)
+    gm = attach_quantize_node(GraphNet(), GDRQ_W, PACT, quantized_op=ALL_OPS).cuda().train()
+    x = torch.rand(4, 3, 8, 8, device="cuda") * 2 - 1
+    loss = gm(x).square().mean()
+    loss.backward()
+    assert torch.isfinite(loss)
+    args, aux = export_quant_params(gm)
+    assert {"pool_gamma", "relu_gamma", "a_gamma", "b_gamma", "c_gamma", "x_gamma"} <= set(args)
+    assert {"conv0_weight_alpha", "up_weight_alpha", "fc_weight_alpha"} <= set(aux)
+    assert all(p.grad is not None for n, p in gm.named_parameters() if n.endswith("gamma") and "quant" in n)
+
+    class Twins(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.d = QuantData("in0")
+            self.add = QuantAdd("res0")
+            self.cat = QuantConcat("cat0", 2)
+            self.up = QuantDeconv2d("up0", 6, (2, 2), (2, 2), (0, 0), 4)
+
+        def forward(self, x):
+            q = self.d(x)
+            s = self.add(q, x * 0.5)
+            return self.up(self.cat([s, q]))
+
+    t = Twins().cuda().train()
+    xin = (torch.rand(2, 3, 6, 6, device="cuda") * 4 - 2).requires_grad_(True)
+    out = t(xin)
+    assert out.shape == (2, 4, 12, 12)
+    out.sum().backward()
+    assert xin.grad is not None and torch.isfinite(xin.grad).all() and t.up.weight.grad is not None
+    _, aux, _ = export_mx_params(t)
+    assert {"in0_data_minmax", "res0add_lhs_data_minmax", "res0add_rhs_data_minmax", "cat0concat_0_data_minmax",
+            "cat0concat_1_data_minmax", "up0_weight_minmax", "up0_data_minmax"} <= set(aux)
+    # first batch: ClipGrad activations initialise the threshold with max|x| (clip_grad_quantization_int8.py:42-44)
+    assert float(aux["in0_data_minmax"]) == float(xin.detach().abs().max())

@@ -181,6 +181,20 @@ int b2q_foldbn_weight_fwd_f32(b2q_ctx* ctx, const float* w, float* w_q, float* b
                               float eps, int64_t cout, int64_t cols, int per_channel, int quantize,
                               int is_train, void* stream);
 
+/* The step either side of the fold-BN operator.  In the reference's graph
+ * (symbol/fold_bn_v1_gdrq.py:268-287) BatchNorm_v1(output_mean_var=True) reduces the convolution output (n, c, hw) to
+ * its batch mean / variance [upstream batch_norm_v1-inl.h: mean = fl(scale * sum x), var = fl(scale * sum (x-mean)^2),
+ * scale = fl(c / size)], which GDRQ_Fold_BN folds into the weight.  b2q_bn_batch_stats_f32 is that reduction;
+ * b2q_bnstat_foldbn_weight_fwd_f32 does the reduction AND the weight path of b2q_foldbn_weight_fwd_f32 in one launch
+ * when the weight is quantised per out-channel (the block that completes a channel folds and quantises its row),
+ * in two launches otherwise.  mean / var [c] are outputs.                                                   */
+int b2q_bn_batch_stats_f32(b2q_ctx* ctx, const float* y, int64_t n, int64_t c, int64_t hw, float* mean, float* var,
+                           void* stream);
+int b2q_bnstat_foldbn_weight_fwd_f32(b2q_ctx* ctx, const float* conv_out, int64_t n, int64_t c, int64_t hw,
+                                     float* mean, float* var, const float* w, float* w_q, float* bias,
+                                     float* aux_weight, const float* gamma, const float* beta, float eps,
+                                     int64_t cols, int per_channel, int quantize, int is_train, void* stream);
+
 /* QUANT_STE_PY (PACT.py:245-252) and PACT forward (PACT.py:125-128,193-198) are b2q_absmax_f32 + b2q_qdq_f32.
  * CLIP_RELU_PY.forward  core/operator/GDRQ.py:200-204: clip(x, 0, threshold) then QDQ with q (= threshold/L
  * computed by the caller in double like the reference); backward is b2q_mask_bwd_f32(B2Q_MASK_LT, thr_imm). */

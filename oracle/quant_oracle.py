@@ -283,6 +283,22 @@ def conv2d_nchw(x, w, stride, pad, dilate, num_group):
     return y.astype(F)
 
 
+def bn_v1_batch_stats(x):
+    """Batch statistics BatchNorm_v1 emits with output_mean_var=True -- what feeds bn_mean / bn_var of GDRQ_Fold_BN in
+    the reference's graph (/root/reference/symbol/fold_bn_v1_gdrq.py:271-272).
+    [upstream src/operator/batch_norm_v1-inl.h]  scale = fl(C / size);  mean = scale * sumall_except_dim<1>(data);
+    var = scale * sumall_except_dim<1>(square(data - broadcast<1>(mean))): every element-wise step float32, the two
+    reductions modelled as correctly rounded sums (float64 accumulation rounded once), biased variance."""
+    x = fl(x)
+    c = x.shape[1]
+    axes = (0,) + tuple(range(2, x.ndim))
+    scale = F(F(c) / F(x.size))
+    mean = mx_mul(scale, mx_sum(x, axis=axes))
+    dev = mx_sub(x, mean.reshape((1, c) + (1,) * (x.ndim - 2)))
+    var = mx_mul(scale, mx_sum(mx_mul(dev, dev), axis=axes))
+    return mean, var
+
+
 class GDRQ_Fold_BN(_Op):
     def __init__(self, quant_mode, is_weight_perchannel, delay_quant, ema_decay,
                  name, num_filter, num_group, kernel, stride, pad, dilate, no_bias,

@@ -228,6 +228,46 @@ def foldbn_weight_fwd(w, w_q, bias, aux_weight, gamma, beta, mean, var, eps, per
                            current_stream(wb))
 
 
+def _nchw(shape):
+    n, c = int(shape[0]), int(shape[1])
+    hw = 1
+    for d in shape[2:]:
+        hw *= int(d)
+    return n, c, hw
+
+
+def bn_batch_stats(y, mean, var):
+    """BatchNorm_v1(output_mean_var=True) statistics of an (N, C, ...) tensor (fold_bn_v1_gdrq.py:271-272)."""
+    yb, mb, vb = as_buffer(y), as_buffer(mean, write=True), as_buffer(var, write=True)
+    n, c, hw = _nchw(yb.shape)
+    if mb.numel != c or vb.numel != c:
+        raise ValueError("mean / var must have %d elements" % c)
+    on_dev, dev = _same_place(yb, mb, vb)
+    require_device(on_dev, "bn_batch_stats")
+    _lib.context(dev).call("b2q_bn_batch_stats_f32", yb.ptr, n, c, hw, mb.ptr, vb.ptr, current_stream(yb))
+
+
+def bnstat_foldbn_weight_fwd(conv_out, mean, var, w, w_q, bias, aux_weight, gamma, beta, eps, per_channel, quantize,
+                             is_train):
+    """batch statistics of ``conv_out`` -> ``mean`` / ``var`` AND the fold-BN weight path (w_q, bias, aux_weight) that
+    consumes them, in one launch for per-channel weights (fold_bn_v1_gdrq.py:268-287 -> :70-96,113)."""
+    yb, mb, vb = as_buffer(conv_out), as_buffer(mean, write=True), as_buffer(var, write=True)
+    wb, qb, bb = as_buffer(w), as_buffer(w_q, write=True), as_buffer(bias, write=True)
+    ab, g, b = as_buffer(aux_weight, write=True), as_buffer(gamma), as_buffer(beta)
+    n, c, hw = _nchw(yb.shape)
+    cout, cols, _ = _rows_cols(wb.shape)
+    if cout != c:
+        raise ValueError("the convolution output has %d channels, the weight %d rows" % (c, cout))
+    for t in (mb, vb, bb, g, b):
+        if t.numel != c:
+            raise ValueError("per-channel array has %d elements, expected %d" % (t.numel, c))
+    on_dev, dev = _same_place(yb, mb, vb, wb, qb, bb, ab, g, b)
+    require_device(on_dev, "GDRQ_Fold_BN")
+    _lib.context(dev).call("b2q_bnstat_foldbn_weight_fwd_f32", yb.ptr, n, c, hw, mb.ptr, vb.ptr, wb.ptr, qb.ptr, bb.ptr,
+                           ab.ptr, g.ptr, b.ptr, _f32(eps), cols, int(bool(per_channel)), int(bool(quantize)),
+                           int(bool(is_train)), current_stream(yb))
+
+
 def clip_relu_fwd(x, y, threshold, qlevel, req):
     xb, yb = as_buffer(x), as_buffer(y, write=True)
     on_dev, dev = _same_place(xb, yb)

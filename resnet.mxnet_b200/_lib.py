@@ -52,6 +52,8 @@ _CTX_FUNCS = {
     "b2q_gdrq_bwd_f32": [_P, _P, _P, _P, _L, _L, _L, _I, _P],
     "b2q_foldbn_data_fwd_f32": [_P, _P, _P, _L, _I, _F, _F, _P],
     "b2q_foldbn_weight_fwd_f32": [_P, _P, _P, _P, _P, _P, _P, _P, _F, _L, _L, _I, _I, _I, _P],
+    "b2q_bn_batch_stats_f32": [_P, _L, _L, _L, _P, _P, _P],
+    "b2q_bnstat_foldbn_weight_fwd_f32": [_P, _L, _L, _L, _P, _P, _P, _P, _P, _P, _P, _P, _F, _L, _I, _I, _I, _P],
     "b2q_clip_relu_fwd_f32": [_P, _P, _L, _F, _F, _I, _P],
     "b2q_wnq_fwd_f32": [_P, _P, _L, _L, _I, _F, _I, _P],
     "b2q_wnq_bwd_f32": [_P, _P, _P, _L, _L, _I, _I, _P],

@@ -1,0 +1,189 @@
+// the step either side of the fold-BN operator.  In the reference's graph
+// (symbol/fold_bn_v1_gdrq.py:268-287) a BatchNorm_v1(output_mean_var=True) reduces the convolution output to its batch
+// mean / variance, and GDRQ_Fold_BN then folds gamma / sqrt(var + eps) into the weight, quantises it per out-channel and
+// builds the folded bias (:70-96,113): a per-channel reduction over the (N, C, H, W) activation followed by a chain of
+// small per-channel launches.  Here it is ONE kernel: every block reduces one piece of one channel (sum and sum of
+// squares in fp64); the block that completes a channel (per-channel release ticket) turns the partials into mean / var
+// and immediately folds, clips and quantises that channel's weight row and writes its bias -- no second launch, no
+// per-channel host round trip, the statistics never leave the chip between the two steps.
+//
+// Numerics of the statistics [upstream src/operator/batch_norm_v1-inl.h]: scale = fl(C / size);
+// mean = fl(scale * sum(x)); var = fl(scale * sum((x - mean)^2)), sums rounded once.  The squared deviations are
+// accumulated here as SS - 2 mean S + n mean^2 in fp64 (mean = the ROUNDED float32 mean, as the reference subtracts it),
+// which agrees with the reference's fp32 (x - mean)^2 terms to ~1e-7 relative: mean / var carry the 1e-6 tolerance of
+// every mean-derived quantity (BASELINE.json north_star); given equal mean / var the folded, quantised weight and the
+// bias are bit-exact (tests/test_gpu_bnfold.py).
+#include <cstring>
+
+#include "b2q_common.cuh"
+#include "b2q_qdq.cuh"
+#include "b2q_reduce.cuh"
+
+#define B2Q_CTX(ctx)                               \
+    B2Q_REQUIRE((ctx) != nullptr, "null context"); \
+    B2Q_CHECK_CUDA(cudaSetDevice((ctx)->device))
+
+struct BnFold {
+    const float* w;        // [C, cols] or null: statistics only
+    float* w_q;
+    float* bias;
+    float* aux_w;          // [C]
+    const float* gamma;
+    const float* beta;
+    float eps;
+    int64_t cols;
+    int is_train, fast;
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(B2Q_THREADS)
+bnstat_fold_kernel(const float* __restrict__ y, SegPlan pl, b2q_slot* slot, float scale, float* __restrict__ mean_out,
+                   float* __restrict__ var_out, BnFold f) {
+    b2q_pdl_sync();
+    __shared__ double smem[32];
+    __shared__ unsigned int s_ticket;
+    __shared__ float s_val[2];
+    const SegPiece pc = seg_piece(pl);
+    double s = 0.0, ss = 0.0;
+    if (VEC == 8) {
+        const unsigned wpr = (unsigned)((pc.i1 - pc.i0) >> 3);
+        const unsigned total = (unsigned)(pc.o1 - pc.o0) * wpr;
+        for (unsigned w0 = threadIdx.x; w0 < total; w0 += 4 * blockDim.x) {
+            f8 v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const unsigned w = w0 + k * blockDim.x;
+                if (w < total) {
+                    const unsigned o = w / wpr, i = w - o * wpr;
+                    v[k] = ld_f8<0>(y + ((pc.o0 + o) * pl.groups + pc.g) * pl.inner + pc.i0 + 8 * (int64_t)i);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[k].v[e] = 0.f;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                for (int e = 0; e < 8; e += 2) {
+                    const double a = (double)v[k].v[e], b = (double)v[k].v[e + 1];
+                    s += a + b;
+                    ss += a * a + b * b;
+                }
+            }
+        }
+    } else {
+        for (int64_t o = pc.o0; o < pc.o1; ++o) {
+            const float* base = y + (o * pl.groups + pc.g) * pl.inner;
+            for (int64_t i = pc.i0 + threadIdx.x; i < pc.i1; i += blockDim.x) {
+                const double a = (double)base[i];
+                s += a;
+                ss += a * a;
+            }
+        }
+    }
+    const double bs = block_reduce<false>(s, smem);
+    const double bss = block_reduce<false>(ss, smem);
+    const int SP = pl.S * pl.P;
+    const int c = (int)pc.g;
+    if (threadIdx.x == 0) {
+        slot->partial[2 * blockIdx.x] = bs;
+        slot->partial[2 * blockIdx.x + 1] = bss;
+        s_ticket = b2q_take_ticket(&slot->row_ticket[c], (unsigned)SP - 1u);
+    }
+    __syncthreads();
+    if (s_ticket != (unsigned)SP - 1u) return;
+    // ---- this block completes channel c: statistics in a fixed order ----
+    double a = 0.0, b = 0.0;
+    for (int l = threadIdx.x; l < SP; l += blockDim.x) {
+        a += __ldcg(&slot->partial[2 * ((int64_t)c * SP + l)]);
+        b += __ldcg(&slot->partial[2 * ((int64_t)c * SP + l) + 1]);
+    }
+    const double S = block_reduce<false>(a, smem);
+    const double SS = block_reduce<false>(b, smem);
+    if (threadIdx.x == 0) {
+        const double n = (double)(pl.outer * pl.inner);
+        const float mean = __fmul_rn(scale, (float)S);
+        const double dm = (double)mean;
+        const double dev = SS - 2.0 * dm * S + n * dm * dm;          // sum of (x - mean)^2
+        s_val[0] = mean;
+        s_val[1] = __fmul_rn(scale, (float)(dev > 0.0 ? dev : 0.0));
+        mean_out[c] = s_val[0];
+        var_out[c] = s_val[1];
+        slot->row_ticket[c] = 0;
+    }
+    __syncthreads();
+    if (f.w == nullptr) return;
+    // ---- fold-BN weight path of channel c (symbol/fold_bn_v1_gdrq.py:70-96,113), same arithmetic as rows_*_kernel ----
+    const float mean = s_val[0], var = s_val[1];
+    const float den = __fsqrt_rn(__fadd_rn(var, f.eps));
+    const float factor = __fdiv_rn(f.gamma[c], den);                  // :72
+    const float* wr = f.w + (int64_t)c * f.cols;
+    float* qr = f.w_q + (int64_t)c * f.cols;
+    double acc = 0.0;
+    for (int64_t i = threadIdx.x; i < f.cols; i += blockDim.x) acc += (double)fabsf(__fmul_rn(wr[i], factor));
+    const double tot = block_reduce<false>(acc, smem);
+    if (threadIdx.x == 0) {
+        const float T = __fmul_rn(2.f, __fdiv_rn((float)tot, (float)f.cols));   // :82
+        s_val[0] = T;
+        if (f.is_train && f.aux_w) f.aux_w[c] = T;                               // :94-95
+        if (f.bias) f.bias[c] = __fsub_rn(f.beta[c], __fdiv_rn(__fmul_rn(mean, f.gamma[c]), den));   // :113
+    }
+    __syncthreads();
+    const float T = s_val[0];
+    const QScale qs = make_qscale(T, 127.f, f.fast != 0);
+    for (int64_t i = threadIdx.x; i < f.cols; i += blockDim.x) {
+        const float v = mx_clip(__fmul_rn(wr[i], factor), -T, T);
+        qr[i] = __fmul_rn(quant_code(v, qs), qs.q);
+    }
+}
+
+static int launch_bnstat(b2q_ctx* ctx, const float* y, int64_t n, int64_t c, int64_t hw, float* mean, float* var, BnFold f,
+                         cudaStream_t st) {
+    B2Q_REQUIRE(y && mean && var && n >= 1 && c >= 1 && hw >= 1, "bad argument");
+    B2Q_REQUIRE(c <= B2Q_MAX_GROUPS, "too many channels (max 8192)");
+    SegPlan pl = b2q_seg_plan(y, nullptr, n, c, hw, ctx->num_sms * 16);
+    while ((int64_t)c * pl.S * pl.P > B2Q_MAX_PIECES / 2 && pl.S > 1) --pl.S;   // two partials per piece
+    B2Q_REQUIRE((int64_t)c * pl.S * pl.P <= B2Q_MAX_PIECES / 2, "activation too large for one statistics launch");
+    // fl(C / size) as batch_norm_v1-inl.h computes it: two float operands
+    const float scale = (float)c / (float)((double)n * (double)c * (double)hw);
+    const unsigned grid = (unsigned)(c * pl.S * pl.P);
+    b2q_slot* slot = b2q_take_slot(ctx);
+    b2q_timed_launch tl(ctx, B2Q_KIND_OTHER, 4.0 * (double)(n * c * hw), st);
+    const bool vec8 = (hw % 8 == 0) && (pl.part % 8 == 0) && ((((uintptr_t)y) & 31) == 0);
+    if (vec8) b2q_launch(ctx, bnstat_fold_kernel<8>, grid, B2Q_THREADS, st, y, pl, slot, scale, mean, var, f);
+    else b2q_launch(ctx, bnstat_fold_kernel<1>, grid, B2Q_THREADS, st, y, pl, slot, scale, mean, var, f);
+    B2Q_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+extern "C" {
+
+int b2q_bn_batch_stats_f32(b2q_ctx* ctx, const float* y, int64_t n, int64_t c, int64_t hw, float* mean, float* var,
+                           void* stream) {
+    B2Q_CTX(ctx);
+    BnFold none;
+    memset(&none, 0, sizeof(none));
+    return launch_bnstat(ctx, y, n, c, hw, mean, var, none, (cudaStream_t)stream);
+}
+
+int b2q_bnstat_foldbn_weight_fwd_f32(b2q_ctx* ctx, const float* conv_out, int64_t n, int64_t c, int64_t hw, float* mean,
+                                     float* var, const float* w, float* w_q, float* bias, float* aux_weight,
+                                     const float* gamma, const float* beta, float eps, int64_t cols, int per_channel,
+                                     int quantize, int is_train, void* stream) {
+    B2Q_CTX(ctx);
+    B2Q_REQUIRE(w && w_q && bias && gamma && beta && cols >= 1, "bad argument");
+    if (per_channel && quantize) {
+        B2Q_REQUIRE(aux_weight != nullptr, "null aux");
+        BnFold f = {w, w_q, bias, aux_weight, gamma, beta, eps, cols, is_train, ctx->fast_div};
+        return launch_bnstat(ctx, conv_out, n, c, hw, mean, var, f, (cudaStream_t)stream);
+    }
+    // per-tensor threshold (needs every channel's statistics) or no quantisation: statistics, then the weight kernels
+    BnFold none;
+    memset(&none, 0, sizeof(none));
+    int rc = launch_bnstat(ctx, conv_out, n, c, hw, mean, var, none, (cudaStream_t)stream);
+    if (rc) return rc;
+    return b2q_foldbn_weight_fwd_f32(ctx, w, w_q, bias, aux_weight, gamma, beta, mean, var, eps, c, cols, per_channel,
+                                     quantize, is_train, stream);
+}
+
+}  // extern "C"

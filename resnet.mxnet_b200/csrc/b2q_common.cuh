@@ -23,6 +23,7 @@ struct b2q_slot {
     float scale[B2Q_MAX_GROUPS];  // threshold T the following QDQ kernel scales with (when it is not aux)
     float clip[B2Q_MAX_GROUPS];   // threshold the following QDQ kernel clips with (when it differs)
     double partial[B2Q_MAX_PIECES];
+    unsigned int row_ticket[B2Q_MAX_GROUPS];   // per-channel "last block finishes" tickets (bnstat_fold_kernel); self-resetting
 };
 
 // Optional per-kernel timing (option "timing"): CUDA events around every launch of the flat kernels, read

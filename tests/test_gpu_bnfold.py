@@ -1,0 +1,82 @@
+"""batch statistics of the convolution output (BatchNorm_v1 with output_mean_var) and the fold-BN
+weight path that consumes them, in one launch -- against the oracle.  Two-stage parity: mean / var
+are mean-derived quantities (1e-6 relative, BASELINE.json north_star); given the SAME mean / var the folded, quantised
+weight, its per-channel thresholds and the bias are bit-exact."""
+import numpy as np
+import pytest
+
+from oracle import quant_oracle as qo
+from tests.golden_util import bits_equal
+
+pytestmark = pytest.mark.gpu
+F = np.float32
+
+
+def dev(T, a):
+    return T.from_numpy(np.ascontiguousarray(a, dtype=F)).cuda()
+
+
+@pytest.mark.parametrize("shape", [(8, 16, 14, 14), (4, 32, 7, 7), (3, 5, 9, 11), (256, 64, 56, 56), (32, 1024, 7, 7),
+                                   (2, 8, 1, 1)])
+def test_batch_stats_match_batchnorm_v1(shape):
+    import torch as T
+    import b200quant._kernels as K
+    g = T.Generator(device="cuda").manual_seed(3)
+    y = T.empty(shape, device="cuda").normal_(0.3, 1.7, generator=g)
+    mean, var = T.empty(shape[1], device="cuda"), T.empty(shape[1], device="cuda")
+    K.bn_batch_stats(y, mean, var)
+    m_r, v_r = qo.bn_v1_batch_stats(y.cpu().numpy())
+    np.testing.assert_allclose(mean.cpu().numpy(), m_r, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(var.cpu().numpy(), v_r, rtol=1e-6)
+    # deterministic: fixed partition, fixed combination order
+    m2, v2 = T.empty_like(mean), T.empty_like(var)
+    K.bn_batch_stats(y, m2, v2)
+    assert T.equal(mean, m2) and T.equal(var, v2)
+    # and it is the library's biased batch variance
+    want = y.double().var(dim=(0, 2, 3), unbiased=False)
+    T.testing.assert_close(var.double(), want, rtol=2e-6, atol=0)
+
+
+@pytest.mark.parametrize("cfg", [dict(n=8, cin=16, cout=32, k=3, group=1, hw=14, pc=True),
+                                 dict(n=8, cin=32, cout=32, k=3, group=32, hw=14, pc=True),       # depthwise: rows of 9
+                                 dict(n=4, cin=64, cout=128, k=1, group=1, hw=7, pc=True),
+                                 dict(n=4, cin=16, cout=24, k=3, group=1, hw=9, pc=False),        # per-tensor: two launches
+                                 dict(n=2, cin=512, cout=512, k=3, group=1, hw=4, pc=True)])      # rows of 4608
+@pytest.mark.parametrize("is_train", [True, False])
+def test_fused_batchstat_fold_quantise(cfg, is_train):
+    import torch as T
+    import b200quant._kernels as K
+    from b200quant import _lib
+    rng = np.random.default_rng(11)
+    n, cin, cout, k, hw = cfg["n"], cfg["cin"], cfg["cout"], cfg["k"], cfg["hw"]
+    w = (rng.standard_normal((cout, cin // cfg["group"], k, k)) * 0.2).astype(F)
+    conv_out = (rng.standard_normal((n, cout, hw, hw)) * 1.3 + 0.2).astype(F)
+    gamma, beta = rng.uniform(0.5, 1.5, cout).astype(F), rng.standard_normal(cout).astype(F)
+    naux = cout if cfg["pc"] else 1
+    wq, bias, aux = dev(T, np.zeros_like(w)), dev(T, np.zeros(cout, F)), dev(T, np.full(naux, 7.0, F))
+    mean, var = dev(T, np.zeros(cout, F)), dev(T, np.zeros(cout, F))
+    ctx = _lib.context(0)
+    l0 = ctx.launch_count()
+    K.bnstat_foldbn_weight_fwd(dev(T, conv_out), mean, var, dev(T, w), wq, bias, aux, dev(T, gamma), dev(T, beta), 1e-5,
+                               cfg["pc"], True, is_train)
+    launches = ctx.launch_count() - l0
+    assert launches == (1 if cfg["pc"] else 3)            # per-channel: ONE launch for statistics + fold + QDQ + bias
+    m_r, v_r = qo.bn_v1_batch_stats(conv_out)
+    np.testing.assert_allclose(mean.cpu().numpy(), m_r, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(var.cpu().numpy(), v_r, rtol=1e-6)
+    # stage 2: the oracle's fold-BN weight path (fold_bn_v1_gdrq.py:70-96,113; oracle/c is bit-equal to the NumPy oracle,
+    # tests/test_oracle_c.py) fed the statistics the kernel produced -> bit-exact
+    from oracle import c_oracle as co
+    wq_r, bias_r, aux_r = np.zeros_like(w), np.zeros(cout, F), np.full(naux, 7.0, F)
+    co.foldbn_weight_fwd(w, wq_r, bias_r, aux_r, gamma, beta, mean.cpu().numpy(), var.cpu().numpy(), 1e-5, cfg["pc"], True,
+                         is_train)
+    assert bits_equal(wq.cpu().numpy(), wq_r)
+    assert bits_equal(bias.cpu().numpy(), bias_r)
+    assert bits_equal(aux.cpu().numpy(), aux_r)
+    if not is_train:
+        assert float(aux.min()) == 7.0        # thresholds are stored only when training (:94-95)
+    # and it equals the stand-alone weight entry point on the same statistics
+    wq2, bias2, aux2 = dev(T, np.zeros_like(w)), dev(T, np.zeros(cout, F)), dev(T, np.full(naux, 7.0, F))
+    K.foldbn_weight_fwd(dev(T, w), wq2, bias2, aux2, dev(T, gamma), dev(T, beta), mean, var, 1e-5, cfg["pc"], True, is_train)
+    assert T.equal(wq.view(T.int32), wq2.view(T.int32)) and T.equal(bias.view(T.int32), bias2.view(T.int32))
+    assert T.equal(aux.view(T.int32), aux2.view(T.int32))

@@ -103,10 +103,17 @@ class GDRQ_Fold_BN(CustomOp):
             self.init = False
         else:
             data_q = data
-        weight_q = self._empty_like(weight)
-        bias = self._empty_like(bn_beta, (self.num_filter,))
-        K.foldbn_weight_fwd(weight, weight_q, bias, aux[1], bn_gamma, bn_beta, bn_mean, bn_var, self.eps,
-                            self.is_weight_perchannel, self.quantize_flag, is_train)   # :70-96, :113
+        pre = getattr(self, "_prefolded", None)
+        if pre is not None:
+            # the caller produced bn_mean / bn_var WITH the fused statistics + fold kernel
+            # (b2q_bnstat_foldbn_weight_fwd_f32, harness.FoldBNConv2d): the weight path is already done for this call
+            weight_q, bias = pre
+            self._prefolded = None
+        else:
+            weight_q = self._empty_like(weight)
+            bias = self._empty_like(bn_beta, (self.num_filter,))
+            K.foldbn_weight_fwd(weight, weight_q, bias, aux[1], bn_gamma, bn_beta, bn_mean, bn_var, self.eps,
+                                self.is_weight_perchannel, self.quantize_flag, is_train)   # :70-96, :113
         self.data_q, self.weight_q, self.bias = data_q, weight_q, bias
         self.assign(out_data[0], req[0], self._conv(data_q, weight_q, bias))   # :99-120
 

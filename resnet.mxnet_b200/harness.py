@@ -253,6 +253,73 @@ class QuantConcat(_DataNodes):
         return torch.cat([q(x) for q, x in zip(self.quants, inputs)], dim=self.dim)
 
 
+class FoldBNConv2d(nn.Module):
+    """``GDRQ_fold_bn`` (symbol/fold_bn_v1_gdrq.py:237-288) as a torch module: convolution -> BatchNorm with batch
+    statistics (``BatchNorm_v1(output_mean_var=True)``) -> the ``GDRQ_Fold_BN`` operator fed (data, weight, bn_output,
+    gamma, beta, mean, var).  Names: weight ``<name>_conv2d_weight``, ``<name>_batchnorm_gamma`` / ``_beta`` (+ moving
+    statistics), node ``<name>_fold_bn`` with aux ``data_minmax`` / ``weight_minmax``.  The gradient reaches the
+    parameters through ``bn_output`` only, as in the reference (:122-129).  gamma / beta have ``num_filter`` elements
+    (the reference declares them with the INPUT channel count, :263-266, which only binds when the two agree).
+    ``fused=True`` (default): batch statistics, fold, per-channel weight quantisation and bias come from ONE launch
+    (``b2q_bnstat_foldbn_weight_fwd_f32``); ``fused=False`` computes the statistics with the
+    stand-alone kernel and lets the operator run its own weight path -- same bits."""
+
+    def __init__(self, name, in_channels, num_filter, kernel, stride=(1, 1), pad=(0, 0), dilate=(1, 1), num_group=1,
+                 quant_mod="minmax", is_weight_perchannel=False, ema_decay=0.99, eps=1e-5, momentum=0.9,
+                 fix_gamma=False, use_global_stats=False, quantize_flag=True, fused=True):
+        super(FoldBNConv2d, self).__init__()
+        self.layer_name = name
+        self.stride, self.pad, self.dilate, self.num_group = tuple(stride), tuple(pad), tuple(dilate), int(num_group)
+        self.eps, self.momentum, self.use_global_stats, self.fused = float(eps), float(momentum), use_global_stats, fused
+        self.per_channel, self.quantize_flag = bool(is_weight_perchannel), bool(quantize_flag)
+        self.weight = nn.Parameter(torch.empty(num_filter, in_channels // num_group, kernel[0], kernel[1]))
+        nn.init.kaiming_normal_(self.weight, mode="fan_in", nonlinearity="relu")
+        self.gamma = nn.Parameter(torch.ones(num_filter), requires_grad=not fix_gamma)
+        self.beta = nn.Parameter(torch.zeros(num_filter))
+        self.register_buffer("moving_mean", torch.zeros(num_filter))
+        self.register_buffer("moving_var", torch.ones(num_filter))
+        self.fold_bn = Custom("GDRQ_Fold_BN", quant_mode=quant_mod, is_weight_perchannel=is_weight_perchannel,
+                              delay_quant=0, ema_decay=ema_decay, name=name, num_filter=num_filter, num_group=num_group,
+                              kernel=tuple(kernel), stride=tuple(stride), pad=tuple(pad), dilate=tuple(dilate),
+                              no_bias=True, eps=eps, momentum=momentum, fix_gamma=fix_gamma, quantize_flag=quantize_flag)
+
+    def mx_names(self):
+        n = self.layer_name
+        args = {n + "_conv2d_weight": self.weight, n + "_batchnorm_gamma": self.gamma, n + "_batchnorm_beta": self.beta}
+        aux = {n + "_batchnorm_moving_mean": self.moving_mean, n + "_batchnorm_moving_var": self.moving_var}
+        for aname in self.fold_bn.aux_names:
+            if getattr(self.fold_bn, aname, None) is not None:
+                aux[n + "_fold_bn_" + aname] = getattr(self.fold_bn, aname)
+        return args, aux
+
+    def forward(self, x):
+        from . import _kernels as K
+        conv = torch.nn.functional.conv2d(x, self.weight, None, self.stride, self.pad, self.dilate, self.num_group)
+        c = conv.shape[1]
+        if self.training and not self.use_global_stats:
+            mean, var = torch.empty(c, device=x.device), torch.empty(c, device=x.device)
+            cd = conv.detach().contiguous()
+            if self.fused and self.quantize_flag and self.per_channel:
+                node = self.fold_bn
+                probe = [x.detach(), self.weight.detach(), cd, self.gamma.detach(), self.beta.detach(), mean, var]
+                node._ensure_aux(probe)
+                w_q, bias = torch.empty_like(self.weight), torch.empty(c, device=x.device)
+                K.bnstat_foldbn_weight_fwd(cd, mean, var, self.weight.detach(), w_q, bias, node.weight_minmax,
+                                           self.gamma.detach(), self.beta.detach(), self.eps, True, True, True)
+                node.op._prefolded = (w_q, bias)
+            else:
+                K.bn_batch_stats(cd, mean, var)
+            with torch.no_grad():   # [upstream batch_norm_v1-inl.h] moving = moving * momentum + batch * (1 - momentum)
+                self.moving_mean.mul_(self.momentum).add_(mean, alpha=1 - self.momentum)
+                self.moving_var.mul_(self.momentum).add_(var, alpha=1 - self.momentum)
+        else:
+            mean, var = self.moving_mean, self.moving_var
+        shape = (1, -1, 1, 1)
+        bn_out = (conv - mean.view(shape)) / torch.sqrt(var.view(shape) + self.eps) * self.gamma.view(shape) \
+            + self.beta.view(shape)
+        return self.fold_bn(x, self.weight, bn_out, self.gamma, self.beta, mean, var)
+
+
 def export_mx_params(model):
     """(arg_params, aux_params) name -> tensor maps in the reference's checkpoint naming (train.py:218,224-227),
     plus the per-op Python state the reference forgets to save (delay_quant countdown, first-batch init flag)."""
@@ -264,6 +331,11 @@ def export_mx_params(model):
             aux_params.update({k: v.detach() for k, v in x.items()})
             op_state[mod.weight_node_name] = mod.weight_quant.get_extra_state()
             op_state[mod.data_node_name] = mod.data_quant.get_extra_state()
+        elif isinstance(mod, FoldBNConv2d):
+            a, x = mod.mx_names()
+            arg_params.update({k: v.detach() for k, v in a.items()})
+            aux_params.update({k: v.detach() for k, v in x.items()})
+            op_state[mod.layer_name + "_fold_bn"] = mod.fold_bn.get_extra_state()
         elif isinstance(mod, _DataNodes):
             _, x = mod.mx_names()
             aux_params.update({k: v.detach() for k, v in x.items()})

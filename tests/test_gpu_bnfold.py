@@ -80,3 +80,36 @@ def test_fused_batchstat_fold_quantise(cfg, is_train):
     K.foldbn_weight_fwd(dev(T, w), wq2, bias2, aux2, dev(T, gamma), dev(T, beta), mean, var, 1e-5, cfg["pc"], True, is_train)
     assert T.equal(wq.view(T.int32), wq2.view(T.int32)) and T.equal(bias.view(T.int32), bias2.view(T.int32))
     assert T.equal(aux.view(T.int32), aux2.view(T.int32))
+
+
+@pytest.mark.parametrize("group", [1, 16])
+def test_foldbn_layer_twin_fused_equals_unfused_and_trains(group):
+    """harness.FoldBNConv2d (GDRQ_fold_bn, fold_bn_v1_gdrq.py:237-288): the fused statistics+fold launch and the
+    operator's own weight path give the same bits; the gradient reaches weight / gamma / beta through bn_output."""
+    import torch as T
+    from b200quant.harness import FoldBNConv2d, export_mx_params
+    outs = []
+    for fused in (True, False):
+        T.manual_seed(5)
+        layer = FoldBNConv2d("stage1", 16, 16, (3, 3), pad=(1, 1), num_group=group, is_weight_perchannel=True,
+                             fused=fused).cuda().train()
+        x = (T.rand(4, 16, 10, 10, device="cuda", generator=T.Generator(device="cuda").manual_seed(1)) * 2 - 1)
+        x.requires_grad_(True)
+        ys = []
+        for _ in range(2):            # first batch initialises data_minmax, second takes the EMA branch
+            y = layer(x)
+            ys.append(y.detach().clone())
+        y.square().mean().backward()
+        outs.append((ys, layer.weight.grad.clone(), layer.gamma.grad.clone(), layer.beta.grad.clone(), x.grad.clone(),
+                     export_mx_params(layer)[1]))
+        assert T.isfinite(layer.weight.grad).all() and float(layer.weight.grad.abs().sum()) > 0
+        assert float(layer.moving_var.mean()) != 1.0
+    (ya, wa, ga, ba, xa, auxa), (yb, wb, gb, bb, xb, auxb) = outs
+    for a, b in zip(ya, yb):
+        assert T.equal(a.view(T.int32), b.view(T.int32))
+    for a, b in ((wa, wb), (ga, gb), (ba, bb), (xa, xb)):
+        assert T.equal(a, b)
+    assert sorted(auxa) == sorted(auxb) == ["stage1_batchnorm_moving_mean", "stage1_batchnorm_moving_var",
+                                            "stage1_fold_bn_data_minmax", "stage1_fold_bn_weight_minmax"]
+    for k in auxa:
+        assert T.equal(auxa[k], auxb[k]), k

@@ -297,6 +297,23 @@ int b2q_peer_meanabs_quant_fwd_f32(b2q_ctx* ctx, int upd_mode, const float* x, f
                                    float p0, float p1, float qlevel, void* const* mailboxes, int rank, int world,
                                    void* stream);
 
+/* ---- one process, N devices (the reference's layout: train.py:34, core/solver.py:58-61) ---------------------------
+ * The same two exchanges without torch.distributed, NCCL or CUDA IPC.  b2q_comm_create takes one context per device,
+ * enables peer access between them and allocates a mailbox per rank; b2q_comm_mailboxes(comm, r, &boxes) yields the
+ * table rank r passes to b2q_peer_minmax_quant_fwd_f32 / b2q_peer_meanabs_quant_fwd_f32 (world = b2q_comm_size), so
+ * the fused threshold exchange works unchanged.  b2q_comm_allreduce_{max,sum}_f32 reduce one float32 buffer per rank
+ * in place (bufs[r] on rank r's device, streams[r] its stream): rank r's kernel reads slice r from every rank over
+ * NVLink, combines in rank order and stores the result into every rank's buffer -- bit-identical results everywhere,
+ * stream-ordered across devices by events, asynchronous.  sum: KVStore 'device' semantics (solver.py:121); average != 0
+ * divides by the rank count.                                                                                  */
+typedef struct b2q_comm b2q_comm;
+int b2q_comm_create(b2q_ctx* const* ctxs, int n, b2q_comm** out);
+int b2q_comm_destroy(b2q_comm* comm);
+int b2q_comm_size(b2q_comm* comm);
+int b2q_comm_mailboxes(b2q_comm* comm, int rank, void* const** mailboxes);
+int b2q_comm_allreduce_max_f32(b2q_comm* comm, float* const* bufs, int64_t count, void* const* streams);
+int b2q_comm_allreduce_sum_f32(b2q_comm* comm, float* const* bufs, int64_t count, int average, void* const* streams);
+
 /* ---- host-buffer path: the call a framework whose tensors live in HOST memory makes (bench.py "e2e") --
  * Same semantics as the device entry points but x / y / aux are HOST pointers (pinned for full speed).
  * Each call stages its tensor through a device staging ring on three internal streams

@@ -92,6 +92,13 @@ _PLAIN_FUNCS = {
     "b2q_last_error": ([], ctypes.c_char_p),
     "b2q_create": ([_I, ctypes.POINTER(ctypes.c_void_p)], _I),
     "b2q_launch_count": ([ctypes.c_void_p], _L),
+    # one process, N devices (b2q_comm): not bound to a single context
+    "b2q_comm_create": ([ctypes.POINTER(ctypes.c_void_p), _I, ctypes.POINTER(ctypes.c_void_p)], _I),
+    "b2q_comm_destroy": ([ctypes.c_void_p], _I),
+    "b2q_comm_size": ([ctypes.c_void_p], _I),
+    "b2q_comm_mailboxes": ([ctypes.c_void_p, _I, ctypes.POINTER(ctypes.POINTER(ctypes.c_void_p))], _I),
+    "b2q_comm_allreduce_max_f32": ([ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), _L, ctypes.POINTER(ctypes.c_void_p)], _I),
+    "b2q_comm_allreduce_sum_f32": ([ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), _L, _I, ctypes.POINTER(ctypes.c_void_p)], _I),
 }
 ALL_SYMBOLS = sorted(list(_CTX_FUNCS) + list(_PLAIN_FUNCS))
 

@@ -85,6 +85,7 @@ static int* option_slot(b2q_ctx* ctx, const char* key) {
     if (!strcmp(key, "timing")) return &ctx->timing;
     if (!strcmp(key, "dorefa_tanh_max")) return &ctx->dorefa_tanh_max;
     if (!strcmp(key, "host_ste_copy")) return &ctx->host_ste_copy;
+    if (!strcmp(key, "shared_slot_rings")) return &ctx->shared_rings;
     if (!strcmp(key, "resident")) return &ctx->resident;
     if (!strcmp(key, "resident_max_mb")) return &ctx->resident_max_mb;
     if (!strcmp(key, "peer_mode")) return &ctx->peer_mode;
@@ -110,6 +111,7 @@ int b2q_timing_read_range(b2q_ctx* ctx, int kind, double min_bytes, double max_b
     B2Q_REQUIRE(kind >= 0 && kind < B2Q_NKINDS, "bad kind");
     double ms = 0.0, bytes = 0.0;
     int64_t n = 0;
+    std::lock_guard<std::mutex> lk(ctx->mu);
     for (const b2q_timing_rec& r : ctx->recs) {
         if (kind != 0 && r.kind != kind) continue;
         if (r.bytes < min_bytes || (max_bytes > 0.0 && r.bytes >= max_bytes)) continue;
@@ -154,7 +156,7 @@ int b2q_absmax_f32(b2q_ctx* ctx, const float* x, int64_t outer, int64_t groups, 
                    void* stream) {
     B2Q_CTX(ctx);
     B2Q_REQUIRE(x && stat, "null pointer");
-    return launch_reduce<true>(ctx, b2q_take_slot(ctx), x, outer, groups, inner, kNoPrescale, stat_only(stat),
+    return launch_reduce<true>(ctx, b2q_take_slot(ctx, (cudaStream_t)stream), x, outer, groups, inner, kNoPrescale, stat_only(stat),
                                (cudaStream_t)stream);
 }
 
@@ -162,7 +164,7 @@ int b2q_meanabs_f32(b2q_ctx* ctx, const float* x, int64_t outer, int64_t groups,
                     void* stream) {
     B2Q_CTX(ctx);
     B2Q_REQUIRE(x && stat, "null pointer");
-    return launch_reduce<false>(ctx, b2q_take_slot(ctx), x, outer, groups, inner, kNoPrescale, stat_only(stat),
+    return launch_reduce<false>(ctx, b2q_take_slot(ctx, (cudaStream_t)stream), x, outer, groups, inner, kNoPrescale, stat_only(stat),
                                 (cudaStream_t)stream);
 }
 
@@ -280,7 +282,7 @@ int b2q_minmax_quant_fwd_f32(b2q_ctx* ctx, int variant, const float* x, float* y
     int eff_req = req;
     if (clip) eff_req = B2Q_REQ_WRITE;
     if (reduce) {
-        b2q_slot* slot = b2q_take_slot(ctx);
+        b2q_slot* slot = b2q_take_slot(ctx, st);
         UpdateArgs u = minmax_update(variant, is_weight, is_train, init, ema_decay, one_minus_decay, aux, slot, &scale_src);
         if (groups == 1 && (eff_req == B2Q_REQ_WRITE || eff_req == B2Q_REQ_INPLACE)) {
             // fused: partial maxima + a sweep that finishes the threshold update itself (no serialized tail)
@@ -318,7 +320,7 @@ int b2q_minmax_quant_stat_f32(b2q_ctx* ctx, const float* x, int64_t rows, int64_
     B2Q_REQUIRE(x && stat_out, "null pointer");
     int64_t outer, groups, inner;
     minmax_groups(rows, cols, per_channel, &outer, &groups, &inner);
-    return launch_reduce<true>(ctx, b2q_take_slot(ctx), x, outer, groups, inner, kNoPrescale, stat_only(stat_out),
+    return launch_reduce<true>(ctx, b2q_take_slot(ctx, (cudaStream_t)stream), x, outer, groups, inner, kNoPrescale, stat_only(stat_out),
                                (cudaStream_t)stream);
 }
 
@@ -332,7 +334,7 @@ int b2q_minmax_quant_finish_f32(b2q_ctx* ctx, int variant, const float* x, float
     int64_t outer, groups, inner;
     minmax_groups(rows, cols, per_channel && is_weight, &outer, &groups, &inner);
     B2Q_REQUIRE(groups <= B2Q_MAX_GROUPS, "too many channels");
-    b2q_slot* slot = b2q_take_slot(ctx);
+    b2q_slot* slot = b2q_take_slot(ctx, st);
     const float* scale_src = aux;
     UpdateArgs u = minmax_update(variant, is_weight, is_train, init, ema_decay, one_minus_decay, aux, slot, &scale_src);
     b2q_launch(ctx, threshold_update_kernel, (unsigned)((groups + 127) / 128), 128, st, stat, (int)groups, u);
@@ -367,7 +369,7 @@ int b2q_gdrq_fwd_f32(b2q_ctx* ctx, const float* x, float* y, float* alpha, int64
         memset(&u, 0, sizeof(u));
         u.mode = is_weight ? B2Q_UPD_GDRQ_WEIGHT : B2Q_UPD_GDRQ_ACT;
         u.write_aux = 1; u.use_aux_as_scale = 1; u.p0 = ktimes; u.p1 = lamda; u.aux = alpha;
-        b2q_slot* slot = b2q_take_slot(ctx);
+        b2q_slot* slot = b2q_take_slot(ctx, st);
         if (groups == 1 && do_round && (req == B2Q_REQ_WRITE || req == B2Q_REQ_INPLACE)) {
             int done = 0;
             int rc = launch_fused_resident<false>(ctx, slot, x, y, outer * inner, u, qlevel, B2Q_CLIP_SYM, 0, st, &done);
@@ -407,7 +409,7 @@ int b2q_foldbn_data_fwd_f32(b2q_ctx* ctx, const float* x, float* y, float* aux_d
     B2Q_CTX(ctx);
     B2Q_REQUIRE(x && y && aux_data && n >= 1, "bad argument");
     cudaStream_t st = (cudaStream_t)stream;
-    b2q_slot* slot = b2q_take_slot(ctx);
+    b2q_slot* slot = b2q_take_slot(ctx, st);
     UpdateArgs u;
     memset(&u, 0, sizeof(u));
     u.mode = init ? B2Q_UPD_TWICE_STORE : B2Q_UPD_TWICE_EMA;   // fold_bn_v1_gdrq.py:58-64
@@ -451,7 +453,7 @@ int b2q_foldbn_weight_fwd_f32(b2q_ctx* ctx, const float* w, float* w_q, float* b
         return 0;
     }
     B2Q_REQUIRE(aux_weight != nullptr, "null aux");
-    b2q_slot* slot = b2q_take_slot(ctx);
+    b2q_slot* slot = b2q_take_slot(ctx, st);
     Prescale ps = {gamma, var, eps};
     FoldBias fb = {bias, beta, mean};
     // view: per-channel (1, cout, cols); per-tensor (cout, 1, cols) so that the prescale row is o*groups+g either way

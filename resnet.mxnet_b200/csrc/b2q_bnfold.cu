@@ -147,7 +147,7 @@ static int launch_bnstat(b2q_ctx* ctx, const float* y, int64_t n, int64_t c, int
     // fl(C / size) as batch_norm_v1-inl.h computes it: two float operands
     const float scale = (float)c / (float)((double)n * (double)c * (double)hw);
     const unsigned grid = (unsigned)(c * pl.S * pl.P);
-    b2q_slot* slot = b2q_take_slot(ctx);
+    b2q_slot* slot = b2q_take_slot(ctx, st);
     b2q_timed_launch tl(ctx, B2Q_KIND_OTHER, 4.0 * (double)(n * c * hw), st);
     const bool vec8 = (hw % 8 == 0) && (pl.part % 8 == 0) && ((((uintptr_t)y) & 31) == 0);
     if (vec8) b2q_launch(ctx, bnstat_fold_kernel<8>, grid, B2Q_THREADS, st, y, pl, slot, scale, mean, var, f);

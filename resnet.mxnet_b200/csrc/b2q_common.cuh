@@ -3,6 +3,7 @@
 #include <utility>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -10,7 +11,8 @@
 
 #define B2Q_MAX_PIECES 16384   // per-launch partial results kept in a workspace slot
 #define B2Q_MAX_GROUPS 8192    // thresholds per tensor (channels / groups)
-#define B2Q_NSLOTS 64          // reductions that may be in flight at once through one ctx
+#define B2Q_NSLOTS 64          // reduction workspaces per ctx
+#define B2Q_NRINGS 4           // ... in per-stream rings of B2Q_NSLOTS / B2Q_NRINGS
 #define B2Q_THREADS 256
 
 // One in-flight reduction.  `ticket` counts finished blocks; the last block combines `partial` in a fixed
@@ -46,7 +48,11 @@ struct b2q_ctx {
     int device = 0;
     int num_sms = 0;
     b2q_slot* slots = nullptr;      // device
-    unsigned int next_slot = 0;
+    std::mutex mu;                  // guards the ring table, the timing records and the event pool
+    bool ring_used[B2Q_NRINGS] = {false, false, false, false};
+    cudaStream_t ring_stream[B2Q_NRINGS] = {nullptr, nullptr, nullptr, nullptr};
+    unsigned int ring_next[B2Q_NRINGS] = {0, 0, 0, 0};
+    int shared_rings = 0;           // times a fifth stream had to share ring 0 (option "shared_slot_rings", read-only)
     long long launches = 0;
     // run-time knobs (never change results)
     int blocks_per_sm = 4096;        // flat QDQ / backward sweeps: grid = min(tiles, SMs x this); the sweep shows one
@@ -84,6 +90,7 @@ struct b2q_timed_launch {
     bool on;
     b2q_timed_launch(b2q_ctx* c, int kind, double bytes, cudaStream_t s) : ctx(c), st(s), e1(nullptr), on(c->timing != 0) {
         if (!on) return;
+        std::lock_guard<std::mutex> lk(c->mu);
         cudaEvent_t ev[2];
         for (int i = 0; i < 2; ++i) {
             if (!c->event_pool.empty()) { ev[i] = c->event_pool.back(); c->event_pool.pop_back(); }
@@ -170,9 +177,26 @@ static inline void b2q_launch(b2q_ctx* ctx, void (*kernel)(KArgs...), unsigned g
     }   // any other error is picked up by B2Q_LAUNCH_CHECK
 }
 
-static inline b2q_slot* b2q_take_slot(b2q_ctx* ctx) {
-    unsigned int i = __atomic_fetch_add(&ctx->next_slot, 1u, __ATOMIC_RELAXED);
-    return ctx->slots + (i % B2Q_NSLOTS);
+// Reduction workspaces are handed out per STREAM: the 64 slots form four rings of 16, and each of the first four
+// distinct streams that use a context gets a ring of its own, so work on different streams (a framework's side stream,
+// the host-buffer path's compute stream, a captured graph replayed next to eager calls) never shares a slot.  Within
+// one stream a slot is reused 16 calls later, which stream order makes safe.  A fifth stream shares ring 0: streams
+// that share a ring must not run concurrently (b2q_get_option(ctx, "shared_slot_rings") counts how often that fallback
+// was taken).  The table is guarded by a mutex: MXNet invokes CustomOps from worker threads.
+static inline b2q_slot* b2q_take_slot(b2q_ctx* ctx, cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    int ring = -1;
+    for (int i = 0; i < B2Q_NRINGS; ++i) {
+        if (ctx->ring_used[i] && ctx->ring_stream[i] == st) { ring = i; break; }
+    }
+    if (ring < 0) {
+        for (int i = 0; i < B2Q_NRINGS; ++i) {
+            if (!ctx->ring_used[i]) { ctx->ring_used[i] = true; ctx->ring_stream[i] = st; ring = i; break; }
+        }
+    }
+    if (ring < 0) { ring = 0; ctx->shared_rings++; }
+    const unsigned int i = ctx->ring_next[ring]++;
+    return ctx->slots + ring * (B2Q_NSLOTS / B2Q_NRINGS) + (i % (B2Q_NSLOTS / B2Q_NRINGS));
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -463,7 +463,7 @@ static int peer_quant_fwd(b2q_ctx* ctx, bool is_max, int upd_mode, float p0, flo
     pb.state = (PeerState*)((char*)mailboxes[rank] + B2Q_PEER_BOX_BYTES);
     static_assert(sizeof(PeerState) <= B2Q_PEER_STATE_BYTES, "mailbox state area");
     pb.resolved = (unsigned long long*)((char*)mailboxes[rank] + B2Q_PEER_BOX_BYTES + B2Q_PEER_STATE_BYTES);
-    b2q_slot* slot = b2q_take_slot(ctx);
+    b2q_slot* slot = b2q_take_slot(ctx, st);
     if (ctx->peer_mode == 1) {
         UpdateArgs ur;
         memset(&ur, 0, sizeof(ur));

@@ -162,12 +162,12 @@ static int launch_ew(b2q_ctx* ctx, Op op, int64_t n, double alg_bytes_per_elem, 
         int64_t grid = (sp.n8 + tile - 1) / tile;
         if (grid > cap) grid = cap;
         if (grid < 1) grid = 1;
-        b2q_launch(ctx, ew_kernel<Op, true>, (unsigned)grid, B2Q_THREADS, st, op, sp, n, b2q_take_slot(ctx));
+        b2q_launch(ctx, ew_kernel<Op, true>, (unsigned)grid, B2Q_THREADS, st, op, sp, n, b2q_take_slot(ctx, st));
     } else {
         int64_t grid = (n + B2Q_THREADS * 4 - 1) / (B2Q_THREADS * 4);
         if (grid > cap) grid = cap;
         if (grid < 1) grid = 1;
-        b2q_launch(ctx, ew_kernel<Op, false>, (unsigned)grid, B2Q_THREADS, st, op, sp, n, b2q_take_slot(ctx));
+        b2q_launch(ctx, ew_kernel<Op, false>, (unsigned)grid, B2Q_THREADS, st, op, sp, n, b2q_take_slot(ctx, st));
     }
     B2Q_LAUNCH_CHECK(ctx);
     return 0;
@@ -676,7 +676,7 @@ int b2q_wnq_fwd_f32(b2q_ctx* ctx, const float* x, float* y, int64_t rows, int64_
     B2Q_REQUIRE(x && y && rows >= 1 && cols >= 1, "bad argument");
     if (req == B2Q_REQ_NULL) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    b2q_slot* slot = b2q_take_slot(ctx);
+    b2q_slot* slot = b2q_take_slot(ctx, st);
     UpdateArgs u;
     memset(&u, 0, sizeof(u));
     u.stat_out = slot->scale;
@@ -698,7 +698,7 @@ int b2q_wnq_bwd_f32(b2q_ctx* ctx, const float* x, const float* dy, float* dx, in
     B2Q_REQUIRE(x && dy && dx && rows >= 1 && cols >= 1, "bad argument");
     if (req == B2Q_REQ_NULL) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    b2q_slot* slot = b2q_take_slot(ctx);
+    b2q_slot* slot = b2q_take_slot(ctx, st);
     UpdateArgs u;
     memset(&u, 0, sizeof(u));
     u.stat_out = slot->scale;
@@ -753,7 +753,7 @@ int b2q_dorefa_bwd_f32(b2q_ctx* ctx, const float* x, const float* dy, float* dx,
     B2Q_REQUIRE(x && dy && dx && vmax && n >= 1, "bad argument");
     if (req == B2Q_REQ_NULL) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    b2q_slot* slot = b2q_take_slot(ctx);
+    b2q_slot* slot = b2q_take_slot(ctx, st);
     DorefaBwdSum sop = {x, dy, vmax, slot->scale, 0.f, 0.f};
     int rc = launch_ew(ctx, sop, n, 8.0, st);
     if (rc) return rc;

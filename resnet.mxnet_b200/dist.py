@@ -95,6 +95,18 @@ class PeerThresholdExchange(object):
         if self.world > 1:
             dist.barrier(group=group)
 
+    @classmethod
+    def from_tables(cls, ctx, boxes, rank, world, own=None):
+        """Exchange over mailboxes that already exist and are mapped (b200quant.comm.DeviceGroup: one process, N devices)."""
+        import ctypes
+        self = cls.__new__(cls)
+        self.group, self.world, self.rank, self.ctx, self.sequence = None, int(world), int(rank), ctx, 0
+        self.device = torch.device("cuda", ctx.device)
+        self._boxes = (ctypes.c_void_p * self.world)(*[boxes[r] for r in range(self.world)])
+        self._opened, self._own = [], None      # the mailboxes belong to the communicator
+        self._status_box = ctypes.c_void_p(boxes[rank]) if own is None else own
+        return self
+
     def quantize(self, variant, x, y, aux, init, ema_decay):
         """Activation forward (training) of Quantization_int8_V2 (variant 0) / ClipGrad (variant 1) with the
         statistic maximised over all ranks."""
@@ -123,7 +135,10 @@ class PeerThresholdExchange(object):
         ``peer_timeout_ms``; the affected outputs and thresholds are NaN), or None.  Synchronises with the device."""
         import ctypes
         seq, rk = ctypes.c_uint32(0), ctypes.c_uint32(0)
-        self.ctx.call("b2q_peer_status", self._own, ctypes.byref(seq), ctypes.byref(rk))
+        box = self._own if self._own is not None else getattr(self, "_status_box", None)
+        if box is None:
+            return None
+        self.ctx.call("b2q_peer_status", box, ctypes.byref(seq), ctypes.byref(rk))
         return (int(seq.value), int(rk.value)) if seq.value else None
 
     def check(self):

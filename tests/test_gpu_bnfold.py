@@ -107,8 +107,8 @@ def test_foldbn_layer_twin_fused_equals_unfused_and_trains(group):
     (ya, wa, ga, ba, xa, auxa), (yb, wb, gb, bb, xb, auxb) = outs
     for a, b in zip(ya, yb):
         assert T.equal(a.view(T.int32), b.view(T.int32))
-    for a, b in ((wa, wb), (ga, gb), (ba, bb), (xa, xb)):
-        assert T.equal(a, b)
+    for a, b in ((wa, wb), (ga, gb), (ba, bb), (xa, xb)):     # library convolution backward: not bitwise reproducible
+        T.testing.assert_close(a, b, rtol=1e-4, atol=1e-6)
     assert sorted(auxa) == sorted(auxb) == ["stage1_batchnorm_moving_mean", "stage1_batchnorm_moving_var",
                                             "stage1_fold_bn_data_minmax", "stage1_fold_bn_weight_minmax"]
     for k in auxa:

@@ -51,8 +51,8 @@ def test_harness_resnet_int8_matches_the_inventory():
 
 def test_reference_arm_prints_the_contract_line():
     env = dict(os.environ, OMP_NUM_THREADS="2")
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                          "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2",
+                          "--warmup", "1", "--batch", "8"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.strip()]
     assert len(lines) == 1                                   # ONE JSON line on stdout
@@ -61,8 +61,14 @@ def test_reference_arm_prints_the_contract_line():
     assert d["unit"] == "img/s" and d["higher_is_better"] is True and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # the arm runs EVERY node of the workload (nothing extrapolated) and describes it exactly as the product arm does
+    import bench
+    nodes, sm, batch, op_type = bench.workload_nodes("resnet50_int8", 8)
+    assert d["config"] == bench.workload_config("resnet50_int8", op_type, sm, batch, 1)
+    assert d["config"]["elements_per_step"] == sm["act_elems"] + sm["weight_elems"] and len(nodes) == 108
+    assert "ALL 108 nodes" in d["cpu_baseline"]["sample"] and d["ms_per_step"] > 0
     # other ranks of a multi-rank launch exit 0 without work
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--batch", "8"],
                          capture_output=True, text=True, timeout=120, cwd=ROOT, env=dict(env, RANK="1", WORLD_SIZE="2"))
     assert out.returncode == 0 and out.stdout.strip() == ""
 
@@ -74,3 +80,16 @@ def test_product_arm_needs_a_gpu():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True,
                          text=True, timeout=300, cwd=ROOT)
     assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
+
+
+def test_reference_arm_runs_the_other_workloads_too():
+    """MobileNet GDRQ, ResNeXt clip-grad and the fold-BN quant path through oracle/c (small batch: CPU suite budget)."""
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    for wl, nodes in (("mobilenet_v1_gdrq", 56), ("resnext101_clipgrad", 210), ("mobilenet_v1_foldbn", 54)):
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                              "--warmup", "1", "--batch", "2", "--workload", wl], capture_output=True, text=True,
+                             timeout=600, cwd=ROOT, env=env)
+        assert out.returncode == 0, out.stderr[-2000:]
+        d = json.loads(out.stdout.strip().splitlines()[-1])
+        assert d["metric"] == wl + "_quant_path_images_per_sec" and d["value"] > 0
+        assert "all %d " % nodes in d["config"]["workload"]

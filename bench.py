@@ -613,13 +613,39 @@ def kernel_table(ctx, peak_gbs):
     return kernels, kinds
 
 
-def measure_kernels(torch, ctx, step, reps, peak_gbs):
+def forward_by_size(ctx, sizes, peak_gbs):
+    """forward (reduction + sweep, 12 B/element algorithmic) of every distinct activation size, from the event records of
+    the timed pass: where the launch-latency regime ends.  Uses the two kernels' records of that exact byte count."""
+    out = {}
+    for n in sorted(set(sizes), reverse=True):
+        t_ms, launches = 0.0, 0
+        for kind, per_elem in ((1, 4.0), (2, 8.0), (6, 12.0)):
+            b = per_elem * n
+            try:
+                ms, _, cnt = ctx.timing_read(kind, min_bytes=b * 0.9999, max_bytes=b * 1.0001)
+            except Exception:
+                continue
+            if cnt and kind != 6:
+                t_ms += ms / cnt
+                launches += 1
+            elif cnt:
+                t_ms, launches = ms / cnt, 2
+                break
+        if launches == 2 and t_ms > 0:
+            out["%d" % n] = {"mb": round(4 * n / 1e6, 1), "us": round(t_ms * 1e3, 2),
+                             "frac_of_peak_on_12B_per_elem": round(12.0 * n / t_ms / 1e6 / peak_gbs, 4)}
+    return out
+
+
+def measure_kernels(torch, ctx, step, reps, peak_gbs, act_sizes=None):
     ctx.set_option("timing", 1)
     ctx.timing_read(0, reset=True)
     for _ in range(reps):
         step()
     torch.cuda.synchronize()
     kernels, kinds = kernel_table(ctx, peak_gbs)
+    if act_sizes:
+        kernels["forward_by_activation_size"] = forward_by_size(ctx, act_sizes, peak_gbs)
     ctx.timing_read(0, reset=True)
     ctx.set_option("timing", 0)
     return kernels, kinds
@@ -935,7 +961,9 @@ def main():
     value = world * batch * args.steps / (ms_eager / 1e3)
 
     # ---- per-kernel timing for the roofline (second timed region, events around every flat-kernel launch) ----
-    kernels, kinds = measure_kernels(torch, ctx, step, 0 if args.profile else min(args.steps, 5), peak_gbs)
+    kernels, kinds = measure_kernels(torch, ctx, step, 0 if args.profile else min(args.steps, 5), peak_gbs,
+                                     act_sizes=[nd["n"] for nd in nodes if nd["kind"] == "act"])
+    fwd_by_size = kernels.pop("forward_by_activation_size", None)
     traffic, traffic_note = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_dominant_kernel.json")) as f:
@@ -965,7 +993,7 @@ def main():
             "ms_per_step_by_mode": timings,
             "hbm_frac_whole_step": alg_bytes_step / (ms_eager / args.steps / 1e3) / 1e9 / peak_gbs,
             "hbm_frac_whole_step_best_mode": alg_bytes_step / (best_ms / args.steps / 1e3) / 1e9 / peak_gbs,
-            "roofline": roofline, "kernels": kernels,
+            "roofline": roofline, "kernels": kernels, "forward_by_activation_size": fwd_by_size,
             "kernels_note": "event-timed per launch in a separate pass, all tensor sizes pooled (54 of the launches per "
                             "kind are weight tensors of a few KB..MB that cost a launch each); a kernel that follows a "
                             "sweep also pays for the write-back of the output lines its predecessor left dirty in L2 "

@@ -81,6 +81,7 @@ static int* option_slot(b2q_ctx* ctx, const char* key) {
     if (!strcmp(key, "deferred")) return &ctx->deferred;
     if (!strcmp(key, "pdl")) return &ctx->pdl;
     if (!strcmp(key, "reverse")) return &ctx->reverse;
+    if (!strcmp(key, "reverse_min_mb")) return &ctx->reverse_min_mb;
     if (!strcmp(key, "fast_div")) return &ctx->fast_div;
     if (!strcmp(key, "timing")) return &ctx->timing;
     if (!strcmp(key, "dorefa_tanh_max")) return &ctx->dorefa_tanh_max;
@@ -89,6 +90,7 @@ static int* option_slot(b2q_ctx* ctx, const char* key) {
     if (!strcmp(key, "resident")) return &ctx->resident;
     if (!strcmp(key, "resident_max_mb")) return &ctx->resident_max_mb;
     if (!strcmp(key, "peer_mode")) return &ctx->peer_mode;
+    if (!strcmp(key, "peer_stage_early")) return &ctx->peer_stage_early;
     if (!strcmp(key, "peer_timeout_ms")) return &ctx->peer_timeout_ms;
     return nullptr;
 }

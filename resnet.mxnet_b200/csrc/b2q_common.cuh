@@ -62,8 +62,8 @@ struct b2q_ctx {
     int pdl = 1;                              // programmatic dependent launch between consecutive whole-tensor kernels
     int peer_reduce_blocks_per_sm = 8;        // max reductions of the peer-memory exchange (atomicMax + ticket per block)
     int deferred = 1;                // consumer-side threshold update in the fused whole-tensor forward
-    int reverse = 1;                 // QDQ sweep walks descending addresses when the tensor exceeds reverse_min_bytes
-    long long reverse_min_bytes = 96ll << 20;
+    int reverse = 1;                 // QDQ sweep walks descending addresses when the tensor exceeds reverse_min_mb MiB
+    int reverse_min_mb = 96;            // (option) tensors above this many MiB are swept in descending order
     int fast_div = 1;
     int dorefa_tanh_max = 0;         // 1: DoReFa takes max|tanh(w)| element-wise instead of tanhf(max|w|) (same float)
     int host_ste_copy = 1;           // host-buffer straight-through backward: copy host to host, no PCIe round trip
@@ -73,7 +73,9 @@ struct b2q_ctx {
                                      // and its barrier latency chain costs more than two PDL-chained launches
                                      // (profiles/r02b_resident_ab.md)
     int resident_max_mb = 72;        // largest tensor (MB) that takes the single-launch resident forward
-    int peer_mode = 1;               // 1: ticket-free reduction, the sweep's first block publishes to the peers; 0: r1 kernels
+    int peer_mode = 1;               // 1: ticket-free reduction, the sweep's first block publishes to the peers; 0: r1 kernels;
+                                     // 2 / 3: as 1 with one / two further tiles per block staged in shared memory during the wait
+    int peer_stage_early = 0;        // 1: issue the staging copies before the dependency wait instead of right after it
     int peer_timeout_ms = 600000;    // how long a sweep waits for a peer's statistic before it gives up (NaN output + flag)
     int timing = 0;
     std::vector<b2q_timing_rec> recs;
@@ -287,6 +289,32 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsig
                      smem_u32(smem_dst)),
                  "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+
+// same with an L2 eviction-priority hint (createpolicy): x is read for the last time by the sweep that stages it
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
+__device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar,
+                                              unsigned long long policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+                 : "memory");
+}
+
+// Kernels that stage tiles in shared memory and bypass L1 for their global accesses: ask for the largest shared-memory
+// carve-out once per kernel so that the register-limited number of blocks stays resident.
+template <typename K>
+static inline void b2q_prefer_shared(K kernel) {
+    static bool done = false;
+    if (!done) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        done = true;
+    }
 }
 
 // "Last block finishes" ticket: a release atomic (+ an acquire fence in the one block that draws `last`) instead of

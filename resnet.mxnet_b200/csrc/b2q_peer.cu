@@ -391,6 +391,148 @@ qdq_peer2_kernel(const float* __restrict__ x, float* __restrict__ y, FlatSplit s
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// peer_mode 2 / 3: qdq_peer2_kernel with its waiting time put to work.  Between the end of this rank's reduction and
+// the arrival of the slowest rank's statistic (NVLink hop + skew, ~5 us per node) the memory system is idle: the first
+// tile of every resident block has long landed in its registers.  Here a block owns 1 + STAGES consecutive tiles: the
+// first is requested into registers before the dependency wait as before; the others are fetched into shared memory
+// by bulk asynchronous copies (TMA engine, mbarrier completion, L2 evict-first hint) issued by one thread right AFTER
+// the dependency wait, i.e. exactly while warp 0 polls the mailbox.  With 8 blocks per SM that is another
+// 128 KB (STAGES = 1) per SM of x on its way during the wait -- 19 / 38 MB over the chip, 3 / 6 us of HBM time that
+// no longer follows the wait.  The arithmetic is qdq8 on the same 256-bit words: results are bit-identical.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ f8 lds_f8(const float* p) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    f8 r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+
+template <int CLIP, int UNROLL, int LDPOL, int STPOL, int STAGES>
+__global__ void __launch_bounds__(B2Q_THREADS)
+qdq_peer3_kernel(const float* __restrict__ x, float* __restrict__ y, FlatSplit sp, PeerBoxes pb, b2q_slot* slot,
+                 UpdateArgs u, float qlevel, int fast, int reverse, int clip_with_fresh, int is_max, int n_partials,
+                 float count, unsigned long long timeout_ns, int stage_early) {
+    __shared__ __align__(128) float s_tile[STAGES][B2Q_THREADS * UNROLL * 8];
+    __shared__ unsigned long long s_bar[STAGES];
+    __shared__ float s_stat;
+    __shared__ double s_red[32];
+    const float* xb = x + sp.head;
+    float* yb = y + sp.head;
+    const int64_t tile = (int64_t)B2Q_THREADS * UNROLL;
+    const int64_t ntiles = (sp.n8 + tile - 1) / tile;
+    const int64_t lt0 = (int64_t)blockIdx.x * (1 + STAGES);       // this block's tiles: lt0 .. lt0 + STAGES (logical order)
+    f8 v[UNROLL];
+    {   // first tile: requested before the dependency wait (the reduction in front of us only reads x)
+        const int64_t t = reverse ? (ntiles - 1 - lt0) : lt0;
+        const int64_t base = t * tile + threadIdx.x;
+#pragma unroll
+        for (int k = 0; k < UNROLL; ++k) {
+            const int64_t i = base + (int64_t)k * B2Q_THREADS;
+            if (lt0 < ntiles && i < sp.n8) v[k] = ld_f8<LDPOL>(xb + 8 * i);
+        }
+    }
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int sgi = 0; sgi < STAGES; ++sgi) mbar_init(&s_bar[sgi], 1);
+        mbar_fence_init();
+    }
+    auto stage = [&]() {   // thread 0 only
+        const unsigned long long pol = l2_policy_evict_first();
+#pragma unroll
+        for (int sgi = 0; sgi < STAGES; ++sgi) {
+            const int64_t lt = lt0 + 1 + sgi;
+            if (lt < ntiles) {
+                const int64_t t = reverse ? (ntiles - 1 - lt) : lt;
+                int64_t words = sp.n8 - t * tile;
+                if (words > tile) words = tile;
+                const unsigned bytes = (unsigned)words * 32u;
+                mbar_expect_tx(&s_bar[sgi], bytes);
+                bulk_g2s_hint(&s_tile[sgi][0], xb + 8 * t * tile, bytes, &s_bar[sgi], pol);
+            }
+        }
+    };
+    if (stage_early && threadIdx.x == 0) stage();
+    b2q_pdl_sync();
+    if (!stage_early && threadIdx.x == 0) stage();
+    const unsigned int seq = pb.state->seq;   // advanced by this call's reduction (block 0), stable during this kernel
+    if (blockIdx.x == 0) {   // publish this rank's statistic to every rank (own mailbox included)
+        float mine;
+        if (is_max) {
+            const unsigned long long word = slot->max64;
+            mine = __uint_as_float((unsigned int)(word & 0xffffffffull));
+            if (threadIdx.x == 0) slot->epoch = (unsigned int)(word >> 32);   // consume the tag
+        } else {
+            double acc = 0.0;
+            for (int i = threadIdx.x; i < n_partials; i += blockDim.x) acc += slot->partial[i];
+            const double tot = block_reduce<false>(acc, s_red);
+            if (threadIdx.x == 0) s_stat = __fdiv_rn((float)tot, count);
+            __syncthreads();
+            mine = s_stat;
+            __syncthreads();
+        }
+        if ((int)threadIdx.x < pb.world) {
+            const unsigned long long word = ((unsigned long long)seq << 32) | __float_as_uint(mine);
+            st_sys_u64(pb.box[threadIdx.x] + (size_t)(seq & 1u) * B2Q_PEER_MAX_RANKS + pb.rank, word);
+        }
+        if (threadIdx.x == 0) pb.state->done = seq;
+    }
+    if (threadIdx.x < 32) {
+        const float g = peer_gather_warp0(pb, seq, timeout_ns);
+        if (threadIdx.x == 0) s_stat = g;
+    }
+    __syncthreads();   // also publishes the initialised mbarriers to the whole block
+    const float stat = s_stat;
+    const float a_old = slot->scale[0];
+    float fresh, next;
+    compute_update(u.mode, u.p0, u.p1, a_old, stat, fresh, next);
+    const float T = next;
+    const float Tc = clip_with_fresh ? fresh : T;   // fold_bn_v1_gdrq.py:67 clips with the batch threshold
+    if (blockIdx.x == 0 && threadIdx.x == 0) u.aux[0] = next;
+    const QScale s = make_qscale(T, qlevel, fast != 0 && !(CLIP != B2Q_CLIP_NONE && !(Tc >= 0.f)));
+    if (lt0 < ntiles) {
+        const int64_t t = reverse ? (ntiles - 1 - lt0) : lt0;
+        const int64_t base = t * tile + threadIdx.x;
+#pragma unroll
+        for (int k = 0; k < UNROLL; ++k) {
+            const int64_t i = base + (int64_t)k * B2Q_THREADS;
+            if (i < sp.n8) {
+                f8 o;
+                qdq8<CLIP>(v[k], o, Tc, s);
+                st_f8<STPOL>(yb + 8 * i, o);
+            }
+        }
+    }
+#pragma unroll
+    for (int sgi = 0; sgi < STAGES; ++sgi) {
+        const int64_t lt = lt0 + 1 + sgi;
+        if (lt < ntiles) {
+            const int64_t t = reverse ? (ntiles - 1 - lt) : lt;
+            const int64_t base = t * tile + threadIdx.x;
+            mbar_wait(&s_bar[sgi], 0);
+#pragma unroll
+            for (int k = 0; k < UNROLL; ++k) {
+                const int64_t i = base + (int64_t)k * B2Q_THREADS;
+                if (i < sp.n8) {
+                    const f8 w = lds_f8(&s_tile[sgi][8 * (k * B2Q_THREADS + (int)threadIdx.x)]);
+                    f8 o;
+                    qdq8<CLIP>(w, o, Tc, s);
+                    st_f8<STPOL>(yb + 8 * i, o);
+                }
+            }
+        }
+    }
+    if (blockIdx.x == 0) {
+        const int64_t tid = threadIdx.x;
+        int64_t idx = -1;
+        if (tid < sp.head) idx = tid;
+        else if (tid - sp.head < sp.tail) idx = sp.head + 8 * sp.n8 + (tid - sp.head);
+        if (idx >= 0) {
+            y[idx] = __fmul_rn(quant_code_exact(clip_value(CLIP, x[idx], Tc), s.q), s.q);
+        }
+    }
+}
+
 extern "C" {
 
 int b2q_peer_mailbox_bytes(void) { return B2Q_PEER_BYTES; }
@@ -464,7 +606,8 @@ static int peer_quant_fwd(b2q_ctx* ctx, bool is_max, int upd_mode, float p0, flo
     static_assert(sizeof(PeerState) <= B2Q_PEER_STATE_BYTES, "mailbox state area");
     pb.resolved = (unsigned long long*)((char*)mailboxes[rank] + B2Q_PEER_BOX_BYTES + B2Q_PEER_STATE_BYTES);
     b2q_slot* slot = b2q_take_slot(ctx, st);
-    if (ctx->peer_mode == 1) {
+    const int mode = ctx->peer_mode;
+    if (mode >= 1) {
         UpdateArgs ur;
         memset(&ur, 0, sizeof(ur));
         ur.aux = aux;                       // the deferred reduction snapshots the old threshold into slot->scale[0]
@@ -479,14 +622,32 @@ static int peer_quant_fwd(b2q_ctx* ctx, bool is_max, int upd_mode, float p0, flo
         u.mode = upd_mode;
         u.write_aux = 1; u.use_aux_as_scale = 1; u.p0 = p0; u.p1 = p1; u.aux = aux;
         const int64_t grid = b2q_flat_grid(ctx, sp.n8, B2Q_QDQ_UNROLL);
-        const int rev = (ctx->reverse && n * 4 > ctx->reverse_min_bytes) ? 1 : 0;
+        const int rev = (ctx->reverse && n * 4 > ((long long)ctx->reverse_min_mb << 20)) ? 1 : 0;
         const bool stream_out = n * 4 > B2Q_STREAM_BYTES;
         const unsigned long long timeout_ns = (unsigned long long)(ctx->peer_timeout_ms > 0 ? ctx->peer_timeout_ms : 1) * 1000000ull;
         b2q_timed_launch tl(ctx, B2Q_KIND_QDQ_HOT, 8.0 * (double)n, st);
 #define B2Q_PEER2_SWEEP(C, S) b2q_launch(ctx, qdq_peer2_kernel<C, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, S>, (unsigned)grid, B2Q_THREADS, st, \
             x, y, sp, pb, slot, u, qlevel, ctx->fast_div, rev, clip_with_fresh, is_max ? 1 : 0, np, (float)n, timeout_ns)
 #define B2Q_PEER2_SWEEP_S(C) do { if (stream_out) B2Q_PEER2_SWEEP(C, 1); else B2Q_PEER2_SWEEP(C, B2Q_QDQ_STPOL); } while (0)
-        if (clip_mode == B2Q_CLIP_SYM) B2Q_PEER2_SWEEP_S(B2Q_CLIP_SYM); else B2Q_PEER2_SWEEP_S(B2Q_CLIP_NONE);
+#define B2Q_PEER3_SWEEP(C, S, G) do {                                                                                  \
+            const int64_t tiles_ = (sp.n8 + (int64_t)B2Q_THREADS * B2Q_QDQ_UNROLL - 1) / ((int64_t)B2Q_THREADS * B2Q_QDQ_UNROLL); \
+            int64_t grid3_ = (tiles_ + G) / (1 + G);                                                                          \
+            if (grid3_ < 1) grid3_ = 1;                                                                                        \
+            b2q_prefer_shared(qdq_peer3_kernel<C, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, S, G>);                                       \
+            b2q_launch(ctx, qdq_peer3_kernel<C, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, S, G>, (unsigned)grid3_, B2Q_THREADS, st, x, y,  \
+                       sp, pb, slot, u, qlevel, ctx->fast_div, rev, clip_with_fresh, is_max ? 1 : 0, np, (float)n, timeout_ns, \
+                       ctx->peer_stage_early);                                                                                 \
+        } while (0)
+#define B2Q_PEER3_SWEEP_S(C, G) do { if (stream_out) B2Q_PEER3_SWEEP(C, 1, G); else B2Q_PEER3_SWEEP(C, B2Q_QDQ_STPOL, G); } while (0)
+        if (mode == 2) {
+            if (clip_mode == B2Q_CLIP_SYM) B2Q_PEER3_SWEEP_S(B2Q_CLIP_SYM, 1); else B2Q_PEER3_SWEEP_S(B2Q_CLIP_NONE, 1);
+        } else if (mode == 3) {
+            if (clip_mode == B2Q_CLIP_SYM) B2Q_PEER3_SWEEP_S(B2Q_CLIP_SYM, 2); else B2Q_PEER3_SWEEP_S(B2Q_CLIP_NONE, 2);
+        } else {
+            if (clip_mode == B2Q_CLIP_SYM) B2Q_PEER2_SWEEP_S(B2Q_CLIP_SYM); else B2Q_PEER2_SWEEP_S(B2Q_CLIP_NONE);
+        }
+#undef B2Q_PEER3_SWEEP_S
+#undef B2Q_PEER3_SWEEP
 #undef B2Q_PEER2_SWEEP_S
 #undef B2Q_PEER2_SWEEP
         B2Q_LAUNCH_CHECK(ctx);
@@ -509,7 +670,7 @@ static int peer_quant_fwd(b2q_ctx* ctx, bool is_max, int upd_mode, float p0, flo
     u.write_aux = 1; u.use_aux_as_scale = 1; u.p0 = p0; u.p1 = p1; u.aux = aux;
     {
         const int64_t grid = b2q_flat_grid(ctx, sp.n8, B2Q_QDQ_UNROLL);
-        const int rev = (ctx->reverse && n * 4 > ctx->reverse_min_bytes) ? 1 : 0;
+        const int rev = (ctx->reverse && n * 4 > ((long long)ctx->reverse_min_mb << 20)) ? 1 : 0;
         const bool stream_out = n * 4 > B2Q_STREAM_BYTES;   // outputs that cannot stay in L2 anyway: streaming stores
         b2q_timed_launch tl(ctx, B2Q_KIND_QDQ_HOT, 8.0 * (double)n, st);
 #define B2Q_PEER_SWEEP(C, S) b2q_launch(ctx, qdq_peer_kernel<C, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, S>, (unsigned)grid, B2Q_THREADS, st, \

@@ -728,7 +728,7 @@ static inline bool same_misalignment(const void* a, const void* b) {
                 const int64_t grid = b2q_flat_grid(ctx, sp.n8, B2Q_QDQ_UNROLL);
                 DeferredUpdate none = {};
                 const bool stream_out = n * 4 > B2Q_STREAM_BYTES;
-                const int rev = (ctx->reverse && n * 4 > ctx->reverse_min_bytes) ? 1 : 0;
+                const int rev = (ctx->reverse && n * 4 > ((long long)ctx->reverse_min_mb << 20)) ? 1 : 0;
 #define B2Q_HOT(C, S) b2q_launch(ctx, qdq_flat_hot_kernel<C, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, S, false>, \
                                  (unsigned)grid, B2Q_THREADS, st, x, y, sp, a, rev, none, 0)
 #define B2Q_HOT_S(C) do { if (stream_out) B2Q_HOT(C, 1); else B2Q_HOT(C, B2Q_QDQ_STPOL); } while (0)
@@ -805,7 +805,7 @@ template <bool IS_MAX>
     {
         b2q_timed_launch tl(ctx, B2Q_KIND_QDQ_HOT, 8.0 * (double)n, st);
         const bool stream_out = n * 4 > B2Q_STREAM_BYTES;
-        const int rev = (ctx->reverse && n * 4 > ctx->reverse_min_bytes) ? 1 : 0;
+        const int rev = (ctx->reverse && n * 4 > ((long long)ctx->reverse_min_mb << 20)) ? 1 : 0;
 #define B2Q_HOT(C, S) b2q_launch(ctx, qdq_flat_hot_kernel<C, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, S, true>, \
                                  (unsigned)grid, B2Q_THREADS, st, x, y, sp, a, rev, d, clip_with_fresh)
         if (clip_mode == B2Q_CLIP_SYM) { if (stream_out) B2Q_HOT(B2Q_CLIP_SYM, 1); else B2Q_HOT(B2Q_CLIP_SYM, B2Q_QDQ_STPOL); }

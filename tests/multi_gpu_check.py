@@ -30,6 +30,11 @@ def main():
         return np.array_equal(np.ascontiguousarray(a, dtype=F).view(np.uint32), np.ascontiguousarray(b, dtype=F).view(np.uint32))
 
     failures = 0
+    from b200quant import _lib
+    ctx = _lib.context(local)
+    for k, v in os.environ.items():   # B2Q_OPT_<option>=<int>, e.g. B2Q_OPT_PEER_MODE=2 (results never depend on them)
+        if k.startswith("B2Q_OPT_"):
+            ctx.set_option(k[len("B2Q_OPT_"):].lower(), int(v))
     for mode in ("nccl", "peer"):
         for op_type, variant in (("Quantization_int8_V2", 0), ("ClipGrad_Quantization_int8", 1)):
             op = b200quant.get_prop(op_type)(quant_mode="minmax", is_weight="False").create_operator(None, None, None)

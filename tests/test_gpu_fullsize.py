@@ -153,22 +153,30 @@ def test_kernel_variants_bit_exact_at_full_size(T, co, shape, opts):
             ctx.set_option(k, v)
 
 
+@pytest.mark.parametrize("peer_mode", [1, 2, 3])
 @pytest.mark.parametrize("shape", [SHAPES[0], SHAPES[2]], ids=[IDS[0], IDS[2]])
-def test_peer_kernels_world1_bit_exact_at_full_size(T, co, shape):
+def test_peer_kernels_world1_bit_exact_at_full_size(T, co, shape, peer_mode):
     """the fused peer-memory exchange kernels (reduce_peer_kernel / qdq_peer_kernel) on real shapes; at world 1 the max
     over ranks is the local max, so the single-GPU oracle applies.  Multi-rank: tests/test_gpu_multi_rank.py and
     bench.py's parity_checked flag."""
+    from b200quant import _lib
     from b200quant.dist import attach_peer_exchange
     c = case(T, co, shape)
-    for kind in ("v2", "clipgrad", "gdrq"):
-        op = new_op(kind)
-        ex = attach_peer_exchange([op], T.device("cuda", 0))
-        try:
-            assert op.peer is ex
-            drive_and_compare(T, c, kind, op, "peer world 1")
-        finally:
-            T.cuda.synchronize()
-            ex.close()
+    ctx = _lib.context(0)
+    saved = ctx.get_option("peer_mode")
+    ctx.set_option("peer_mode", peer_mode)
+    try:
+        for kind in ("v2", "clipgrad", "gdrq"):
+            op = new_op(kind)
+            ex = attach_peer_exchange([op], T.device("cuda", 0))
+            try:
+                assert op.peer is ex
+                drive_and_compare(T, c, kind, op, "peer world 1, peer_mode %d" % peer_mode)
+            finally:
+                T.cuda.synchronize()
+                ex.close()
+    finally:
+        ctx.set_option("peer_mode", saved)
 
 
 @pytest.mark.parametrize("kind", ["v2", "clipgrad"])

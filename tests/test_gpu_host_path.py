@@ -61,3 +61,20 @@ def test_numpy_arrays_are_accepted_zero_copy():
     yr, ar = np.zeros_like(x), np.ones(1, F)
     ref.forward(True, ["write"], [x.copy()], [yr], [ar])
     assert bits_equal(aux, ar) and bits_equal(y, yr)
+
+
+@pytest.mark.parametrize("n", [1, 15, 16, 17, 63, 64, 65, 255, 256, 257, 4099, (8 << 20) // 4 + 13, 3 * (8 << 20) // 4 + 5])
+def test_host_ste_copy_any_alignment(n):
+    """The straight-through backward of a host caller (quant_ops.py:42-43) is a host-to-host streaming copy (64-byte
+    non-temporal stores with a head/tail split): every source / destination misalignment, sizes around the vector
+    width and the 8 MB job size, and nothing outside [dst, dst + n) is touched."""
+    from b200quant import _kernels as K
+    rng = np.random.default_rng(n)
+    for so in (0, 1, 3):
+        for do in (0, 1, 5, 15):
+            src = rng.standard_normal(n + 32).astype(F)
+            dst = np.full(n + 48, 7.0, F)
+            K.ste_bwd(src[so:so + n], dst[do:do + n], "write")
+            K.host_sync()
+            assert bits_equal(dst[do:do + n], src[so:so + n])
+            assert (dst[:do] == 7.0).all() and (dst[do + n:] == 7.0).all()

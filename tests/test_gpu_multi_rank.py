@@ -33,6 +33,50 @@ def test_peer_exchange_world1_matches_plain_path():
         ex.close()
 
 
+@pytest.mark.parametrize("peer_mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("reverse_all", [False, True])
+def test_peer_sweep_variants_equal_plain_path_around_tile_edges(peer_mode, reverse_all):
+    """peer_mode 2 / 3 give every block 2 / 3 tiles (one in registers, the others staged in shared memory by bulk
+    copies issued while the block waits for the peers' statistic): tensor sizes around the 4096-element tile and the
+    super-tile boundaries, odd heads and tails, ascending and descending tile order, both staging points."""
+    import torch
+    import b200quant
+    from b200quant import _lib
+    from b200quant.dist import attach_peer_exchange
+    ctx = _lib.context(0)
+    saved = {k: ctx.get_option(k) for k in ("peer_mode", "reverse_min_mb", "peer_stage_early")}
+    g = torch.Generator(device="cuda").manual_seed(11)
+    sizes = [1, 7, 8, 4095, 4096, 4097, 8191, 8192, 8200, 12287, 12288, 12296, 3 * 4096 + 8, 5 * 4096 - 8, 6 * 4096,
+             7 * 4096 + 24, 100003, 1 << 20, (1 << 22) + 40]
+    try:
+        for early in (0, 1):
+            ctx.set_option("peer_mode", peer_mode)
+            ctx.set_option("peer_stage_early", early)
+            if reverse_all:
+                ctx.set_option("reverse_min_mb", 0)
+            for op_type in ("Quantization_int8_V2", "ClipGrad_Quantization_int8"):
+                mk = lambda: b200quant.get_prop(op_type)(quant_mode="minmax", is_weight="False").create_operator(None, None, None)
+                a, b = mk(), mk()
+                ex = attach_peer_exchange([b], torch.device("cuda", 0))
+                aux_a, aux_b = torch.ones(1, device="cuda"), torch.ones(1, device="cuda")
+                for step, n in enumerate(sizes):
+                    for off in (0, 3):                      # a misaligned view: scalar head and tail
+                        buf = torch.randn(n + 8, device="cuda", generator=g) * (1 + step % 5)
+                        x = buf[off:off + n]
+                        ybuf_a, ybuf_b = torch.full_like(buf, 7.0), torch.full_like(buf, 7.0)
+                        a.forward(True, ["write"], [x], [ybuf_a[off:off + n]], [aux_a])
+                        b.forward(True, ["write"], [x], [ybuf_b[off:off + n]], [aux_b])
+                        assert torch.equal(aux_a.view(torch.int32), aux_b.view(torch.int32)), (op_type, n, off)
+                        assert torch.equal(ybuf_a.view(torch.int32), ybuf_b.view(torch.int32)), (op_type, n, off)
+                torch.cuda.synchronize()
+                ex.close()
+            if peer_mode < 2:
+                break
+    finally:
+        for k, v in saved.items():
+            ctx.set_option(k, v)
+
+
 def test_peer_exchange_world1_mean_based_ops():
     """Whole-tensor GDRQ_PY activations and the GDRQ_Fold_BN data path through b2q_peer_meanabs_quant_fwd_f32."""
     import torch

@@ -35,8 +35,12 @@ struct BnFold {
     int is_train, fast;
 };
 
-template <int VEC>
-__global__ void __launch_bounds__(B2Q_THREADS)
+// Register budget matters more than anything else here: the first version held four 256-bit words plus their
+// double-precision images per thread (94 registers -> 2 blocks per SM, 24 % of the warps, 30 % of DRAM throughput in ncu,
+// profiles/r02g_ncu_micro.csv).  Now: two loads in flight per thread, more resident blocks, and per element one
+// conversion, one DADD (pair tree for the sum) and one DFMA (squares, two independent chains).
+template <int VEC, int BN_UNROLL, int BN_BLOCKS>
+__global__ void __launch_bounds__(B2Q_THREADS, BN_BLOCKS)
 bnstat_fold_kernel(const float* __restrict__ y, SegPlan pl, b2q_slot* slot, float scale, float* __restrict__ mean_out,
                    float* __restrict__ var_out, BnFold f) {
     b2q_pdl_sync();
@@ -48,36 +52,41 @@ bnstat_fold_kernel(const float* __restrict__ y, SegPlan pl, b2q_slot* slot, floa
     if (VEC == 8) {
         const unsigned wpr = (unsigned)((pc.i1 - pc.i0) >> 3);
         const unsigned total = (unsigned)(pc.o1 - pc.o0) * wpr;
-        for (unsigned w0 = threadIdx.x; w0 < total; w0 += 4 * blockDim.x) {
-            f8 v[4];
+        const float* base = y + (pc.o0 * pl.groups + pc.g) * pl.inner + pc.i0;
+        const int64_t ostride = pl.groups * pl.inner;
+        double q0 = 0.0, q1 = 0.0;
+        for (unsigned w0 = threadIdx.x; w0 < total; w0 += BN_UNROLL * blockDim.x) {
+            f8 v[BN_UNROLL];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < BN_UNROLL; ++k) {
                 const unsigned w = w0 + k * blockDim.x;
                 if (w < total) {
                     const unsigned o = w / wpr, i = w - o * wpr;
-                    v[k] = ld_f8<0>(y + ((pc.o0 + o) * pl.groups + pc.g) * pl.inner + pc.i0 + 8 * (int64_t)i);
+                    v[k] = ld_f8<1>(base + o * ostride + 8 * (int64_t)i);
                 } else {
 #pragma unroll
                     for (int e = 0; e < 8; ++e) v[k].v[e] = 0.f;
                 }
             }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-#pragma unroll
-                for (int e = 0; e < 8; e += 2) {
-                    const double a = (double)v[k].v[e], b = (double)v[k].v[e + 1];
-                    s += a + b;
-                    ss += a * a + b * b;
-                }
+            for (int k = 0; k < BN_UNROLL; ++k) {
+                const double d0 = (double)v[k].v[0], d1 = (double)v[k].v[1], d2 = (double)v[k].v[2], d3 = (double)v[k].v[3];
+                const double d4 = (double)v[k].v[4], d5 = (double)v[k].v[5], d6 = (double)v[k].v[6], d7 = (double)v[k].v[7];
+                s += ((d0 + d1) + (d2 + d3)) + ((d4 + d5) + (d6 + d7));
+                q0 = fma(d0, d0, q0); q1 = fma(d1, d1, q1);
+                q0 = fma(d2, d2, q0); q1 = fma(d3, d3, q1);
+                q0 = fma(d4, d4, q0); q1 = fma(d5, d5, q1);
+                q0 = fma(d6, d6, q0); q1 = fma(d7, d7, q1);
             }
         }
+        ss = q0 + q1;
     } else {
         for (int64_t o = pc.o0; o < pc.o1; ++o) {
             const float* base = y + (o * pl.groups + pc.g) * pl.inner;
             for (int64_t i = pc.i0 + threadIdx.x; i < pc.i1; i += blockDim.x) {
                 const double a = (double)base[i];
                 s += a;
-                ss += a * a;
+                ss = fma(a, a, ss);
             }
         }
     }
@@ -141,7 +150,7 @@ static int launch_bnstat(b2q_ctx* ctx, const float* y, int64_t n, int64_t c, int
                          cudaStream_t st) {
     B2Q_REQUIRE(y && mean && var && n >= 1 && c >= 1 && hw >= 1, "bad argument");
     B2Q_REQUIRE(c <= B2Q_MAX_GROUPS, "too many channels (max 8192)");
-    SegPlan pl = b2q_seg_plan(y, nullptr, n, c, hw, ctx->num_sms * 16);
+    SegPlan pl = b2q_seg_plan(y, nullptr, n, c, hw, ctx->num_sms * (ctx->bn_pieces_per_sm > 0 ? ctx->bn_pieces_per_sm : 16));
     while ((int64_t)c * pl.S * pl.P > B2Q_MAX_PIECES / 2 && pl.S > 1) --pl.S;   // two partials per piece
     B2Q_REQUIRE((int64_t)c * pl.S * pl.P <= B2Q_MAX_PIECES / 2, "activation too large for one statistics launch");
     // fl(C / size) as batch_norm_v1-inl.h computes it: two float operands
@@ -150,8 +159,21 @@ static int launch_bnstat(b2q_ctx* ctx, const float* y, int64_t n, int64_t c, int
     b2q_slot* slot = b2q_take_slot(ctx, st);
     b2q_timed_launch tl(ctx, B2Q_KIND_OTHER, 4.0 * (double)(n * c * hw), st);
     const bool vec8 = (hw % 8 == 0) && (pl.part % 8 == 0) && ((((uintptr_t)y) & 31) == 0);
-    if (vec8) b2q_launch(ctx, bnstat_fold_kernel<8>, grid, B2Q_THREADS, st, y, pl, slot, scale, mean, var, f);
-    else b2q_launch(ctx, bnstat_fold_kernel<1>, grid, B2Q_THREADS, st, y, pl, slot, scale, mean, var, f);
+    // (loads in flight per thread, resident blocks per SM); option bn_variant, default 0 (tools/gpu_r2h.sh A/B)
+#define B2Q_BN_LAUNCH(U, B) do {                                                                                          \
+        if (vec8) b2q_launch(ctx, bnstat_fold_kernel<8, U, B>, grid, B2Q_THREADS, st, y, pl, slot, scale, mean, var, f);   \
+        else b2q_launch(ctx, bnstat_fold_kernel<1, U, B>, grid, B2Q_THREADS, st, y, pl, slot, scale, mean, var, f);         \
+    } while (0)
+    switch (ctx->bn_variant) {
+        case 1: B2Q_BN_LAUNCH(2, 5); break;
+        case 2: B2Q_BN_LAUNCH(3, 4); break;
+        case 3: B2Q_BN_LAUNCH(4, 3); break;
+        case 4: B2Q_BN_LAUNCH(1, 8); break;
+        case 5: B2Q_BN_LAUNCH(1, 6); break;
+        case 6: B2Q_BN_LAUNCH(2, 6); break;
+        default: B2Q_BN_LAUNCH(2, 4); break;
+    }
+#undef B2Q_BN_LAUNCH
     B2Q_LAUNCH_CHECK(ctx);
     return 0;
 }

@@ -75,6 +75,8 @@ struct b2q_ctx {
     int resident_max_mb = 72;        // largest tensor (MB) that takes the single-launch resident forward
     int peer_mode = 1;               // 1: ticket-free reduction, the sweep's first block publishes to the peers; 0: r1 kernels;
                                      // 2 / 3: as 1 with one / two further tiles per block staged in shared memory during the wait
+    int bn_variant = 0;              // bnstat_fold_kernel tuning variant (b2q_bnfold.cu)
+    int bn_pieces_per_sm = 16;       // pieces (blocks) per SM the batch-statistics launch is split into
     int peer_stage_early = 0;        // 1: issue the staging copies before the dependency wait instead of right after it
     int peer_timeout_ms = 600000;    // how long a sweep waits for a peer's statistic before it gives up (NaN output + flag)
     int timing = 0;

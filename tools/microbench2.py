@@ -20,10 +20,13 @@ def run(torch, ctx, peak_gbs, quick=False, verbose=False):
 
     NB = 4 if quick else 6
     reps_big = 8 if quick else 12
+    once = os.environ.get("B2Q_MICRO_ONCE") == "1"     # profiling aid: every line launched twice (ncu captures them)
     rows = {}
 
     def bench(name, fn, alg_bytes, reps=reps_big):
-        for i in range(3):
+        if once:
+            reps = 1
+        for i in range(1 if once else 3):
             fn(i % NB)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -111,6 +114,17 @@ def run(torch, ctx, peak_gbs, quick=False, verbose=False):
     bench("CLIP_RELU fwd (sweep)", lambda i: o.forward(True, ["write"], [xs[i]], [ys[i]], []), 8 * n)
     thr1 = torch.ones(1, device="cuda")
     bench("int8 export (codes + step)", lambda i: K.export_int8(xs[i], thr1, 127, _lib.CLIP_SYM), 5 * n)
+    # ---- batch statistics of the conv output + fold + per-channel weight QDQ + bias, one launch ----
+    for cshape, wshape in (((256, 64, 64, 64), (64, 64, 3, 3)), ((256, 1024, 16, 16), (1024, 512, 1, 1))):
+        c = cshape[1]
+        conv = [x_.view(cshape) for x_ in xs]
+        w_ = torch.randn(wshape, device="cuda") * 0.05
+        wq_, bias_, aw_ = torch.empty_like(w_), torch.empty(c, device="cuda"), torch.ones(c, device="cuda")
+        mu_, var_ = torch.empty(c, device="cuda"), torch.empty(c, device="cuda")
+        gmm_, bt_ = torch.rand(c, device="cuda") + 0.5, torch.randn(c, device="cuda")
+        bench("BN batch stats + fold + weight QDQ + bias, conv out %s (one launch)" % "x".join(map(str, cshape)),
+              lambda i: K.bnstat_foldbn_weight_fwd(conv[i], mu_, var_, w_, wq_, bias_, aw_, gmm_, bt_, 1e-5, True, True, True),
+              4 * n + 8 * w_.numel())
     del xs, ys, dys
     torch.cuda.empty_cache()
 

@@ -230,7 +230,9 @@ int b2q_qil_bwd_f32(b2q_ctx* ctx, int variant, const float* x, const float* dy, 
  * max|tanh(w)| = max(tanhf(max|w|), max of tanhf over the elements in a 129-ulp window around |w| = 0.6): tanhf is odd,
  * monotonic non-decreasing over all finite positive floats outside that window, and the window's values lie between
  * tanhf of its lowest float and tanhf of the first float above it.  which = 3 / 4 (diagnostic): bit pattern of the
- * largest x with tanhf(next(x)) < tanhf(x) / with tanhf(-x) != -tanhf(x), 0 if none.  Synchronous.              */
+ * largest x with tanhf(next(x)) < tanhf(x) / with tanhf(-x) != -tanhf(x), 0 if none.  which = 5: the float32 ->
+ * float64 conversion on the integer pipe that every double-precision sum uses (mean|x| of GDRQ_PY / GDRQ_Fold_BN,
+ * BatchNorm_v1 statistics) against the conversion instruction over all 2^32 bit patterns.  Synchronous.          */
 int b2q_selftest(b2q_ctx* ctx, int which, int64_t* failures);
 
 /* ---- multi-tensor: every weight of a network in two launches (forward) / one launch (backward) ---------

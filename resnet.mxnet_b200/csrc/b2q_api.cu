@@ -90,6 +90,9 @@ static int* option_slot(b2q_ctx* ctx, const char* key) {
     if (!strcmp(key, "resident")) return &ctx->resident;
     if (!strcmp(key, "resident_max_mb")) return &ctx->resident_max_mb;
     if (!strcmp(key, "peer_mode")) return &ctx->peer_mode;
+    if (!strcmp(key, "stream_reduce")) return &ctx->stream_reduce;
+    if (!strcmp(key, "stream_stages")) return &ctx->stream_stages;
+    if (!strcmp(key, "stream_icvt")) return &ctx->stream_icvt;
     if (!strcmp(key, "bn_variant")) return &ctx->bn_variant;
     if (!strcmp(key, "bn_pieces_per_sm")) return &ctx->bn_pieces_per_sm;
     if (!strcmp(key, "peer_stage_early")) return &ctx->peer_stage_early;

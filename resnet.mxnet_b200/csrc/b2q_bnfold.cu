@@ -37,24 +37,33 @@ struct BnFold {
 
 // Register budget matters more than anything else here: the first version held four 256-bit words plus their
 // double-precision images per thread (94 registers -> 2 blocks per SM, 24 % of the warps, 30 % of DRAM throughput in ncu,
-// profiles/r02g_ncu_micro.csv).  Now: two loads in flight per thread, more resident blocks, and per element one
-// conversion, one DADD (pair tree for the sum) and one DFMA (squares, two independent chains).
-template <int VEC, int BN_UNROLL, int BN_BLOCKS>
+// profiles/r02g_ncu_micro.csv; 0.38 of the copy peak).  Now each element is converted, added and squared inside ONE asm
+// statement (acc1_sq_asm: the compiler cannot convert a batch of words first and keep 32 doubles alive), two alternating
+// chains per sum: 48 registers with two loads in flight and five resident blocks -> 0.72-0.78 of the copy peak
+// (profiles/r02i_bnstat_pipes.md; the segmented max|x| reduction, which has no fp64 work at all, reaches 0.82 on the
+// same access pattern).  BN_UNROLL / BN_BLOCKS / ICVT variants are selectable (options bn_variant, stream_icvt).
+template <int VEC, int BN_UNROLL, int BN_BLOCKS, int ICVT>
 __global__ void __launch_bounds__(B2Q_THREADS, BN_BLOCKS)
 bnstat_fold_kernel(const float* __restrict__ y, SegPlan pl, b2q_slot* slot, float scale, float* __restrict__ mean_out,
-                   float* __restrict__ var_out, BnFold f) {
+                   float* __restrict__ var_out, BnFold f, int nst) {
     b2q_pdl_sync();
     __shared__ double smem[32];
     __shared__ unsigned int s_ticket;
     __shared__ float s_val[2];
     const SegPiece pc = seg_piece(pl);
     double s = 0.0, ss = 0.0;
-    if (VEC == 8) {
+    if (VEC >= 16) {   // TMA-staged ring (b2q_reduce.cuh: seg_stream_accumulate); 17: conversions on the integer pipe
+        extern __shared__ __align__(128) unsigned char s_dyn[];
+        float* s_buf = reinterpret_cast<float*>(s_dyn);
+        unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_dyn + (size_t)nst * B2Q_STREAM_CH * 4);
+        float unused = 0.f;
+        seg_stream_accumulate<2, VEC == 17>(y, pl, pc, s_buf, s_bar, nst, s, ss, unused);
+    } else if (VEC == 8) {
         const unsigned wpr = (unsigned)((pc.i1 - pc.i0) >> 3);
         const unsigned total = (unsigned)(pc.o1 - pc.o0) * wpr;
         const float* base = y + (pc.o0 * pl.groups + pc.g) * pl.inner + pc.i0;
         const int64_t ostride = pl.groups * pl.inner;
-        double q0 = 0.0, q1 = 0.0;
+        double q0 = 0.0, q1 = 0.0, s1 = 0.0;
         for (unsigned w0 = threadIdx.x; w0 < total; w0 += BN_UNROLL * blockDim.x) {
             f8 v[BN_UNROLL];
 #pragma unroll
@@ -70,15 +79,10 @@ bnstat_fold_kernel(const float* __restrict__ y, SegPlan pl, b2q_slot* slot, floa
             }
 #pragma unroll
             for (int k = 0; k < BN_UNROLL; ++k) {
-                const double d0 = (double)v[k].v[0], d1 = (double)v[k].v[1], d2 = (double)v[k].v[2], d3 = (double)v[k].v[3];
-                const double d4 = (double)v[k].v[4], d5 = (double)v[k].v[5], d6 = (double)v[k].v[6], d7 = (double)v[k].v[7];
-                s += ((d0 + d1) + (d2 + d3)) + ((d4 + d5) + (d6 + d7));
-                q0 = fma(d0, d0, q0); q1 = fma(d1, d1, q1);
-                q0 = fma(d2, d2, q0); q1 = fma(d3, d3, q1);
-                q0 = fma(d4, d4, q0); q1 = fma(d5, d5, q1);
-                q0 = fma(d6, d6, q0); q1 = fma(d7, d7, q1);
+                acc8_sq_seq<ICVT>(s, s1, q0, q1, v[k]);
             }
         }
+        s += s1;
         ss = q0 + q1;
     } else {
         for (int64_t o = pc.o0; o < pc.o1; ++o) {
@@ -115,7 +119,7 @@ bnstat_fold_kernel(const float* __restrict__ y, SegPlan pl, b2q_slot* slot, floa
         const double dm = (double)mean;
         const double dev = SS - 2.0 * dm * S + n * dm * dm;          // sum of (x - mean)^2
         s_val[0] = mean;
-        s_val[1] = __fmul_rn(scale, (float)(dev > 0.0 ? dev : 0.0));
+        s_val[1] = __fmul_rn(scale, (float)(dev < 0.0 ? 0.0 : dev));   // NaN (a NaN / Inf in the channel) stays NaN
         mean_out[c] = s_val[0];
         var_out[c] = s_val[1];
         slot->row_ticket[c] = 0;
@@ -159,17 +163,34 @@ static int launch_bnstat(b2q_ctx* ctx, const float* y, int64_t n, int64_t c, int
     b2q_slot* slot = b2q_take_slot(ctx, st);
     b2q_timed_launch tl(ctx, B2Q_KIND_OTHER, 4.0 * (double)(n * c * hw), st);
     const bool vec8 = (hw % 8 == 0) && (pl.part % 8 == 0) && ((((uintptr_t)y) & 31) == 0);
-    // (loads in flight per thread, resident blocks per SM); option bn_variant, default 0 (tools/gpu_r2h.sh A/B)
+    if (vec8 && ctx->stream_reduce && b2q_stream_ok(pl)) {
+        const int nst = b2q_stream_stages(ctx);
+        const size_t smem = b2q_stream_smem(nst);
+        if (ctx->stream_icvt) {
+            B2Q_CHECK_CUDA(b2q_allow_smem(bnstat_fold_kernel<17, 1, 1, 0>, smem));
+            b2q_launch_smem(ctx, bnstat_fold_kernel<17, 1, 1, 0>, grid, B2Q_THREADS, smem, st, y, pl, slot, scale, mean, var, f, nst);
+        } else {
+            B2Q_CHECK_CUDA(b2q_allow_smem(bnstat_fold_kernel<16, 1, 1, 0>, smem));
+            b2q_launch_smem(ctx, bnstat_fold_kernel<16, 1, 1, 0>, grid, B2Q_THREADS, smem, st, y, pl, slot, scale, mean, var, f, nst);
+        }
+        B2Q_LAUNCH_CHECK(ctx);
+        return 0;
+    }
+    // (loads in flight per thread, resident blocks per SM); option bn_variant
 #define B2Q_BN_LAUNCH(U, B) do {                                                                                          \
-        if (vec8) b2q_launch(ctx, bnstat_fold_kernel<8, U, B>, grid, B2Q_THREADS, st, y, pl, slot, scale, mean, var, f);   \
-        else b2q_launch(ctx, bnstat_fold_kernel<1, U, B>, grid, B2Q_THREADS, st, y, pl, slot, scale, mean, var, f);         \
+        if (!vec8) b2q_launch(ctx, bnstat_fold_kernel<1, U, B, 0>, grid, B2Q_THREADS, st, y, pl, slot, scale, mean, var, f, 0);  \
+        else if (ctx->stream_icvt == 1)                                                                                    \
+            b2q_launch(ctx, bnstat_fold_kernel<8, U, B, 1>, grid, B2Q_THREADS, st, y, pl, slot, scale, mean, var, f, 0);       \
+        else if (ctx->stream_icvt == 2)                                                                                    \
+            b2q_launch(ctx, bnstat_fold_kernel<8, U, B, 2>, grid, B2Q_THREADS, st, y, pl, slot, scale, mean, var, f, 0);       \
+        else b2q_launch(ctx, bnstat_fold_kernel<8, U, B, 0>, grid, B2Q_THREADS, st, y, pl, slot, scale, mean, var, f, 0);      \
     } while (0)
     switch (ctx->bn_variant) {
         case 1: B2Q_BN_LAUNCH(2, 5); break;
-        case 2: B2Q_BN_LAUNCH(3, 4); break;
-        case 3: B2Q_BN_LAUNCH(4, 3); break;
-        case 4: B2Q_BN_LAUNCH(1, 8); break;
-        case 5: B2Q_BN_LAUNCH(1, 6); break;
+        case 2: B2Q_BN_LAUNCH(4, 4); break;
+        case 3: B2Q_BN_LAUNCH(4, 5); break;
+        case 4: B2Q_BN_LAUNCH(2, 8); break;
+        case 5: B2Q_BN_LAUNCH(4, 6); break;
         case 6: B2Q_BN_LAUNCH(2, 6); break;
         default: B2Q_BN_LAUNCH(2, 4); break;
     }

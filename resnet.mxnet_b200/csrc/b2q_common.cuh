@@ -3,6 +3,7 @@
 #include <utility>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -75,8 +76,11 @@ struct b2q_ctx {
     int resident_max_mb = 72;        // largest tensor (MB) that takes the single-launch resident forward
     int peer_mode = 1;               // 1: ticket-free reduction, the sweep's first block publishes to the peers; 0: r1 kernels;
                                      // 2 / 3: as 1 with one / two further tiles per block staged in shared memory during the wait
-    int bn_variant = 0;              // bnstat_fold_kernel tuning variant (b2q_bnfold.cu)
-    int bn_pieces_per_sm = 16;       // pieces (blocks) per SM the batch-statistics launch is split into
+    int stream_reduce = 0;           // 1: segmented / batch-statistics reductions through the TMA-staged ring when eligible (measured slower)
+    int stream_stages = 4;           // 16 KB stages per block of that ring
+    int stream_icvt = 0;             // float -> double conversions of the statistics kernels: 0 XU pipe, 1 integer pipe, 2 half / half
+    int bn_variant = 1;              // bnstat_fold_kernel tuning variant (b2q_bnfold.cu)
+    int bn_pieces_per_sm = 8;        // pieces (blocks) per SM the batch-statistics launch is split into
     int peer_stage_early = 0;        // 1: issue the staging copies before the dependency wait instead of right after it
     int peer_timeout_ms = 600000;    // how long a sweep waits for a peer's statistic before it gives up (NaN output + flag)
     int timing = 0;
@@ -249,6 +253,38 @@ __device__ __forceinline__ void st_i8(int32_t* p, const int (&c)[8]) {
                  : "memory");
 }
 
+// ---- exact float32 -> float64 on the integer pipe (option stream_icvt; OFF by default) ---------------------------------
+// Every sum in this library is accumulated in double (deterministic, correctly rounded results), one conversion per
+// element.  F2F.F64.F32 issues on the XU pipe, which ncu shows 64-77 % busy at 44-49 % of DRAM throughput in the
+// batch-statistics kernel.  The same value is available from four integer instructions: the float's exponent and
+// mantissa fields dropped into a double's (shift by 3 / 29 bits) give x * 2^-896 EXACTLY for every finite x -- zeros and
+// denormals included, because a float denormal m * 2^-149 lands on the double denormal m * 2^-1045 -- and one
+// multiplication by 2^896 (exact) restores the scale.  Only Inf / NaN (exponent field 255) do not map: the caller tests
+// for them and redoes the word with the real conversion.  b2q_selftest(5) compares both conversions over all 2^32 bit
+// patterns.  MEASURED (profiles/r02i_bnstat_pipes.md): equal bits, but 5-8 % slower than the conversion instruction in
+// every kernel tried (four ALU instructions + a DMUL per element cost more issue slots than the XU pipe saves), so the
+// kernels keep the instruction; the option remains for A/B runs.
+__device__ __forceinline__ double b2q_two_p896() { return __hiloint2double(0x77f00000, 0); }   // 2^896
+__device__ __forceinline__ double b2q_two_m896() { return __hiloint2double(0x07f00000, 0); }   // 2^-896
+
+__device__ __forceinline__ double f2d_scaled(float x, bool& special) {           // x * 2^-896
+    const unsigned f = __float_as_uint(x), a = f & 0x7fffffffu;
+    special |= (a >= 0x7f800000u);
+    return __hiloint2double((int)((a >> 3) | (f & 0x80000000u)), (int)(f << 29));
+}
+
+__device__ __forceinline__ double f2d_abs_scaled(float x, bool& special) {       // |x| * 2^-896
+    const unsigned a = __float_as_uint(x) & 0x7fffffffu;
+    special |= (a >= 0x7f800000u);
+    return __hiloint2double((int)(a >> 3), (int)(a << 29));
+}
+
+__device__ __forceinline__ double f2d_cvt(float x) {   // the conversion instruction, not speculated by the compiler
+    double d;
+    asm volatile("cvt.f64.f32 %0, %1;" : "=d"(d) : "f"(x));
+    return d;
+}
+
 // First statement of every kernel launched through b2q_launch (no effect for an ordinary launch).
 __device__ __forceinline__ void b2q_pdl_sync() {
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -308,16 +344,24 @@ __device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gsrc, 
                  : "memory");
 }
 
-// Kernels that stage tiles in shared memory and bypass L1 for their global accesses: ask for the largest shared-memory
-// carve-out once per kernel so that the register-limited number of blocks stays resident.
-template <typename K>
-static inline void b2q_prefer_shared(K kernel) {
-    static bool done = false;
-    if (!done) {
-        cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        done = true;
-    }
+// Kernels that stage tiles in shared memory: ask once per KERNEL (keyed by its address -- template instantiations share
+// a function-pointer type) for the dynamic shared memory it needs and the largest shared-memory carve-out.
+static inline cudaError_t b2q_kernel_smem_once(const void* kernel, size_t dyn_smem) {
+    static std::mutex mu;
+    static std::map<const void*, size_t> done;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = done.find(kernel);
+    if (it != done.end() && it->second >= dyn_smem) return cudaSuccess;
+    cudaError_t e = cudaSuccess;
+    if (dyn_smem > 0) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
+    if (e != cudaSuccess) return e;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    done[kernel] = dyn_smem;
+    return cudaSuccess;
 }
+
+template <typename K>
+static inline void b2q_prefer_shared(K kernel) { (void)b2q_kernel_smem_once((const void*)kernel, 0); }
 
 // "Last block finishes" ticket: a release atomic (+ an acquire fence in the one block that draws `last`) instead of
 // __threadfence() + atomicAdd.  __threadfence() is a sequentially consistent fence that also invalidates the SM's whole

@@ -36,19 +36,122 @@ __device__ __forceinline__ void acc1(double& a, float& m, float v) {
     if (IS_MAX) m = fmax_nan(m, fabsf(v)); else a += (double)fabsf(v);
 }
 
-template <bool IS_MAX>
+// ICVT selects where the float -> double conversions of a sum run: false = the conversion instruction (XU pipe; best
+// for the register-staged loops, where occupancy is the limit), true = the integer pipe (f2d_abs_scaled,
+// b2q_common.cuh; for the TMA-staged loops, where the XU pipe would be).  Same bits either way (b2q_selftest(5)).
+template <bool IS_MAX, bool ICVT = false>
 __device__ __forceinline__ void acc8(double& a, float& m, const f8& r) {
     if (IS_MAX) {
         const float m0 = fmax_nan(fabsf(r.v[0]), fabsf(r.v[1])), m1 = fmax_nan(fabsf(r.v[2]), fabsf(r.v[3]));
         const float m2 = fmax_nan(fabsf(r.v[4]), fabsf(r.v[5])), m3 = fmax_nan(fabsf(r.v[6]), fabsf(r.v[7]));
         m = fmax_nan(m, fmax_nan(fmax_nan(m0, m1), fmax_nan(m2, m3)));
-    } else {
+    } else if (!ICVT) {
         // double accumulation: every float32 -> double conversion and each pair sum below 2^53 ulps is exact
         const double s0 = (double)fabsf(r.v[0]) + (double)fabsf(r.v[1]);
         const double s1 = (double)fabsf(r.v[2]) + (double)fabsf(r.v[3]);
         const double s2 = (double)fabsf(r.v[4]) + (double)fabsf(r.v[5]);
         const double s3 = (double)fabsf(r.v[6]) + (double)fabsf(r.v[7]);
         a += (s0 + s1) + (s2 + s3);
+    } else {
+        // the same tree at scale 2^-896 -- which rounds exactly as the unscaled tree does, every operand being a
+        // multiple of 2^-149 * 2^-896 -- rescaled once per word
+        unsigned t = 0;   // bit 31 set iff some exponent field is 255
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t |= (__float_as_uint(r.v[j]) & 0x7fffffffu) + 0x00800000u;
+        if (t & 0x80000000u) {   // Inf / NaN in this word: the real conversion (they propagate as in the reference's sum)
+            const double s0 = f2d_cvt(fabsf(r.v[0])) + f2d_cvt(fabsf(r.v[1])), s1 = f2d_cvt(fabsf(r.v[2])) + f2d_cvt(fabsf(r.v[3]));
+            const double s2 = f2d_cvt(fabsf(r.v[4])) + f2d_cvt(fabsf(r.v[5])), s3 = f2d_cvt(fabsf(r.v[6])) + f2d_cvt(fabsf(r.v[7]));
+            a += (s0 + s1) + (s2 + s3);
+        } else {
+            bool unused = false;
+            const double s0 = f2d_abs_scaled(r.v[0], unused) + f2d_abs_scaled(r.v[1], unused);
+            const double s1 = f2d_abs_scaled(r.v[2], unused) + f2d_abs_scaled(r.v[3], unused);
+            const double s2 = f2d_abs_scaled(r.v[4], unused) + f2d_abs_scaled(r.v[5], unused);
+            const double s3 = f2d_abs_scaled(r.v[6], unused) + f2d_abs_scaled(r.v[7], unused);
+            a += ((s0 + s1) + (s2 + s3)) * b2q_two_p896();
+        }
+    }
+}
+
+// sum and sum of squares of one 256-bit word (BatchNorm_v1 statistics, b2q_bnfold.cu): one conversion, one DADD (pair
+// tree) and one DFMA (two independent chains) per element
+template <bool ICVT>
+__device__ __forceinline__ void acc8_sq(double& s, double& q0, double& q1, const f8& r) {
+    double d[8];
+    if (!ICVT) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d[e] = (double)r.v[e];
+    } else {
+        unsigned t = 0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) t |= (__float_as_uint(r.v[e]) & 0x7fffffffu) + 0x00800000u;
+        if (t & 0x80000000u) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) d[e] = f2d_cvt(r.v[e]);
+        } else {
+            bool unused = false;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) d[e] = f2d_scaled(r.v[e], unused) * b2q_two_p896();   // exact
+        }
+    }
+    s += ((d[0] + d[1]) + (d[2] + d[3])) + ((d[4] + d[5]) + (d[6] + d[7]));
+    q0 = fma(d[0], d[0], q0); q1 = fma(d[1], d[1], q1);
+    q0 = fma(d[2], d[2], q0); q1 = fma(d[3], d[3], q1);
+    q0 = fma(d[4], d[4], q0); q1 = fma(d[5], d[5], q1);
+    q0 = fma(d[6], d[6], q0); q1 = fma(d[7], d[7], q1);
+}
+
+// The same sums with the smallest register footprint: each element is converted, added and squared before the next
+// one is touched (two alternating chains per sum), so only the loaded words and four accumulators stay live and more
+// loads fit in flight per SM -- what the register-staged segmented loops are short of (profiles/r02i_bnstat_pipes.md).
+__device__ __forceinline__ void acc1_sq_asm(double& s, double& q, float x) {
+    // one statement, so that the compiler cannot convert a whole batch of words first and keep the doubles alive
+    asm volatile("{\n\t.reg .f64 d;\n\tcvt.f64.f32 d, %2;\n\tadd.rn.f64 %0, %0, d;\n\tfma.rn.f64 %1, d, d, %1;\n\t}"
+                 : "+d"(s), "+d"(q)
+                 : "f"(x));
+}
+
+// the same step with the conversion on the integer pipe (f2d_scaled, b2q_common.cuh); finite x only
+__device__ __forceinline__ void acc1_sq_asm_icvt(double& s, double& q, float x) {
+    asm volatile(
+        "{\n\t.reg .f64 d;\n\t.reg .b32 a, hi, lo;\n\t"
+        "and.b32 a, %2, 0x7fffffff;\n\tshr.u32 hi, a, 3;\n\tlop3.b32 hi, hi, %2, 0x80000000, 0xf8;\n\tshl.b32 lo, %2, 29;\n\t"
+        "mov.b64 d, {lo, hi};\n\tmul.rn.f64 d, d, %3;\n\tadd.rn.f64 %0, %0, d;\n\tfma.rn.f64 %1, d, d, %1;\n\t}"
+        : "+d"(s), "+d"(q)
+        : "r"(__float_as_uint(x)), "d"(b2q_two_p896()));
+}
+
+// CVT: 0 = every conversion on the XU pipe, 1 = every conversion on the integer pipe, 2 = half and half (elements 0-3 /
+// 4-7 of the word), which loads both pipes
+template <int CVT>
+__device__ __forceinline__ void acc8_sq_seq(double& s0, double& s1, double& q0, double& q1, const f8& r) {
+    const int first_int = CVT == 1 ? 0 : (CVT == 2 ? 4 : 8);   // elements [first_int, 8) go through the integer pipe
+    bool fast = true;
+    if (CVT != 0) {
+        unsigned t = 0;   // bit 31 set iff some exponent field is 255 (Inf / NaN): those words take the real conversion
+#pragma unroll
+        for (int e = first_int; e < 8; ++e) t |= (__float_as_uint(r.v[e]) & 0x7fffffffu) + 0x00800000u;
+        fast = (t & 0x80000000u) == 0;
+    }
+#pragma unroll
+    for (int e = 0; e < first_int; e += 2) {
+        acc1_sq_asm(s0, q0, r.v[e]);
+        acc1_sq_asm(s1, q1, r.v[e + 1]);
+    }
+    if (CVT != 0) {
+        if (fast) {
+#pragma unroll
+            for (int e = first_int; e < 8; e += 2) {
+                acc1_sq_asm_icvt(s0, q0, r.v[e]);
+                acc1_sq_asm_icvt(s1, q1, r.v[e + 1]);
+            }
+        } else {
+#pragma unroll
+            for (int e = first_int; e < 8; e += 2) {
+                acc1_sq_asm(s0, q0, r.v[e]);
+                acc1_sq_asm(s1, q1, r.v[e + 1]);
+            }
+        }
     }
 }
 
@@ -185,6 +288,91 @@ __device__ __forceinline__ SegPiece seg_piece(const SegPlan& pl) {
     return sp;
 }
 
+// ------------------------------------------------------------------------------------------------
+// TMA-staged accumulation of one piece of an (outer, groups, inner) view (option stream_reduce = 1; OFF by default).
+// The register-staged loops below keep 2-4 256-bit loads per thread in flight: 60-130 KB per SM, and ncu shows the
+// warps waiting on the scoreboard for L1TEX 56 % of the time at 49 % of DRAM throughput.  Here the piece streams through
+// a ring of 16 KB shared-memory stages filled by bulk asynchronous copies (cp.async.bulk + mbarrier transaction counts,
+// L2 evict-first hint): the data in flight (stages x 16 KB per block) costs no registers, and the threads only ever
+// read shared memory.  A row of the piece (contiguous, a multiple of 32 bytes) is cut into sub-rows of at most one
+// stage; short rows are packed several to a stage, one copy each, issued by the lanes of warp 0.  Because this is a
+// reduction, which thread takes which 16 bytes of a stage is free: thread t reads the float4s t and t + 256,
+// conflict-free.  MEASURED (profiles/r02i_bnstat_pipes.md): bit-identical results, but 10-25 % SLOWER than the
+// register-staged loops at every ring depth -- a 16 KB stage is one loop iteration per thread, so the wait / barrier /
+// refill round per stage costs more than the deeper prefetch gains, and deeper rings cost resident blocks.  Kept as a
+// tested option, not as the default.
+//   MODE 0: sum |x|   MODE 1: max |x|   MODE 2: sum x and sum x^2 (acc = sum, acc2 = sum of squares)
+// ------------------------------------------------------------------------------------------------
+#define B2Q_STREAM_CH 4096   // floats per stage (16 KB)
+
+template <int MODE, bool ICVT>
+__device__ __forceinline__ void seg_stream_accumulate(const float* __restrict__ x, const SegPlan& pl, const SegPiece& pc,
+                                                      float* s_buf, unsigned long long* s_bar, int nst, double& acc,
+                                                      double& acc2, float& mx) {
+    const int64_t len = pc.i1 - pc.i0;                    // floats per row inside this piece (multiple of 8)
+    const int64_t rows = pc.o1 - pc.o0;
+    const float* base = x + (pc.o0 * pl.groups + pc.g) * pl.inner + pc.i0;
+    const int64_t ostride = pl.groups * pl.inner;
+    const int cpr = (int)((len + B2Q_STREAM_CH - 1) / B2Q_STREAM_CH);   // sub-rows per row
+    const int L = cpr > 1 ? B2Q_STREAM_CH : (int)len;     // floats per (full) sub-row
+    const int spf = cpr > 1 ? 1 : B2Q_STREAM_CH / L;      // sub-rows per fill
+    const int64_t tsub = rows * cpr;
+    const int64_t fills = (tsub + spf - 1) / spf;
+    const int lane = threadIdx.x & 31;
+    auto fill_floats = [&](int64_t f) -> int {
+        const int64_t j0 = f * spf;
+        if (cpr > 1) {
+            const int64_t c = j0 % cpr;
+            const int64_t n = len - c * B2Q_STREAM_CH;
+            return (int)(n < B2Q_STREAM_CH ? n : B2Q_STREAM_CH);
+        }
+        const int64_t cnt = tsub - j0 < spf ? tsub - j0 : spf;
+        return (int)cnt * L;
+    };
+    auto issue = [&](int64_t f) {   // all lanes of warp 0
+        const int stage = (int)(f % nst);
+        const int64_t j0 = f * spf;
+        const int cnt = (int)(tsub - j0 < spf ? tsub - j0 : spf);
+        const unsigned long long pol = l2_policy_evict_first();
+        if (lane == 0) mbar_expect_tx(&s_bar[stage], (unsigned)fill_floats(f) * 4u);
+        __syncwarp();
+        for (int q = lane; q < cnt; q += 32) {
+            const int64_t j = j0 + q;
+            const int64_t row = j / cpr, c = j - row * cpr;
+            int64_t n = cpr > 1 ? len - c * B2Q_STREAM_CH : (int64_t)L;
+            if (n > B2Q_STREAM_CH) n = B2Q_STREAM_CH;
+            bulk_g2s_hint(s_buf + (size_t)stage * B2Q_STREAM_CH + (size_t)q * L, base + row * ostride + c * B2Q_STREAM_CH,
+                          (unsigned)n * 4u, &s_bar[stage], pol);
+        }
+    };
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < nst; ++i) mbar_init(&s_bar[i], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        for (int64_t f = 0; f < fills && f < nst; ++f) issue(f);
+    }
+    double q0 = 0.0, q1 = 0.0;
+    for (int64_t f = 0; f < fills; ++f) {
+        const int stage = (int)(f % nst);
+        mbar_wait(&s_bar[stage], (unsigned)((f / nst) & 1));
+        const int nq = fill_floats(f) >> 2;               // float4s in this stage (even)
+        const float4* s4 = reinterpret_cast<const float4*>(s_buf + (size_t)stage * B2Q_STREAM_CH);
+        for (int q = threadIdx.x; q < nq; q += 2 * B2Q_THREADS) {
+            const float4 a = s4[q];
+            const float4 b = (q + B2Q_THREADS < nq) ? s4[q + B2Q_THREADS] : make_float4(0.f, 0.f, 0.f, 0.f);
+            f8 v;
+            v.v[0] = a.x; v.v[1] = a.y; v.v[2] = a.z; v.v[3] = a.w; v.v[4] = b.x; v.v[5] = b.y; v.v[6] = b.z; v.v[7] = b.w;
+            if (MODE == 2) acc8_sq<ICVT>(acc, q0, q1, v);
+            else acc8<MODE == 1, ICVT>(acc, mx, v);
+        }
+        __syncthreads();                                   // everyone is done with this stage: refill it
+        if (threadIdx.x < 32 && f + nst < fills) issue(f + nst);
+    }
+    acc2 = q0 + q1;
+}
+
 struct Prescale {  // fold-BN factor gamma/sqrt(var+eps) per row (o*groups+g); gamma == nullptr: none
     const float* gamma;
     const float* var;
@@ -196,15 +384,24 @@ __device__ __forceinline__ float prescale_factor(const Prescale& ps, int64_t row
     return __fdiv_rn(ps.gamma[row], __fsqrt_rn(__fadd_rn(ps.var[row], ps.eps)));
 }
 
+// VEC: 1 / 4 / 8 = register-staged loads of that many floats; 16 / 17 = the TMA-staged ring above (17: float -> double
+// conversions on the integer pipe), `nst` stages of dynamic shared memory
 template <bool IS_MAX, int VEC>
-__global__ void __launch_bounds__(VEC == 8 ? B2Q_THREADS : 128)
-reduce_seg_kernel(const float* __restrict__ x, SegPlan pl, Prescale ps, b2q_slot* slot, UpdateArgs u) {
+__global__ void __launch_bounds__(VEC >= 8 ? B2Q_THREADS : 128)
+reduce_seg_kernel(const float* __restrict__ x, SegPlan pl, Prescale ps, b2q_slot* slot, UpdateArgs u, int nst) {
     b2q_pdl_sync();
     __shared__ double smem[32];
     __shared__ unsigned int s_ticket;
     const SegPiece pc = seg_piece(pl);
     double acc = 0.0;
     float mx = 0.f;
+    if (VEC >= 16) {
+        extern __shared__ __align__(128) unsigned char s_dyn[];
+        float* s_buf = reinterpret_cast<float*>(s_dyn);
+        unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_dyn + (size_t)nst * B2Q_STREAM_CH * 4);
+        double unused = 0.0;
+        seg_stream_accumulate<IS_MAX ? 1 : 0, VEC == 17>(x, pl, pc, s_buf, s_bar, nst, acc, unused, mx);
+    }
     if (VEC == 8) {
         // 256-bit loads, four in flight per thread, over the piece's (row, word) space FLATTENED into one index: short
         // rows (gs = 1 on 56x56 maps: 392 words per row) would otherwise leave most lanes of every iteration idle
@@ -237,7 +434,7 @@ reduce_seg_kernel(const float* __restrict__ x, SegPlan pl, Prescale ps, b2q_slot
             }
         }
     }
-    for (int64_t o = pc.o0; VEC != 8 && o < pc.o1; ++o) {
+    for (int64_t o = pc.o0; VEC < 8 && o < pc.o1; ++o) {
         const int64_t row = o * pl.groups + pc.g;
         const float* base = x + row * pl.inner;
         const float f = ps.gamma ? prescale_factor(ps, row) : 1.f;
@@ -328,6 +525,26 @@ static inline int64_t b2q_flat_grid(const b2q_ctx* ctx, int64_t n8, int unroll, 
     return grid;
 }
 
+// TMA-staged reductions: eligibility (rows of a piece are contiguous runs of >= 1 KB, 16-byte aligned -- guaranteed by the
+// callers' 256-bit checks), number of stages and dynamic shared memory
+static inline bool b2q_stream_ok(const SegPlan& pl) {
+    const int64_t len = pl.P > 1 ? pl.part : pl.inner;
+    const int64_t last = pl.inner - (int64_t)(pl.P - 1) * pl.part;     // the last inner part may be shorter
+    return len >= 256 && last >= 256 && (len % 8) == 0 && (last % 8) == 0;
+}
+
+static inline int b2q_stream_stages(const b2q_ctx* ctx) {
+    int n = ctx->stream_stages;
+    if (n < 2) n = 2;
+    if (n > 12) n = 12;
+    return n;
+}
+
+static inline size_t b2q_stream_smem(int nst) { return (size_t)nst * B2Q_STREAM_CH * 4 + (size_t)nst * 8; }
+
+template <typename K>
+static inline cudaError_t b2q_allow_smem(K kernel, size_t smem) { return b2q_kernel_smem_once((const void*)kernel, smem); }
+
 // Reduction half of the fused whole-tensor forward with the update deferred to the consumer.  Returns the number of
 // partials through *n_partials (0: tensor not eligible, caller must use launch_reduce).
 template <bool IS_MAX>
@@ -367,10 +584,22 @@ static int launch_reduce(b2q_ctx* ctx, b2q_slot* slot, const float* x, int64_t o
     SegPlan pl = b2q_seg_plan(x, nullptr, outer, groups, inner, ctx->num_sms * 16);
     const unsigned grid = (unsigned)(groups * pl.S * pl.P);
     b2q_timed_launch tl(ctx, B2Q_KIND_OTHER, 4.0 * (double)n, st);
-    if (pl.vec == 4 && inner % 8 == 0 && pl.part % 8 == 0 && (((uintptr_t)x) & 31) == 0 && n >= (1 << 20))
-        b2q_launch(ctx, reduce_seg_kernel<IS_MAX, 8>, grid, B2Q_THREADS, st, x, pl, ps, slot, u);
-    else if (pl.vec == 4) b2q_launch(ctx, reduce_seg_kernel<IS_MAX, 4>, grid, 128, st, x, pl, ps, slot, u);
-    else b2q_launch(ctx, reduce_seg_kernel<IS_MAX, 1>, grid, 128, st, x, pl, ps, slot, u);
+    const bool vec8 = pl.vec == 4 && inner % 8 == 0 && pl.part % 8 == 0 && (((uintptr_t)x) & 31) == 0 && n >= (1 << 20);
+    if (vec8 && ctx->stream_reduce && ps.gamma == nullptr && b2q_stream_ok(pl)) {
+        // large activations with rows of at least 1 KB per piece: TMA-staged ring (see seg_stream_accumulate)
+        const int nst = b2q_stream_stages(ctx);
+        const size_t smem = b2q_stream_smem(nst);
+        if (ctx->stream_icvt) {
+            B2Q_CHECK_CUDA(b2q_allow_smem(reduce_seg_kernel<IS_MAX, 17>, smem));
+            b2q_launch_smem(ctx, reduce_seg_kernel<IS_MAX, 17>, grid, B2Q_THREADS, smem, st, x, pl, ps, slot, u, nst);
+        } else {
+            B2Q_CHECK_CUDA(b2q_allow_smem(reduce_seg_kernel<IS_MAX, 16>, smem));
+            b2q_launch_smem(ctx, reduce_seg_kernel<IS_MAX, 16>, grid, B2Q_THREADS, smem, st, x, pl, ps, slot, u, nst);
+        }
+    } else if (vec8)
+        b2q_launch(ctx, reduce_seg_kernel<IS_MAX, 8>, grid, B2Q_THREADS, st, x, pl, ps, slot, u, 0);
+    else if (pl.vec == 4) b2q_launch(ctx, reduce_seg_kernel<IS_MAX, 4>, grid, 128, st, x, pl, ps, slot, u, 0);
+    else b2q_launch(ctx, reduce_seg_kernel<IS_MAX, 1>, grid, 128, st, x, pl, ps, slot, u, 0);
     B2Q_LAUNCH_CHECK(ctx);
     return 0;
 }

@@ -614,16 +614,41 @@ __global__ void selftest_tanh_kernel(unsigned long long* bad, int mode) {
     }
 }
 
+// mode 5: the integer-pipe float32 -> float64 conversion (f2d_scaled / f2d_abs_scaled, b2q_common.cuh) against the
+// conversion instruction over ALL 2^32 bit patterns: equal bits for every finite value (zeros, denormals), `special`
+// raised exactly for Inf / NaN; and the scaled value times 2^896 is the value itself.
+__global__ void selftest_f2d_kernel(unsigned long long* bad) {
+    unsigned long long local = 0;
+    for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b < (1ull << 32);
+         b += (unsigned long long)gridDim.x * blockDim.x) {
+        const float x = __uint_as_float((unsigned int)b);
+        const bool finite = ((unsigned int)b & 0x7f800000u) != 0x7f800000u;
+        bool sp = false, spa = false;
+        const double d = f2d_scaled(x, sp) * b2q_two_p896();
+        const double da = f2d_abs_scaled(x, spa) * b2q_two_p896();
+        const double ref = f2d_cvt(x), refa = f2d_cvt(fabsf(x));
+        if (sp == finite || spa == finite) ++local;
+        if (finite && (__double_as_longlong(d) != __double_as_longlong(ref) ||
+                       __double_as_longlong(da) != __double_as_longlong(refa))) ++local;
+        // the scaled image is exact too: scaling the reference down gives the same bits
+        bool t = false;
+        if (finite && __double_as_longlong(f2d_scaled(x, t)) != __double_as_longlong(ref * b2q_two_m896())) ++local;
+    }
+    if (local) atomicAdd(bad, local);
+}
+
 extern "C" {
 
 int b2q_selftest(b2q_ctx* ctx, int which, int64_t* failures) {
     B2Q_CTX(ctx);
-    B2Q_REQUIRE(failures != nullptr && which >= 1 && which <= 4,
-                "which: 1 level division, 2 tanhf monotonic/odd (count), 3 / 4 where (bit pattern of the largest x)");
+    B2Q_REQUIRE(failures != nullptr && which >= 1 && which <= 5,
+                "which: 1 level division, 2 tanhf monotonic/odd (count), 3 / 4 where (bit pattern of the largest x), "
+                "5 integer-pipe float -> double conversion");
     unsigned long long* d = nullptr;
     B2Q_CHECK_CUDA(cudaMalloc(&d, sizeof(unsigned long long)));
     B2Q_CHECK_CUDA(cudaMemset(d, 0, sizeof(unsigned long long)));
     if (which == 1) selftest_div_level_kernel<<<ctx->num_sms, 256>>>(d);
+    else if (which == 5) selftest_f2d_kernel<<<ctx->num_sms * 8, 256>>>(d);
     else selftest_tanh_kernel<<<ctx->num_sms * 8, 256>>>(d, which);
     unsigned long long h = 0;
     cudaError_t e = cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost);

@@ -113,3 +113,89 @@ def test_foldbn_layer_twin_fused_equals_unfused_and_trains(group):
                                             "stage1_fold_bn_data_minmax", "stage1_fold_bn_weight_minmax"]
     for k in auxa:
         assert T.equal(auxa[k], auxb[k]), k
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 6])
+def test_batch_stats_conversion_paths_agree_on_special_values(variant):
+    """The statistics kernel converts float32 -> float64 on the integer pipe (option stream_icvt, default on; exact for
+    every finite value, b2q_selftest(5)) and falls back to the conversion instruction for words holding Inf / NaN.
+    Channels of zeros, negative zeros, denormals, huge values, Inf and NaN: both paths give the same bits, for every
+    tuning variant of the kernel, and equal the double-precision NumPy statistics where those are finite."""
+    import torch as T
+    import b200quant._kernels as K
+    from b200quant import _lib
+    rng = np.random.default_rng(17)
+    y = rng.standard_normal((6, 12, 16, 16)).astype(F)
+    y[:, 1] = 0.0
+    y[:, 2] = -0.0
+    y[:, 3] = (rng.integers(1, 1 << 22, size=(6, 16, 16)).astype(np.uint32)).view(F)            # denormals
+    y[:, 4] = y[:, 4] * F(1e30)
+    y[2, 5, 3, 3] = np.inf
+    y[1, 6, 0, 0] = np.nan
+    y[:, 7, ::2] = 0.0                                                                           # half zeros (post-ReLU)
+    y[0, 8, 0, 0] = -np.inf
+    y[:, 9] = F(3.0)                                                                             # constant: variance 0
+    ctx = _lib.context(0)
+    saved = {k: ctx.get_option(k) for k in ("stream_icvt", "bn_variant")}
+    got = []
+    try:
+        ctx.set_option("bn_variant", variant)
+        for icvt in (1, 2, 0):
+            ctx.set_option("stream_icvt", icvt)
+            mean, var = T.empty(12, device="cuda"), T.empty(12, device="cuda")
+            K.bn_batch_stats(dev(T, y), mean, var)
+            got.append((mean.cpu().numpy(), var.cpu().numpy()))
+    finally:
+        for k, v in saved.items():
+            ctx.set_option(k, v)
+    for other in got[1:]:
+        assert bits_equal(got[0][0], other[0]) and bits_equal(got[0][1], other[1])
+    mean, var = got[0]
+    yd = y.astype(np.float64)
+    finite = [0, 1, 2, 3, 7, 9, 10, 11]
+    want_m = yd.mean(axis=(0, 2, 3))
+    want_v = yd.var(axis=(0, 2, 3))
+    np.testing.assert_allclose(mean[finite], want_m[finite], rtol=1e-6, atol=1e-37)
+    np.testing.assert_allclose(var[finite], want_v[finite], rtol=2e-6, atol=1e-37)
+    assert mean[1] == 0.0 and var[1] == 0.0 and mean[2] == 0.0 and var[9] == 0.0 and mean[9] == 3.0
+    assert np.isinf(mean[5]) and np.isnan(mean[6]) and np.isnan(var[6]) and mean[8] == -np.inf
+
+
+def test_tma_staged_ring_gives_the_same_bits_as_the_register_loops():
+    """option stream_reduce=1 routes the batch statistics and the grouped mean|x| / max|x| reductions through a ring of
+    16 KB shared-memory stages filled by bulk asynchronous copies (off by default: measured slower).  Same bits as the
+    default path: rows longer than a stage, rows packed several to a stage, a ragged last stage, 2..6 stages."""
+    import torch as T
+    import b200quant._kernels as K
+    from b200quant import _lib
+    ctx = _lib.context(0)
+    saved = {k: ctx.get_option(k) for k in ("stream_reduce", "stream_stages", "stream_icvt")}
+    g = T.Generator(device="cuda").manual_seed(9)
+    cases = [(8, 16, 96, 96), (32, 24, 16, 16), (5, 7, 40, 40), (64, 8, 56, 56)]
+    try:
+        for shape in cases:
+            y = T.empty(shape, device="cuda").normal_(0.2, 1.5, generator=g)
+            c = shape[1]
+            view = (shape[0], c, shape[2] * shape[3])
+            ref = None
+            for cfg in ((0, 4, 0), (1, 2, 0), (1, 3, 1), (1, 4, 0), (1, 6, 1)):
+                ctx.set_option("stream_reduce", cfg[0])
+                ctx.set_option("stream_stages", cfg[1])
+                ctx.set_option("stream_icvt", cfg[2])
+                mean, var = T.empty(c, device="cuda"), T.empty(c, device="cuda")
+                K.bn_batch_stats(y, mean, var)
+                ma, mx = T.zeros(c, device="cuda"), T.zeros(c, device="cuda")
+                K.meanabs(y, ma, view)
+                K.absmax(y, mx, view)
+                got = [t.clone() for t in (mean, var, ma, mx)]
+                if ref is None:
+                    ref = got
+                    assert T.equal(mx, y.abs().amax(dim=(0, 2, 3)))
+                else:
+                    for a, b in zip(ref[2:], got[2:]):                 # mean|x| (correctly rounded sum) and max|x|: same bits
+                        assert T.equal(a.view(T.int32), b.view(T.int32)), (shape, cfg)
+                    T.testing.assert_close(got[0], ref[0], rtol=1e-6, atol=1e-7)      # a different summation order:
+                    T.testing.assert_close(got[1], ref[1], rtol=1e-6, atol=0)         # mean-derived tolerance
+    finally:
+        for k, v in saved.items():
+            ctx.set_option(k, v)

@@ -31,6 +31,13 @@ def test_tanhf_facts_behind_the_dorefa_max_over_every_positive_float():
     assert _selftest(4) == 0
 
 
+def test_integer_pipe_float_to_double_conversion_over_every_bit_pattern():
+    """Sums are accumulated in double; the float -> double conversions run on the integer pipe (exponent / mantissa
+    fields shifted into a double's, times 2^896) because the conversion instruction's pipe caps sum reductions below
+    the HBM roofline.  Bit-equal to cvt.f64.f32 for every finite float (zeros, denormals), Inf / NaN flagged."""
+    assert _selftest(5) == 0
+
+
 def test_dorefa_max_when_the_maximum_sits_on_the_non_monotonic_step():
     """the adversarial case for the shortcut: the largest |w| is the float right above the decreasing step and the float
     right below it is present too, so max|tanh| is NOT tanhf(max|w|)."""

@@ -1,4 +1,6 @@
-"""A/B of the batch-statistics + fold kernel's tuning options (bn_variant, bn_pieces_per_sm) on 2^26-element conv outputs."""
+"""A/B of the segmented reductions' tuning options on 2^26-element tensors: the batch-statistics + fold kernel and the
+grouped mean|x| / max|x| reductions, register-staged (stream_reduce=0) vs the TMA-staged ring (stages, integer-pipe
+conversions, pieces per SM)."""
 import json
 import os
 import sys
@@ -18,29 +20,39 @@ peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs
 NB = 6
 n = 1 << 26
 xs = [torch.empty(n, device="cuda").uniform_(-1, 1) for _ in range(NB)]
-for cshape, wshape in (((256, 64, 64, 64), (64, 64, 3, 3)), ((256, 1024, 16, 16), (1024, 512, 1, 1)),
-                       ((256, 256, 32, 32), (256, 1, 3, 3))):
+
+
+def timeit(fn, reps=12):
+    for i in range(3):
+        fn(i % NB)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(reps):
+        fn(i % NB)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+CONFIGS = []
+for variant in (1, 3, 6):
+    for icvt in (0, 2):
+        for pieces in (8, 16):
+            CONFIGS.append(dict(stream_reduce=0, bn_variant=variant, stream_icvt=icvt, bn_pieces_per_sm=pieces))
+
+for cshape, wshape in (((256, 64, 64, 64), (64, 64, 3, 3)), ((256, 1024, 16, 16), (1024, 512, 1, 1))):
     c = cshape[1]
     conv = [x.view(cshape) for x in xs]
     w = torch.randn(wshape, device="cuda") * 0.05
     wq, bias, aw = torch.empty_like(w), torch.empty(c, device="cuda"), torch.ones(c, device="cuda")
     mu, var = torch.empty(c, device="cuda"), torch.empty(c, device="cuda")
     gm, bt = torch.rand(c, device="cuda") + 0.5, torch.randn(c, device="cuda")
-    for variant in (1, 4, 5, 6):
-        for pieces in (4, 8, 12):
-            ctx.set_option("bn_variant", variant)
-            ctx.set_option("bn_pieces_per_sm", pieces)
-            fn = lambda i: K.bnstat_foldbn_weight_fwd(conv[i], mu, var, w, wq, bias, aw, gm, bt, 1e-5, True, True, True)
-            for i in range(3):
-                fn(i % NB)
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for i in range(12):
-                fn(i % NB)
-            e1.record()
-            torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1) / 12
-            gbs = 4 * n / ms / 1e6
-            print("conv out %-16s variant %d pieces/SM %2d: %7.1f us %7.1f GB/s %.3f" % (
-                "x".join(map(str, cshape)), variant, pieces, ms * 1e3, gbs, gbs / peak), flush=True)
+    for cfg in CONFIGS:
+        for k, v in cfg.items():
+            ctx.set_option(k, v)
+        ms = timeit(lambda i: K.bnstat_foldbn_weight_fwd(conv[i], mu, var, w, wq, bias, aw, gm, bt, 1e-5, True, True, True))
+        gbs = 4 * n / ms / 1e6
+        print("bnstat %-16s %-70s %7.1f us %7.1f GB/s %.3f" % ("x".join(map(str, cshape)), cfg, ms * 1e3, gbs, gbs / peak),
+              flush=True)
+

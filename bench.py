@@ -793,6 +793,7 @@ def main():
 
     bucket = None
     exchange = "none"
+    grad_exchange = "none"
     peer_ex = None
     if world == 1 and os.environ.get("B2Q_DEBUG_PEER_WORLD1") == "1":   # experiment: mailbox kernels without a peer
         from b200quant.dist import attach_peer_exchange
@@ -813,7 +814,13 @@ def main():
         if nccl_forward and exchange.startswith("fused peer"):
             exchange = "nccl allreduce(max) of the per-node statistic (no fused exchange for this operator)"
         wn = [nd for nd in nodes if nd["kind"] == "weight"]
-        bucket = GradBucket([nd["shape"] for nd in wn], device)
+        grad_exchange = "nccl allreduce(avg), one flat bucket"
+        if peer_ex is not None and os.environ.get("B2Q_GRAD_EXCHANGE", "peer") == "peer":
+            from b200quant.dist import PeerGradBucket   # slice-owner kernel over NVLink: no NCCL call in the step at all
+            bucket = PeerGradBucket([nd["shape"] for nd in wn], peer_ex)
+            grad_exchange = "peer-memory slice-owner kernel (b2q_peer_allreduce_sum_f32), one flat bucket"
+        else:
+            bucket = GradBucket([nd["shape"] for nd in wn], device)
         for nd, view in zip(wn, bucket.views):
             nd["dx"] = view
         if os.environ.get("B2Q_DEBUG_SKIP_GRAD_ALLREDUCE") == "1":   # experiment only: isolates the exchange cost
@@ -823,7 +830,7 @@ def main():
     # The weight gradients are complete once every weight node's backward has run; their allreduce(sum) then runs on a
     # side stream while the activation backward sweeps continue (standard overlap of gradient communication with the
     # backward pass).  In the per-node (drop-in) order the weight backward calls come first for that reason.
-    side = torch.cuda.Stream() if bucket is not None else None
+    side = torch.cuda.Stream(priority=-1) if bucket is not None else None   # the collective's blocks are dispatched first
     wnodes = [nd for nd in nodes if nd["kind"] == "weight"]
     anodes = [nd for nd in nodes if nd["kind"] == "act"]
 
@@ -990,6 +997,7 @@ def main():
             "value_dropin": value, "mode": DROPIN_MODE,
             "value_best": world * batch * args.steps / (best_ms / 1e3), "mode_best": best_mode,
             "threshold_exchange": exchange,
+            "gradient_exchange": grad_exchange if world > 1 else "none",
             "ms_per_step_by_mode": timings,
             "hbm_frac_whole_step": alg_bytes_step / (ms_eager / args.steps / 1e3) / 1e9 / peak_gbs,
             "hbm_frac_whole_step_best_mode": alg_bytes_step / (best_ms / args.steps / 1e3) / 1e9 / peak_gbs,

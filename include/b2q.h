@@ -287,6 +287,20 @@ int b2q_peer_mailbox_create(b2q_ctx* ctx, void** mailbox, void* ipc_handle_out /
 int b2q_peer_mailbox_open(b2q_ctx* ctx, const void* ipc_handle /* 64 bytes */, void** peer_ptr);
 int b2q_peer_mailbox_close(b2q_ctx* ctx, void* peer_ptr);
 int b2q_peer_mailbox_destroy(b2q_ctx* ctx, void* mailbox);
+/* A device buffer other ranks can map (cudaMalloc + CUDA IPC handle, zero-filled); map / unmap / free with
+ * b2q_peer_mailbox_open / _close / _destroy.  For the gradient bucket and the statistic vectors below.            */
+int b2q_peer_buffer_create(b2q_ctx* ctx, int64_t bytes, void** buffer, void* ipc_handle_out /* 64 bytes */);
+/* Allreduce of one float32 buffer per rank over peer memory, one process per GPU, ONE kernel per rank and no NCCL:
+ * gradients (sum, KVStore 'device' semantics of core/solver.py:121; average != 0 divides by world) and per-group
+ * threshold statistics (max; grouped GDRQ_PY activations, core/operator/GDRQ.py:88-118 under data parallelism).
+ * bufs[r] = rank r's buffer as mapped on THIS device, mailboxes as for the threshold exchange.  Rank r reduces the
+ * r-th slice of every rank's buffer in rank order and stores it into every rank's buffer (bit-identical everywhere);
+ * two flag barriers through the mailboxes order it with the peers' streams.  All ranks call it in the same order
+ * with the same count; asynchronous on `stream`; waits bounded by "peer_timeout_ms" (b2q_peer_status).            */
+int b2q_peer_allreduce_sum_f32(b2q_ctx* ctx, float* const* bufs, int64_t count, int average, void* const* mailboxes,
+                               int rank, int world, void* stream);
+int b2q_peer_allreduce_max_f32(b2q_ctx* ctx, float* const* bufs, int64_t count, void* const* mailboxes, int rank, int world,
+                               void* stream);
 int b2q_peer_minmax_quant_fwd_f32(b2q_ctx* ctx, int variant, const float* x, float* y, float* aux, int64_t n,
                                   int init, float ema_decay, float one_minus_decay, void* const* mailboxes,
                                   int rank, int world, uint32_t sequence, void* stream);

@@ -70,6 +70,9 @@ _CTX_FUNCS = {
     "b2q_peer_mailbox_open": [_P, ctypes.POINTER(ctypes.c_void_p)],
     "b2q_peer_mailbox_close": [_P],
     "b2q_peer_mailbox_destroy": [_P],
+    "b2q_peer_buffer_create": [_L, ctypes.POINTER(ctypes.c_void_p), _P],
+    "b2q_peer_allreduce_sum_f32": [ctypes.POINTER(ctypes.c_void_p), _L, _I, ctypes.POINTER(ctypes.c_void_p), _I, _I, _P],
+    "b2q_peer_allreduce_max_f32": [ctypes.POINTER(ctypes.c_void_p), _L, ctypes.POINTER(ctypes.c_void_p), _I, _I, _P],
     "b2q_peer_minmax_quant_fwd_f32": [_I, _P, _P, _P, _L, _I, _F, _F, ctypes.POINTER(ctypes.c_void_p), _I, _I,
                                       ctypes.c_uint32, _P],
     "b2q_peer_meanabs_quant_fwd_f32": [_I, _P, _P, _P, _L, _F, _F, _F, ctypes.POINTER(ctypes.c_void_p), _I, _I, _P],

@@ -38,14 +38,21 @@ class GDRQ_PY(CustomOp):
             # applies the same alpha (k*max(mean) == max(k*mean): the scaling is monotonic)
             x, alpha = in_data[0], aux[0]
             view = K._gdrq_view(tuple(x.shape), self.group_size, False)
-            if self._stat is None:
-                self._stat = K.scratch_like(x, view[1])
-            K.meanabs(x, self._stat, view)
-            if self.sync is None:   # peer exchange attached but this call is outside its fused case (delay_quant)
-                from ..dist import ThresholdSync
-                self.sync = ThresholdSync()
-            self.sync(self._stat)
-            K.threshold_update(_lib.UPD_GDRQ_ACT, self._stat, alpha, self.ktimes, self.lamda)
+            if self.sync is None and getattr(self.peer, "vectors", False):
+                # per-group statistics in peer-addressable memory, maximised over ranks by one kernel per rank
+                stat = self.peer.stat_vector(view[1])
+                K.meanabs(x, stat, view)
+                self.peer.allreduce_max_vector(view[1])
+            else:
+                if self._stat is None:
+                    self._stat = K.scratch_like(x, view[1])
+                stat = self._stat
+                K.meanabs(x, stat, view)
+                if self.sync is None:   # an exchange without vectors (comm.DeviceGroup): NCCL for this call
+                    from ..dist import ThresholdSync
+                    self.sync = ThresholdSync()
+                self.sync(stat)
+            K.threshold_update(_lib.UPD_GDRQ_ACT, stat, alpha, self.ktimes, self.lamda)
             K.qdq(x, out_data[0], alpha, self.QUANT_LEVEL, _lib.CLIP_SYM if view[1] == 1 else _lib.CLIP_WHERE_LE,
                   req[0], view=view, do_round=do_round)
             return

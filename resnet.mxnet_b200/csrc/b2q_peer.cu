@@ -43,6 +43,10 @@ struct PeerState {
     unsigned long long local_max;   // (seq << 32 | bits): running local max|x| of the call in flight
     unsigned int timeout_seq;       // != 0: a sweep gave up waiting for a peer at this sequence number (its output is NaN)
     unsigned int timeout_rank;      // the first rank whose statistic was missing
+    unsigned int ar_seq;            // allreduce calls completed (peer_allreduce_kernel; device-side so graphs replay)
+    unsigned int ar_ticket;         // blocks of the allreduce in flight that have finished their slice
+    unsigned int ar_timeout_seq;    // != 0: an allreduce gave up waiting for a peer (the buffer is not valid)
+    unsigned int ar_timeout_rank;
 };
 
 struct PeerBoxes {
@@ -533,6 +537,133 @@ qdq_peer3_kernel(const float* __restrict__ x, float* __restrict__ y, FlatSplit s
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Allreduce (sum / max) of one float32 buffer per rank over peer memory, one process per GPU: ONE kernel per rank, no
+// NCCL, no host synchronisation.  bufs[r] is rank r's buffer as mapped on this device (CUDA IPC).  Rank r owns the r-th
+// slice: it reads that slice from every rank (peer loads over NVLink), combines the values in rank order -- so every
+// rank ends up with the same bits -- and stores the result into every rank's buffer (peer stores): reduce-scatter and
+// all-gather in one pass, (n-1)/n of the buffer in each direction per device like a ring, but in one hop.
+// Two flag barriers through the mailboxes (slots 62 / 63 of the box area, 8-byte system-scope words, sequence-tagged):
+//   in   block 0 tells every rank "my buffer is complete" (stream order: everything before this kernel has finished);
+//        every block waits until all ranks said so before it reads a peer's data
+//   out  the block that finishes last (ticket) tells every rank "my slice is stored everywhere" and then waits for the
+//        same word from every rank, so the kernel -- and with it this rank's stream -- completes only when the whole
+//        buffer is final here and nobody still reads the old contents.
+// All ranks must call it in the same order with the same count (data parallel).  The waits are bounded by
+// peer_timeout_ms like the threshold exchange (b2q_peer_status reports an expiry; the buffer is then not valid).
+// ------------------------------------------------------------------------------------------------------------------
+#define B2Q_AR_SLOT_IN 62
+#define B2Q_AR_SLOT_OUT 63
+
+struct ArPtrs {
+    float* buf[B2Q_PEER_MAX_RANKS];
+};
+
+// all 32 lanes of one warp: wait until every rank's word in `slot` of the own mailbox carries `seq`
+__device__ __forceinline__ bool ar_wait_all(const PeerBoxes& pb, int slot, unsigned int seq, unsigned long long timeout_ns) {
+    const int lane = threadIdx.x & 31;
+    bool late = false;
+    if (lane < pb.world) {
+        const unsigned long long* p = pb.box[pb.rank] + (size_t)slot * B2Q_PEER_MAX_RANKS + lane;
+        unsigned long long m = ld_sys_u64(p);
+        if ((unsigned int)m != seq) {
+            const unsigned long long t0 = global_ns();
+            unsigned int polls = 0;
+            while (true) {
+                __nanosleep(polls < 256 ? 20 : (polls < 4096 ? 200 : 2000));
+                m = ld_sys_u64(p);
+                if ((unsigned int)m == seq) break;
+                if ((++polls & 63u) == 0 && global_ns() - t0 > timeout_ns) { late = true; break; }
+            }
+        }
+    }
+    const unsigned int late_mask = __ballot_sync(0xffffffffu, late);
+    if (late_mask && lane == 0) {
+        pb.state->ar_timeout_seq = seq;
+        pb.state->ar_timeout_rank = (unsigned int)(__ffs(late_mask) - 1);
+    }
+    return late_mask == 0;
+}
+
+template <bool IS_MAX>
+__global__ void __launch_bounds__(256)
+peer_allreduce_kernel(ArPtrs p, PeerBoxes pb, int64_t begin, int64_t end, int vec, float post_scale,
+                      unsigned long long timeout_ns) {
+    __shared__ unsigned int s_ticket;
+    const unsigned int seq = pb.state->ar_seq + 1u;   // read by every block before it takes its ticket (below)
+    if (blockIdx.x == 0 && (int)threadIdx.x < pb.world)
+        st_sys_u64(pb.box[threadIdx.x] + (size_t)B2Q_AR_SLOT_IN * B2Q_PEER_MAX_RANKS + pb.rank, (unsigned long long)seq);
+    if (threadIdx.x < 32) ar_wait_all(pb, B2Q_AR_SLOT_IN, seq, timeout_ns);
+    __syncthreads();
+    __threadfence_system();   // acquire: the peers' buffers are complete and visible
+    const int n_ranks = pb.world;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t sbegin = begin;   // scalar part: everything when the buffers are not 16-byte aligned, else the ragged tail
+    if (vec) {
+        // four 128-bit words per thread and pass: the loads of one rank are all in flight before the first is used
+        const int64_t w_end = end >> 2;
+        for (int64_t i0 = (begin >> 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < w_end; i0 += 4 * stride) {
+            float4 acc[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t i = i0 + u * stride;
+                acc[u] = i < w_end ? __ldcg(reinterpret_cast<const float4*>(p.buf[0]) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            for (int r = 1; r < n_ranks; ++r) {
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int64_t i = i0 + u * stride;
+                    v[u] = i < w_end ? __ldcg(reinterpret_cast<const float4*>(p.buf[r]) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (IS_MAX) {
+                        acc[u].x = fmax_nan(acc[u].x, v[u].x); acc[u].y = fmax_nan(acc[u].y, v[u].y);
+                        acc[u].z = fmax_nan(acc[u].z, v[u].z); acc[u].w = fmax_nan(acc[u].w, v[u].w);
+                    } else {
+                        acc[u].x = __fadd_rn(acc[u].x, v[u].x); acc[u].y = __fadd_rn(acc[u].y, v[u].y);
+                        acc[u].z = __fadd_rn(acc[u].z, v[u].z); acc[u].w = __fadd_rn(acc[u].w, v[u].w);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t i = i0 + u * stride;
+                if (i >= w_end) continue;
+                if (!IS_MAX && post_scale != 1.f) {
+                    acc[u].x = __fmul_rn(acc[u].x, post_scale); acc[u].y = __fmul_rn(acc[u].y, post_scale);
+                    acc[u].z = __fmul_rn(acc[u].z, post_scale); acc[u].w = __fmul_rn(acc[u].w, post_scale);
+                }
+                for (int r = 0; r < n_ranks; ++r) __stcg(reinterpret_cast<float4*>(p.buf[r]) + i, acc[u]);
+            }
+        }
+        sbegin = (end >> 2) << 2;
+        if (sbegin < begin) sbegin = begin;
+    }
+    for (int64_t i = sbegin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += stride) {
+        float acc = __ldcg(p.buf[0] + i);
+        for (int r = 1; r < n_ranks; ++r) {
+            const float v = __ldcg(p.buf[r] + i);
+            acc = IS_MAX ? fmax_nan(acc, v) : __fadd_rn(acc, v);
+        }
+        if (!IS_MAX && post_scale != 1.f) acc = __fmul_rn(acc, post_scale);
+        for (int r = 0; r < n_ranks; ++r) p.buf[r][i] = acc;
+    }
+    __threadfence_system();   // release: this block's peer stores are visible before its ticket
+    __syncthreads();
+    if (threadIdx.x == 0) s_ticket = b2q_take_ticket(&pb.state->ar_ticket, gridDim.x - 1);
+    __syncthreads();
+    if (s_ticket != gridDim.x - 1) return;
+    // ---- last block: every slice element of this rank is stored everywhere ----
+    __threadfence_system();
+    if (threadIdx.x == 0) { pb.state->ar_ticket = 0; pb.state->ar_seq = seq; }
+    if ((int)threadIdx.x < pb.world)
+        st_sys_u64(pb.box[threadIdx.x] + (size_t)B2Q_AR_SLOT_OUT * B2Q_PEER_MAX_RANKS + pb.rank, (unsigned long long)seq);
+    if (threadIdx.x < 32) ar_wait_all(pb, B2Q_AR_SLOT_OUT, seq, timeout_ns);
+    __threadfence_system();
+}
+
 extern "C" {
 
 int b2q_peer_mailbox_bytes(void) { return B2Q_PEER_BYTES; }
@@ -542,8 +673,8 @@ int b2q_peer_status(b2q_ctx* ctx, const void* own_mailbox, uint32_t* timeout_seq
     B2Q_REQUIRE(own_mailbox && timeout_sequence, "null argument");
     PeerState st;
     B2Q_CHECK_CUDA(cudaMemcpy(&st, (const char*)own_mailbox + B2Q_PEER_BOX_BYTES, sizeof(st), cudaMemcpyDeviceToHost));
-    *timeout_sequence = st.timeout_seq;
-    if (timeout_rank) *timeout_rank = st.timeout_rank;
+    *timeout_sequence = st.timeout_seq ? st.timeout_seq : st.ar_timeout_seq;
+    if (timeout_rank) *timeout_rank = st.timeout_seq ? st.timeout_rank : st.ar_timeout_rank;
     return 0;
 }
 
@@ -682,6 +813,74 @@ static int peer_quant_fwd(b2q_ctx* ctx, bool is_max, int upd_mode, float p0, flo
         B2Q_LAUNCH_CHECK(ctx);
     }
     return 0;
+}
+
+int b2q_peer_buffer_create(b2q_ctx* ctx, int64_t bytes, void** buffer, void* ipc_handle_out) {
+    B2Q_CTX(ctx);
+    B2Q_REQUIRE(buffer && ipc_handle_out && bytes >= 1, "bad argument");
+    void* p = nullptr;
+    B2Q_CHECK_CUDA(cudaMalloc(&p, (size_t)bytes));
+    B2Q_CHECK_CUDA(cudaMemset(p, 0, (size_t)bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        b2q_set_error(std::string("cudaIpcGetMemHandle failed: ") + cudaGetErrorString(e));
+        return 1;
+    }
+    memcpy(ipc_handle_out, &h, sizeof(h));
+    *buffer = p;
+    return 0;
+}
+
+static int peer_allreduce(b2q_ctx* ctx, bool is_max, float* const* bufs, int64_t count, float post, void* const* mailboxes,
+                          int rank, int world, cudaStream_t st) {
+    B2Q_REQUIRE(bufs && mailboxes && count >= 1, "bad argument");
+    B2Q_REQUIRE(world >= 1 && world <= B2Q_PEER_MAX_RANKS && rank >= 0 && rank < world, "bad rank / world");
+    ArPtrs p;
+    memset(&p, 0, sizeof(p));
+    PeerBoxes pb;
+    memset(&pb, 0, sizeof(pb));
+    bool aligned = true;
+    for (int r = 0; r < world; ++r) {
+        B2Q_REQUIRE(bufs[r] != nullptr && mailboxes[r] != nullptr, "null buffer / mailbox pointer");
+        p.buf[r] = bufs[r];
+        pb.box[r] = (unsigned long long*)mailboxes[r];
+        aligned = aligned && ((((uintptr_t)bufs[r]) & 15) == 0);
+    }
+    pb.rank = rank; pb.world = world;
+    pb.state = (PeerState*)((char*)mailboxes[rank] + B2Q_PEER_BOX_BYTES);
+    pb.resolved = nullptr;
+    // rank r owns the r-th slice, in units of four floats when every buffer is 16-byte aligned
+    const int64_t unit = aligned ? 4 : 1;
+    const int64_t units = (count + unit - 1) / unit;
+    int64_t b = (units * rank) / world * unit, e = (units * (rank + 1)) / world * unit;
+    if (e > count || rank == world - 1) e = count;
+    if (b > e) b = e;
+    int64_t work = (e - b + unit - 1) / unit;
+    int64_t grid = (work + 255) / 256;
+    const int64_t cap = (int64_t)ctx->num_sms * (ctx->peer_allreduce_blocks_per_sm > 0 ? ctx->peer_allreduce_blocks_per_sm : 2);
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    const unsigned long long timeout_ns = (unsigned long long)(ctx->peer_timeout_ms > 0 ? ctx->peer_timeout_ms : 1) * 1000000ull;
+    b2q_timed_launch tl(ctx, B2Q_KIND_OTHER, 8.0 * (double)(e - b) * (double)world, st);
+    if (is_max) peer_allreduce_kernel<true><<<(unsigned)grid, 256, 0, st>>>(p, pb, b, e, aligned ? 1 : 0, 1.f, timeout_ns);
+    else peer_allreduce_kernel<false><<<(unsigned)grid, 256, 0, st>>>(p, pb, b, e, aligned ? 1 : 0, post, timeout_ns);
+    B2Q_LAUNCH_CHECK(ctx);
+    return 0;
+}
+
+int b2q_peer_allreduce_sum_f32(b2q_ctx* ctx, float* const* bufs, int64_t count, int average, void* const* mailboxes,
+                               int rank, int world, void* stream) {
+    B2Q_CTX(ctx);
+    return peer_allreduce(ctx, false, bufs, count, average ? 1.f / (float)world : 1.f, mailboxes, rank, world,
+                          (cudaStream_t)stream);
+}
+
+int b2q_peer_allreduce_max_f32(b2q_ctx* ctx, float* const* bufs, int64_t count, void* const* mailboxes, int rank, int world,
+                               void* stream) {
+    B2Q_CTX(ctx);
+    return peer_allreduce(ctx, true, bufs, count, 1.f, mailboxes, rank, world, (cudaStream_t)stream);
 }
 
 int b2q_peer_minmax_quant_fwd_f32(b2q_ctx* ctx, int variant, const float* x, float* y, float* aux, int64_t n, int init,

@@ -72,6 +72,8 @@ class PeerThresholdExchange(object):
         self.device = torch.device(device)
         self.ctx = _lib.context(self.device.index)
         self.sequence = 0
+        self.vectors = True      # stat_vector / allreduce_max_vector available (needs the process group for the handles)
+        self._stats = None
         own = ctypes.c_void_p()
         handle = ctypes.create_string_buffer(64)
         self.ctx.call("b2q_peer_mailbox_create", ctypes.byref(own), ctypes.cast(handle, ctypes.c_void_p))
@@ -104,6 +106,7 @@ class PeerThresholdExchange(object):
         self.device = torch.device("cuda", ctx.device)
         self._boxes = (ctypes.c_void_p * self.world)(*[boxes[r] for r in range(self.world)])
         self._opened, self._own = [], None      # the mailboxes belong to the communicator
+        self.vectors, self._stats = False, None
         self._status_box = ctypes.c_void_p(boxes[rank]) if own is None else own
         return self
 
@@ -129,6 +132,20 @@ class PeerThresholdExchange(object):
         self.ctx.call("b2q_peer_meanabs_quant_fwd_f32", int(upd_mode), xb.ptr, yb.ptr, ab.ptr, xb.numel,
                       float(np.float32(p0)), float(np.float32(p1)), float(np.float32(qlevel)), self._boxes, self.rank,
                       self.world, current_stream(xb))
+
+    def stat_vector(self, n):
+        """A float32 vector of ``n`` elements in peer-addressable memory for per-group statistics (grouped GDRQ_PY
+        activations); one buffer per exchange, shared by its operators (stream order makes that safe: the allreduce's
+        closing barrier means no rank still reads it when the next operator writes)."""
+        if getattr(self, "_stats", None) is None:
+            self._stats = PeerBuffer(self, 8192)
+        if n > self._stats.numel:
+            raise ValueError("more than %d groups" % self._stats.numel)
+        return self._stats.tensor[:n]
+
+    def allreduce_max_vector(self, n):
+        """max over ranks of the first ``n`` elements of ``stat_vector`` (one kernel per rank, no NCCL)."""
+        self._stats.allreduce_max(n)
 
     def status(self):
         """(sequence, rank) of the first exchange in which this rank gave up waiting for a peer's statistic (option
@@ -156,6 +173,9 @@ class PeerThresholdExchange(object):
                 self._close()
 
     def _close(self):
+        if getattr(self, "_stats", None) is not None:
+            self._stats.close()
+            self._stats = None
         for p in self._opened:
             self.ctx.call("b2q_peer_mailbox_close", p)
         self._opened = []
@@ -164,15 +184,108 @@ class PeerThresholdExchange(object):
             self._own = None
 
 
+class _RawCudaArray(object):
+    """Lets torch wrap device memory this package allocated (``torch.as_tensor`` reads ``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr, numel):
+        self.__cuda_array_interface__ = {"shape": (int(numel),), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+class PeerBuffer(object):
+    """A float32 device buffer every rank of the exchange can address: allocated by the library (cudaMalloc + CUDA IPC
+    handle), the handles all-gathered once through torch.distributed, the peers' buffers mapped into this process.
+    ``tensor`` is the rank's own buffer as a torch tensor (zero-filled); ``allreduce_sum`` / ``allreduce_max`` reduce the
+    first ``count`` elements over all ranks in place with ONE kernel per rank over NVLink (b2q_peer_allreduce_*_f32): no
+    NCCL call.  All ranks must issue the same calls in the same order."""
+
+    def __init__(self, exchange, numel):
+        import ctypes
+        self.ex = exchange
+        self.ctx = exchange.ctx
+        self.numel = int(numel)
+        own = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        self.ctx.call("b2q_peer_buffer_create", 4 * max(self.numel, 1), ctypes.byref(own), ctypes.cast(handle, ctypes.c_void_p))
+        self._own = own
+        world, rank = exchange.world, exchange.rank
+        handles = [None] * world
+        if world > 1:
+            dist.all_gather_object(handles, bytes(handle.raw), group=exchange.group)
+        else:
+            handles[0] = bytes(handle.raw)
+        self._ptrs = (ctypes.c_void_p * world)()
+        self._opened = []
+        for r in range(world):
+            if r == rank:
+                self._ptrs[r] = own.value
+            else:
+                p = ctypes.c_void_p()
+                buf = ctypes.create_string_buffer(handles[r], 64)
+                self.ctx.call("b2q_peer_mailbox_open", ctypes.cast(buf, ctypes.c_void_p), ctypes.byref(p))
+                self._ptrs[r] = p.value
+                self._opened.append(p)
+        self.tensor = torch.as_tensor(_RawCudaArray(own.value, max(self.numel, 1)), device=exchange.device)[:self.numel]
+        if world > 1:
+            dist.barrier(group=exchange.group)
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.ex.device).cuda_stream
+
+    def allreduce_sum(self, count=None, average=False):
+        n = self.numel if count is None else int(count)
+        self.ctx.call("b2q_peer_allreduce_sum_f32", self._ptrs, n, int(bool(average)), self.ex._boxes, self.ex.rank,
+                      self.ex.world, self._stream())
+        return self.tensor
+
+    def allreduce_max(self, count=None):
+        n = self.numel if count is None else int(count)
+        self.ctx.call("b2q_peer_allreduce_max_f32", self._ptrs, n, self.ex._boxes, self.ex.rank, self.ex.world,
+                      self._stream())
+        return self.tensor
+
+    def close(self):
+        self.tensor = None
+        for p in self._opened:
+            self.ctx.call("b2q_peer_mailbox_close", p)
+        self._opened = []
+        if self._own is not None:
+            self.ctx.call("b2q_peer_mailbox_destroy", self._own)
+            self._own = None
+
+
+class PeerGradBucket(object):
+    """GradBucket whose flat buffer lives in peer-addressable memory: the weight-node ``in_grad`` views are slices of it
+    and ``allreduce`` is one slice-owner kernel per rank over NVLink instead of an NCCL call (KVStore 'device' semantics,
+    core/solver.py:121: summed -- averaged with ``average=True`` -- in rank order, bit-identical on every rank)."""
+
+    def __init__(self, shapes, exchange):
+        self.numel = [int(torch.Size(s).numel()) for s in shapes]
+        self.buffer = PeerBuffer(exchange, sum(self.numel))
+        self.flat = self.buffer.tensor
+        self.views = []
+        off = 0
+        for s, n in zip(shapes, self.numel):
+            self.views.append(self.flat[off:off + n].view(s))
+            off += n
+
+    def allreduce(self, group=None, average=True):
+        return self.buffer.allreduce_sum(average=average)
+
+    def close(self):
+        self.views, self.flat = [], None
+        self.buffer.close()
+
+
 def attach_peer_exchange(ops, device, group=None):
     """Route every activation node in ``ops`` that has a fused peer-memory exchange through it: the minmax operators,
-    whole-tensor GDRQ_PY activations and the data path of GDRQ_Fold_BN.  Grouped GDRQ activations (one threshold per
-    channel group) keep the NCCL sync."""
+    GDRQ_PY activations and the data path of GDRQ_Fold_BN.  Grouped GDRQ activations (one threshold per channel
+    group) exchange their statistic vector with the peer-memory allreduce(max) kernel between the reduction and the
+    threshold update."""
     ex = PeerThresholdExchange(device, group)
     for op in ops:
         kind = op.__class__.__name__
         if (not getattr(op, "is_weight", True) and hasattr(op, "VARIANT")) \
-                or (kind == "GDRQ_PY" and not op.is_weight and op.group_size == -1) or kind == "GDRQ_Fold_BN":
-            op.peer = ex
+                or (kind == "GDRQ_PY" and not op.is_weight) or kind == "GDRQ_Fold_BN":
+            op.peer = ex       # grouped GDRQ_PY activations: per-group statistics through ex.allreduce_max_vector
             op.sync = None
     return ex

@@ -75,7 +75,7 @@ def main():
                 dist.barrier()
                 ex.close()
     # GDRQ_PY activations (mean-based threshold): statistic = max over ranks of mean|x|, then the alpha update
-    for group_size, mode in ((-1, "nccl"), (4, "nccl"), (-1, "peer")):
+    for group_size, mode in ((-1, "nccl"), (4, "nccl"), (-1, "peer"), (4, "peer"), (1, "peer")):
         op = b200quant.get_prop("GDRQ_PY")(nbits="8", group_size=str(group_size), is_weight="False", lamda="0.001",
                                            ktimes="3").create_operator(None, None, None)
         ex = None
@@ -118,6 +118,66 @@ def main():
             torch.cuda.synchronize()
             dist.barrier()
             ex.close()
+
+    # peer-memory allreduce (gradients: sum / average in rank order; statistic vectors: max) against the same reduction
+    # done on the host from the all-gathered inputs -- bit for bit, identical on every rank
+    from b200quant.dist import PeerBuffer, PeerGradBucket, PeerThresholdExchange
+    ex = PeerThresholdExchange(torch.device("cuda", local))
+    big = PeerBuffer(ex, (1 << 22) + 3)
+    for it, count in enumerate([1, 3, 4, 5, 8, 1023, 4096, 65537, (1 << 20) + 1, (1 << 22) + 3]):
+        for kind in ("sum", "avg", "max"):
+            rng = np.random.default_rng(31 * it + 7 * rank + len(kind))
+            mine = (rng.standard_normal(count) * (1 + rank)).astype(F)
+            if kind == "max" and count > 4:
+                mine[rank % count] = np.nan if rank == world - 1 else mine[rank % count]      # NaN propagates
+            big.tensor[:count].copy_(torch.from_numpy(mine))
+            big.tensor[count:count + 2] = 7.0 if count + 2 <= big.numel else 0.0
+            everyone = [torch.zeros(count, device="cuda") for _ in range(world)]
+            dist.all_gather(everyone, torch.from_numpy(mine).cuda())
+            if kind == "max":
+                big.allreduce_max(count)
+            else:
+                big.allreduce_sum(count, average=(kind == "avg"))
+            got = big.tensor[:count].cpu().numpy()
+            acc = everyone[0].cpu().numpy().copy()
+            for r in range(1, world):
+                o = everyone[r].cpu().numpy()
+                acc = np.where(np.isnan(acc) | np.isnan(o), F(np.nan), np.maximum(acc, o)).astype(F) if kind == "max" else (acc + o).astype(F)
+            if kind == "avg":
+                acc = (acc * F(1.0 / world)).astype(F)
+            ok = bits(got, acc) if kind != "max" else (np.array_equal(np.isnan(got), np.isnan(acc)) and
+                                                       np.array_equal(got[~np.isnan(got)], acc[~np.isnan(acc)]))
+            if count + 2 <= big.numel and not bool((big.tensor[count:count + 2] == 7.0).all()):
+                ok = False                                      # nothing beyond `count` may be touched
+            if not ok:
+                failures += 1
+                print("rank %d FAIL peer allreduce %s count=%d" % (rank, kind, count), flush=True)
+    shapes = [(64, 3, 7, 7), (64, 64, 1, 1), (512, 512, 3, 3), (1000, 2048), (7,)]
+    bucket = PeerGradBucket(shapes, ex)
+    for step in range(3):
+        rng = np.random.default_rng(900 + step * 10 + rank)
+        for v in bucket.views:
+            v.copy_(torch.from_numpy(rng.standard_normal(tuple(v.shape)).astype(F)))
+        ref = bucket.flat.clone()
+        dist.all_reduce(ref, op=dist.ReduceOp.SUM)
+        ref /= world
+        bucket.allreduce(average=True)
+        if not torch.allclose(bucket.flat, ref, rtol=1e-6, atol=1e-6):
+            failures += 1
+            print("rank %d FAIL PeerGradBucket step %d" % (rank, step), flush=True)
+        gathered = [torch.zeros_like(bucket.flat) for _ in range(world)]
+        dist.all_gather(gathered, bucket.flat)
+        if not all(torch.equal(gathered[0].view(torch.int32), g.view(torch.int32)) for g in gathered):
+            failures += 1
+            print("rank %d FAIL PeerGradBucket not identical across ranks" % rank, flush=True)
+    torch.cuda.synchronize()
+    dist.barrier()
+    if ex.status() is not None:
+        failures += 1
+        print("rank %d FAIL peer exchange timed out %r" % (rank, ex.status()), flush=True)
+    bucket.close()
+    big.close()
+    ex.close()
 
     t = torch.tensor([failures], device="cuda")
     dist.all_reduce(t)

@@ -161,6 +161,54 @@ def test_mean_based_ops_sync_path_matches_fused_path():
         assert torch.equal(ya.view(torch.int32), yb.view(torch.int32)), step
 
 
+def test_peer_allreduce_and_grouped_statistics_at_world1():
+    """b2q_peer_allreduce_{sum,max}_f32 and the grouped GDRQ_PY exchange through them on one GPU (world 1: the flag
+    barriers go through the own mailbox): sum / max are the identity, average too, nothing outside `count` is touched;
+    grouped GDRQ activations with the exchange attached give the bits of the plain path."""
+    import torch
+    import b200quant
+    from b200quant.dist import PeerBuffer, PeerGradBucket, PeerThresholdExchange, attach_peer_exchange
+    dev = torch.device("cuda", 0)
+    ex = PeerThresholdExchange(dev)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    buf = PeerBuffer(ex, 100003)
+    for count in (1, 3, 4, 5, 4099, 100003):
+        for kind in ("sum", "avg", "max"):
+            x = torch.randn(count, device="cuda", generator=g)
+            buf.tensor.fill_(7.0)
+            buf.tensor[:count].copy_(x)
+            if kind == "max":
+                buf.allreduce_max(count)
+            else:
+                buf.allreduce_sum(count, average=(kind == "avg"))
+            assert torch.equal(buf.tensor[:count].view(torch.int32), x.view(torch.int32)), (count, kind)
+            assert bool((buf.tensor[count:] == 7.0).all())
+    bucket = PeerGradBucket([(8, 3, 3, 3), (10, 8), (5,)], ex)
+    assert [tuple(v.shape) for v in bucket.views] == [(8, 3, 3, 3), (10, 8), (5,)] and bucket.flat.numel() == 216 + 80 + 5
+    bucket.views[1].fill_(2.0)
+    bucket.allreduce(average=True)
+    assert float(bucket.flat.sum()) == 160.0
+    torch.cuda.synchronize()
+    assert ex.status() is None
+    bucket.close()
+    buf.close()
+    ex.close()
+    mk = lambda: b200quant.get_prop("GDRQ_PY")(nbits="8", group_size="4", is_weight="False").create_operator(None, None, None)
+    a, b = mk(), mk()
+    ex = attach_peer_exchange([b], dev)
+    assert b.peer is ex and b.sync is None
+    al_a, al_b = torch.ones(4, device="cuda"), torch.ones(4, device="cuda")
+    for step, shape in enumerate([(4, 16, 9, 9), (2, 16, 56, 56), (3, 16, 7, 5)]):
+        x = torch.randn(shape, device="cuda", generator=g) * (1 + step)
+        ya, yb = torch.zeros_like(x), torch.zeros_like(x)
+        a.forward(True, ["write"], [x], [ya], [al_a])
+        b.forward(True, ["write"], [x], [yb], [al_b])
+        assert torch.equal(al_a.view(torch.int32), al_b.view(torch.int32)), step
+        assert torch.equal(ya.view(torch.int32), yb.view(torch.int32)), step
+    torch.cuda.synchronize()
+    ex.close()
+
+
 def test_two_rank_threshold_exchange():
     import torch
     if torch.cuda.device_count() < 2:

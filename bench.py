@@ -467,6 +467,7 @@ def full_model_leg(torch, device, batch, steps=8, warmup=3, world=1, rank=0):
     thresholds through the fused peer-memory exchange, gradients through DistributedDataParallel (NCCL)."""
     from b200quant.harness import ResNetInt8, quant_nodes
     torch.manual_seed(11)
+    torch.backends.cudnn.benchmark = True     # library convolutions: let cuDNN pick its fastest algorithms
     model = ResNetInt8().to(device)
     net, ex = model, None
     if world > 1:
@@ -1023,6 +1024,10 @@ def main():
     # ---- e2e: host buffers through the host C ABI (rank-local; N ranks run it concurrently) ----
     if not args.no_e2e and op_type == "Quantization_int8_V2":
         try:
+            host_cores = None
+            if world > 1:   # every rank its own host cores (its GPU's NUMA node when the platform reports one)
+                from b200quant.dist import pin_rank_to_host_cores
+                host_cores = pin_rank_to_host_cores(local, int(os.environ.get("LOCAL_WORLD_SIZE", world)), local)
             hstep, b_in, b_out, ste_on_host = host_step_factory(torch, nodes, ctx)
             hstep()
             if world > 1:
@@ -1044,6 +1049,7 @@ def main():
             line["e2e"] = {"value": world * batch * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": b_in,
                            "d2h_bytes_per_step": b_out, "steps": args.e2e_steps, "ms_per_step": dt / args.e2e_steps * 1e3,
                            "per_rank_gbs_each_direction": [round(b_in * args.e2e_steps / t_ / 1e9, 2) for t_ in per_rank],
+                           "host_cores_per_rank": (len(host_cores) if host_cores else os.cpu_count()),
                            "ste_backward": ("host-to-host copy inside the library (no PCIe round trip, no arithmetic)"
                                             if ste_on_host else "staged through the GPU (H2D dy, D2H dx)"),
                            "path": "CustomOp.forward/backward with pinned HOST tensors -> b2q_*_host_f32 (three-stream "

@@ -184,6 +184,51 @@ class PeerThresholdExchange(object):
             self._own = None
 
 
+def pin_rank_to_host_cores(local_rank, local_world, device_index=None):
+    """Give every rank of a node its own host cores (and with them, by first touch, its own host memory): the cores of the
+    GPU's NUMA node when the platform reports one (``/sys/bus/pci/devices/<bus id>/numa_node``), otherwise an even split
+    of the cores this process may use.  The host-buffer path (pinned staging, the host-to-host straight-through copy pool)
+    then neither migrates between sockets nor fights the other ranks for the same cores.  Returns the core list; sets
+    ``B2Q_HOST_COPY_THREADS`` to its length unless the variable is already set.  Call before the first host-buffer call."""
+    import os
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+    except AttributeError:  # pragma: no cover
+        return []
+    cores = None
+    if device_index is not None and torch.cuda.is_available():
+        try:
+            bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+            dom = torch.cuda.get_device_properties(device_index).pci_domain_id
+            devid = torch.cuda.get_device_properties(device_index).pci_device_id
+            path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, devid)
+            node = int(open(path).read().strip())
+            if node >= 0:
+                spans = open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(",")
+                on_node = []
+                for sp in spans:
+                    lo, _, hi = sp.partition("-")
+                    on_node += list(range(int(lo), int(hi or lo) + 1))
+                on_node = [c for c in on_node if c in allowed]
+                # ranks that share the node share its cores evenly, in rank order
+                same = [r for r in range(local_world)]
+                share = max(1, len(on_node) // max(1, len(same)))
+                k = local_rank % max(1, len(on_node) // share)
+                if on_node:
+                    cores = on_node[k * share:(k + 1) * share] or on_node
+        except Exception:
+            cores = None
+    if cores is None:
+        share = max(1, len(allowed) // max(1, local_world))
+        cores = allowed[local_rank * share:(local_rank + 1) * share] or allowed
+    try:
+        os.sched_setaffinity(0, cores)
+    except OSError:  # pragma: no cover
+        return allowed
+    os.environ.setdefault("B2Q_HOST_COPY_THREADS", str(max(1, len(cores))))
+    return cores
+
+
 class _RawCudaArray(object):
     """Lets torch wrap device memory this package allocated (``torch.as_tensor`` reads ``__cuda_array_interface__``)."""
 

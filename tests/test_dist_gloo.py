@@ -70,3 +70,33 @@ def test_threshold_sync_and_grad_bucket_world2():
         assert r[4] and r[5]                              # sync attached to activation node only
         assert r[6] == [3.0] * 6 + [30.0] * 4             # allreduce(sum) over the flat bucket
         assert r[7] == 1
+
+
+def test_ranks_of_a_node_get_disjoint_host_cores():
+    """dist.pin_rank_to_host_cores (the e2e leg at N > 1): without a NUMA hint every local rank gets its own slice of the
+    cores the process may use, the slices are disjoint, and the copy-pool size follows.  Run in child processes: the
+    call changes the caller's CPU affinity."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ncpu = len(os.sched_getaffinity(0))
+    world = 2 if ncpu >= 2 else 1
+    got = []
+    for r in range(world):
+        code = ("import sys, os, json; sys.path.insert(0, %r); import b200quant; "
+                "from b200quant.dist import pin_rank_to_host_cores; "
+                "c = pin_rank_to_host_cores(%d, %d); "
+                "print(json.dumps([c, sorted(os.sched_getaffinity(0)), os.environ.get('B2Q_HOST_COPY_THREADS')]))"
+                % (root, r, world))
+        env = dict(os.environ)
+        env.pop("B2Q_HOST_COPY_THREADS", None)
+        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env)
+        assert out.returncode == 0, out.stderr[-2000:]
+        got.append(json.loads(out.stdout.strip().splitlines()[-1]))
+    for cores, affinity, threads in got:
+        assert cores == affinity and len(cores) >= 1 and int(threads) == len(cores)
+    if world == 2:
+        assert not set(got[0][0]) & set(got[1][0])
+        assert len(got[0][0]) == ncpu // 2

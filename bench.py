@@ -816,7 +816,9 @@ def main():
             exchange = "nccl allreduce(max) of the per-node statistic (no fused exchange for this operator)"
         wn = [nd for nd in nodes if nd["kind"] == "weight"]
         grad_exchange = "nccl allreduce(avg), one flat bucket"
-        if peer_ex is not None and os.environ.get("B2Q_GRAD_EXCHANGE", "peer") == "peer":
+        # measured (profiles/r02q_gradient_exchange.md): NCCL's allreduce (in-switch reduction at 8 GPUs) beats the
+        # peer-memory slice-owner kernel by 0.4 % of the step at 2 GPUs and 1.5 % at 8, so it stays the default here
+        if peer_ex is not None and os.environ.get("B2Q_GRAD_EXCHANGE", "nccl") == "peer":
             from b200quant.dist import PeerGradBucket   # slice-owner kernel over NVLink: no NCCL call in the step at all
             bucket = PeerGradBucket([nd["shape"] for nd in wn], peer_ex)
             grad_exchange = "peer-memory slice-owner kernel (b2q_peer_allreduce_sum_f32), one flat bucket"

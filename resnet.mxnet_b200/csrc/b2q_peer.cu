@@ -859,7 +859,8 @@ static int peer_allreduce(b2q_ctx* ctx, bool is_max, float* const* bufs, int64_t
     if (b > e) b = e;
     int64_t work = (e - b + unit - 1) / unit;
     int64_t grid = (work + 255) / 256;
-    const int64_t cap = (int64_t)ctx->num_sms * (ctx->peer_allreduce_blocks_per_sm > 0 ? ctx->peer_allreduce_blocks_per_sm : 2);
+    const int64_t cap = ctx->peer_allreduce_blocks > 0 ? (int64_t)ctx->peer_allreduce_blocks
+                                                       : (int64_t)ctx->num_sms * (ctx->peer_allreduce_blocks_per_sm > 0 ? ctx->peer_allreduce_blocks_per_sm : 2);
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
     const unsigned long long timeout_ns = (unsigned long long)(ctx->peer_timeout_ms > 0 ? ctx->peer_timeout_ms : 1) * 1000000ull;

@@ -6,6 +6,7 @@
 #include "b2q_qdq.cuh"
 #include "b2q_reduce.cuh"
 #include "b2q_resident.cuh"
+#include "b2q_cluster.cuh"
 
 static thread_local std::string g_last_error;
 
@@ -87,6 +88,10 @@ static int* option_slot(b2q_ctx* ctx, const char* key) {
     if (!strcmp(key, "dorefa_tanh_max")) return &ctx->dorefa_tanh_max;
     if (!strcmp(key, "host_ste_copy")) return &ctx->host_ste_copy;
     if (!strcmp(key, "shared_slot_rings")) return &ctx->shared_rings;
+    if (!strcmp(key, "cluster_fwd")) return &ctx->cluster_fwd;
+    if (!strcmp(key, "cluster_max_elems")) return &ctx->cluster_max_elems;
+    if (!strcmp(key, "cluster_max_elems_mean")) return &ctx->cluster_max_elems_mean;
+    if (!strcmp(key, "cluster_words_per_cta")) return &ctx->cluster_words_per_cta;
     if (!strcmp(key, "resident")) return &ctx->resident;
     if (!strcmp(key, "resident_max_mb")) return &ctx->resident_max_mb;
     if (!strcmp(key, "peer_mode")) return &ctx->peer_mode;
@@ -298,8 +303,11 @@ int b2q_minmax_quant_fwd_f32(b2q_ctx* ctx, int variant, const float* x, float* y
             UpdateArgs ud = u;
             ud.scale_out = nullptr;
             int done = 0;
+            // small tensors (weights): one launch of one thread-block cluster, the tensor read once (b2q_cluster.cuh)
+            int rc = launch_fused_cluster<true>(ctx, x, y, inner, ud, 127.f, clip ? B2Q_CLIP_SYM : B2Q_CLIP_NONE, 0, st, &done);
+            if (rc || done) return rc;
             // tensors that fit on chip: one launch (reduce -> grid barrier -> sweep out of shared memory / L2)
-            int rc = launch_fused_resident<true>(ctx, slot, x, y, inner, ud, 127.f, clip ? B2Q_CLIP_SYM : B2Q_CLIP_NONE, 0,
+            rc = launch_fused_resident<true>(ctx, slot, x, y, inner, ud, 127.f, clip ? B2Q_CLIP_SYM : B2Q_CLIP_NONE, 0,
                                                  st, &done);
             if (rc || done) return rc;
             rc = launch_fused_flat_fwd<true>(ctx, slot, x, y, inner, ud, 127.f, clip ? B2Q_CLIP_SYM : B2Q_CLIP_NONE, 0,
@@ -381,7 +389,9 @@ int b2q_gdrq_fwd_f32(b2q_ctx* ctx, const float* x, float* y, float* alpha, int64
         b2q_slot* slot = b2q_take_slot(ctx, st);
         if (groups == 1 && do_round && (req == B2Q_REQ_WRITE || req == B2Q_REQ_INPLACE)) {
             int done = 0;
-            int rc = launch_fused_resident<false>(ctx, slot, x, y, outer * inner, u, qlevel, B2Q_CLIP_SYM, 0, st, &done);
+            int rc = launch_fused_cluster<false>(ctx, x, y, outer * inner, u, qlevel, B2Q_CLIP_SYM, 0, st, &done);
+            if (rc || done) return rc;
+            rc = launch_fused_resident<false>(ctx, slot, x, y, outer * inner, u, qlevel, B2Q_CLIP_SYM, 0, st, &done);
             if (rc || done) return rc;
             rc = launch_fused_flat_fwd<false>(ctx, slot, x, y, outer * inner, u, qlevel, B2Q_CLIP_SYM, 0, st, &done);
             if (rc || done) return rc;
@@ -425,7 +435,9 @@ int b2q_foldbn_data_fwd_f32(b2q_ctx* ctx, const float* x, float* y, float* aux_d
     u.write_aux = 1; u.use_aux_as_scale = 1; u.p0 = ema_decay; u.p1 = one_minus_decay; u.aux = aux_data;
     {
         int done = 0;
-        int rc = launch_fused_resident<false>(ctx, slot, x, y, n, u, 127.f, B2Q_CLIP_SYM, /*clip_with_fresh=*/1, st, &done);
+        int rc = launch_fused_cluster<false>(ctx, x, y, n, u, 127.f, B2Q_CLIP_SYM, /*clip_with_fresh=*/1, st, &done);
+        if (rc || done) return rc;
+        rc = launch_fused_resident<false>(ctx, slot, x, y, n, u, 127.f, B2Q_CLIP_SYM, /*clip_with_fresh=*/1, st, &done);
         if (rc || done) return rc;
         rc = launch_fused_flat_fwd<false>(ctx, slot, x, y, n, u, 127.f, B2Q_CLIP_SYM, /*clip_with_fresh=*/1, st, &done);
         if (rc || done) return rc;

@@ -76,6 +76,11 @@ struct b2q_ctx {
     int resident_max_mb = 72;        // largest tensor (MB) that takes the single-launch resident forward
     int peer_mode = 1;               // 1: ticket-free reduction, the sweep's first block publishes to the peers; 0: r1 kernels;
                                      // 2 / 3: as 1 with one / two further tiles per block staged in shared memory during the wait
+    int cluster_fwd = 1;             // small whole-tensor forwards in ONE launch of one thread-block cluster (b2q_cluster.cuh)
+    int cluster_max_elems = 0;       // ... up to this many elements for the max-based operators (kernel limit 327 680;
+                                     // 0 = off: measured neutral in the step, profiles/r02s_cluster_sweep.log)
+    int cluster_max_elems_mean = 147456;   // ... and for the mean-based ones
+    int cluster_words_per_cta = 1024;   // grow the cluster (1/2/4/8 CTAs) while a CTA would hold more 256-bit words than this
     int stream_reduce = 0;           // 1: segmented / batch-statistics reductions through the TMA-staged ring when eligible (measured slower)
     int stream_stages = 4;           // 16 KB stages per block of that ring
     int stream_icvt = 0;             // float -> double conversions of the statistics kernels: 0 XU pipe, 1 integer pipe, 2 half / half

@@ -85,14 +85,50 @@ bnstat_fold_kernel(const float* __restrict__ y, SegPlan pl, b2q_slot* slot, floa
         s += s1;
         ss = q0 + q1;
     } else {
-        for (int64_t o = pc.o0; o < pc.o1; ++o) {
-            const float* base = y + (o * pl.groups + pc.g) * pl.inner;
-            for (int64_t i = pc.i0 + threadIdx.x; i < pc.i1; i += blockDim.x) {
-                const double a = (double)base[i];
-                s += a;
-                ss = fma(a, a, ss);
+        // Feature maps whose rows are not a multiple of eight floats -- 14x14 (196) and 7x7 (49), half the layers of
+        // ResNet / MobileNet: the piece's (row, element) space flattened into ONE index, so that a row of 49 floats does
+        // not leave 207 of 256 threads idle, walked incrementally (no division per element), four 128-bit loads (rows a
+        // multiple of four floats, 16-byte aligned) or sixteen scalar loads in flight per thread.  See
+        // profiles/r02v_bnstat_small_maps.md (0.14 -> 0.57 on 14x14, 0.036 -> 0.26 on 7x7)
+        constexpr int V = (VEC == 4) ? 4 : 1;
+        constexpr int U = (VEC == 4) ? 4 : 16;
+        const unsigned len = (unsigned)((pc.i1 - pc.i0) / V);          // vectors per row inside this piece
+        const unsigned long long total = (unsigned long long)(pc.o1 - pc.o0) * len;
+        const float* base = y + (pc.o0 * pl.groups + pc.g) * pl.inner + pc.i0;
+        const int64_t ostride = pl.groups * pl.inner;
+        const unsigned T = blockDim.x;
+        const unsigned qT = T / len, rT = T % len;
+        unsigned o = threadIdx.x / len, i = threadIdx.x % len;
+        double s1 = 0.0, q0 = 0.0, q1 = 0.0;
+        for (unsigned long long w = threadIdx.x; w < total; w += (unsigned long long)U * T) {
+            float v[U][V];
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                const float* p = base + (int64_t)o * ostride + (int64_t)i * V;
+                if (w + (unsigned long long)k * T < total) {
+                    if (V == 4) {
+                        const float4 t4 = *reinterpret_cast<const float4*>(p);
+                        v[k][0] = t4.x; v[k][V > 1 ? 1 : 0] = t4.y; v[k][V > 2 ? 2 : 0] = t4.z; v[k][V > 3 ? 3 : 0] = t4.w;
+                    } else {
+                        v[k][0] = *p;
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < V; ++e) v[k][e] = 0.f;
+                }
+                i += rT; o += qT;
+                if (i >= len) { i -= len; ++o; }
+            }
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+#pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    if ((k * V + e) & 1) acc1_sq_asm(s1, q1, v[k][e]); else acc1_sq_asm(s, q0, v[k][e]);
+                }
             }
         }
+        s += s1;
+        ss = q0 + q1;
     }
     const double bs = block_reduce<false>(s, smem);
     const double bss = block_reduce<false>(ss, smem);
@@ -163,6 +199,7 @@ static int launch_bnstat(b2q_ctx* ctx, const float* y, int64_t n, int64_t c, int
     b2q_slot* slot = b2q_take_slot(ctx, st);
     b2q_timed_launch tl(ctx, B2Q_KIND_OTHER, 4.0 * (double)(n * c * hw), st);
     const bool vec8 = (hw % 8 == 0) && (pl.part % 8 == 0) && ((((uintptr_t)y) & 31) == 0);
+    const bool vec4 = !vec8 && (hw % 4 == 0) && (pl.part % 4 == 0) && ((((uintptr_t)y) & 15) == 0);
     if (vec8 && ctx->stream_reduce && b2q_stream_ok(pl)) {
         const int nst = b2q_stream_stages(ctx);
         const size_t smem = b2q_stream_smem(nst);
@@ -178,7 +215,8 @@ static int launch_bnstat(b2q_ctx* ctx, const float* y, int64_t n, int64_t c, int
     }
     // (loads in flight per thread, resident blocks per SM); option bn_variant
 #define B2Q_BN_LAUNCH(U, B) do {                                                                                          \
-        if (!vec8) b2q_launch(ctx, bnstat_fold_kernel<1, U, B, 0>, grid, B2Q_THREADS, st, y, pl, slot, scale, mean, var, f, 0);  \
+        if (vec4) b2q_launch(ctx, bnstat_fold_kernel<4, U, B, 0>, grid, B2Q_THREADS, st, y, pl, slot, scale, mean, var, f, 0);     \
+        else if (!vec8) b2q_launch(ctx, bnstat_fold_kernel<1, U, B, 0>, grid, B2Q_THREADS, st, y, pl, slot, scale, mean, var, f, 0);  \
         else if (ctx->stream_icvt == 1)                                                                                    \
             b2q_launch(ctx, bnstat_fold_kernel<8, U, B, 1>, grid, B2Q_THREADS, st, y, pl, slot, scale, mean, var, f, 0);       \
         else if (ctx->stream_icvt == 2)                                                                                    \

@@ -35,15 +35,14 @@ def timeit(fn, reps=12):
     return e0.elapsed_time(e1) / reps
 
 
-CONFIGS = []
-for variant in (1, 3, 6):
-    for icvt in (0, 2):
-        for pieces in (8, 16):
-            CONFIGS.append(dict(stream_reduce=0, bn_variant=variant, stream_icvt=icvt, bn_pieces_per_sm=pieces))
+CONFIGS = [dict()]
 
-for cshape, wshape in (((256, 64, 64, 64), (64, 64, 3, 3)), ((256, 1024, 16, 16), (1024, 512, 1, 1))):
+for cshape, wshape in (((256, 64, 64, 64), (64, 64, 3, 3)), ((256, 1024, 16, 16), (1024, 512, 1, 1)),
+                       ((128, 512, 28, 28), (512, 128, 1, 1)), ((256, 1024, 14, 14), (1024, 256, 1, 1)),
+                       ((256, 2048, 7, 7), (2048, 512, 1, 1)), ((256, 1024, 7, 7), (1024, 1, 3, 3))):
     c = cshape[1]
-    conv = [x.view(cshape) for x in xs]
+    m = int(torch.Size(cshape).numel())
+    conv = [x[:m].view(cshape) for x in xs]
     w = torch.randn(wshape, device="cuda") * 0.05
     wq, bias, aw = torch.empty_like(w), torch.empty(c, device="cuda"), torch.ones(c, device="cuda")
     mu, var = torch.empty(c, device="cuda"), torch.empty(c, device="cuda")
@@ -52,7 +51,7 @@ for cshape, wshape in (((256, 64, 64, 64), (64, 64, 3, 3)), ((256, 1024, 16, 16)
         for k, v in cfg.items():
             ctx.set_option(k, v)
         ms = timeit(lambda i: K.bnstat_foldbn_weight_fwd(conv[i], mu, var, w, wq, bias, aw, gm, bt, 1e-5, True, True, True))
-        gbs = 4 * n / ms / 1e6
+        gbs = 4 * m / ms / 1e6
         print("bnstat %-16s %-70s %7.1f us %7.1f GB/s %.3f" % ("x".join(map(str, cshape)), cfg, ms * 1e3, gbs, gbs / peak),
               flush=True)
 

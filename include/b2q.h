@@ -296,7 +296,9 @@ int b2q_peer_buffer_create(b2q_ctx* ctx, int64_t bytes, void** buffer, void* ipc
  * bufs[r] = rank r's buffer as mapped on THIS device, mailboxes as for the threshold exchange.  Rank r reduces the
  * r-th slice of every rank's buffer in rank order and stores it into every rank's buffer (bit-identical everywhere);
  * two flag barriers through the mailboxes order it with the peers' streams.  All ranks call it in the same order
- * with the same count; asynchronous on `stream`; waits bounded by "peer_timeout_ms" (b2q_peer_status).            */
+ * with the same count; asynchronous on `stream`; waits bounded by "peer_timeout_ms" (b2q_peer_status).  The calls of
+ * one set of mailboxes share one sequence counter: issue them stream-ordered with each other (not concurrently on two
+ * streams).                                                                                                   */
 int b2q_peer_allreduce_sum_f32(b2q_ctx* ctx, float* const* bufs, int64_t count, int average, void* const* mailboxes,
                                int rank, int world, void* stream);
 int b2q_peer_allreduce_max_f32(b2q_ctx* ctx, float* const* bufs, int64_t count, void* const* mailboxes, int rank, int world,

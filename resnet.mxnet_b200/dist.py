@@ -241,7 +241,9 @@ class PeerBuffer(object):
     handle), the handles all-gathered once through torch.distributed, the peers' buffers mapped into this process.
     ``tensor`` is the rank's own buffer as a torch tensor (zero-filled); ``allreduce_sum`` / ``allreduce_max`` reduce the
     first ``count`` elements over all ranks in place with ONE kernel per rank over NVLink (b2q_peer_allreduce_*_f32): no
-    NCCL call.  All ranks must issue the same calls in the same order."""
+    NCCL call.  All ranks must issue the same calls in the same order, and the allreduce calls of one exchange must be
+    ordered with each other on the device (one stream, or streams that wait for each other): they share the exchange's
+    sequence counter.  ``tensor`` is a view of library-owned memory: do not use it after ``close()``."""
 
     def __init__(self, exchange, numel):
         import ctypes

@@ -386,6 +386,79 @@ qdq_seg_kernel(const float* __restrict__ x, float* __restrict__ y, SegPlan pl, P
     }
 }
 
+// Grouped ACTIVATIONS with SHORT rows that are not a multiple of eight floats (GDRQ group_size on 14x14 / 7x7 maps: rows
+// of 196 / 49 floats): the row-at-a-time loops above keep 49 of 128 threads busy with one access each.  Here the piece's
+// (row, element) space is flattened into one index walked incrementally (no division per element), U accesses of V
+// floats in flight per thread.  V = 4: rows a multiple of four floats and 16-byte aligned; V = 1: anything.
+struct FlatWalk {
+    unsigned len, qT, rT, o, i;
+    unsigned long long total;
+    int64_t ostride, base;      // element offset of the piece's first row / between rows
+};
+
+__device__ __forceinline__ FlatWalk flat_walk(const SegPlan& pl, const SegPiece& pc, int V) {
+    FlatWalk w;
+    w.len = (unsigned)((pc.i1 - pc.i0) / V);
+    w.total = (unsigned long long)(pc.o1 - pc.o0) * w.len;
+    w.base = (pc.o0 * pl.groups + pc.g) * pl.inner + pc.i0;
+    w.ostride = pl.groups * pl.inner;
+    w.qT = blockDim.x / w.len;
+    w.rT = blockDim.x % w.len;
+    w.o = threadIdx.x / w.len;
+    w.i = threadIdx.x % w.len;
+    return w;
+}
+
+__device__ __forceinline__ void flat_walk_next(FlatWalk& w) {
+    w.i += w.rT; w.o += w.qT;
+    if (w.i >= w.len) { w.i -= w.len; ++w.o; }
+}
+
+template <int V>
+__global__ void __launch_bounds__(B2Q_THREADS)
+qdq_seg_flatidx_kernel(const float* __restrict__ x, float* __restrict__ y, SegPlan pl, QdqArgs a) {
+    b2q_pdl_sync();
+    constexpr int U = (V == 4) ? 4 : 8;
+    const SegPiece pc = seg_piece(pl);
+    const float T = a.thr ? __ldg(a.thr + pc.g) : a.thr_imm;
+    const float Tc = a.clip_thr ? __ldg(a.clip_thr + pc.g) : (a.thr ? T : a.clip_imm);
+    const QScale qs = make_qscale(T, a.qlevel, a.fast != 0);
+    const bool add = (a.req == B2Q_REQ_ADD);
+    FlatWalk w = flat_walk(pl, pc, V);
+    for (unsigned long long t = threadIdx.x; t < w.total; t += (unsigned long long)U * blockDim.x) {
+        float v[U][V];
+        int64_t off[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            off[k] = w.base + (int64_t)w.o * w.ostride + (int64_t)w.i * V;
+            if (t + (unsigned long long)k * blockDim.x < w.total) {
+                if (V == 4) {
+                    const float4 t4 = *reinterpret_cast<const float4*>(x + off[k]);
+                    v[k][0] = t4.x; v[k][V > 1 ? 1 : 0] = t4.y; v[k][V > 2 ? 2 : 0] = t4.z; v[k][V > 3 ? 3 : 0] = t4.w;
+                } else {
+                    v[k][0] = x[off[k]];
+                }
+            } else {
+                off[k] = -1;
+            }
+            flat_walk_next(w);
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            if (off[k] < 0) continue;
+            float r[V];
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                float code;
+                r[e] = qdq_generic(a, v[k][e], Tc, qs, code);
+                if (add) r[e] = __fadd_rn(y[off[k] + e], r[e]);
+            }
+            if (V == 4) *reinterpret_cast<float4*>(y + off[k]) = make_float4(r[0], r[V > 1 ? 1 : 0], r[V > 2 ? 2 : 0], r[V > 3 ? 3 : 0]);
+            else y[off[k]] = r[0];
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Row-fused weight path (K2 / K9): one WARP per row (out-channel or GDRQ group), ONE kernel.
 // pass 1: statistic of the row (max|w| or sum|w|, optional fold-BN prescale) -> warp shuffle tree (fixed order);
@@ -705,6 +778,54 @@ bwd_seg_kernel(const float* __restrict__ x, const float* __restrict__ dy, float*
     }
 }
 
+// the same flattened walk for the masked / straight-through backward of grouped activations with short rows
+template <int MASK, bool ADD, int V>
+__global__ void __launch_bounds__(B2Q_THREADS)
+bwd_seg_flatidx_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, SegPlan pl,
+                       const float* thr, float thr_imm) {
+    b2q_pdl_sync();
+    constexpr int U = (V == 4) ? 2 : 4;
+    const SegPiece pc = seg_piece(pl);
+    const float T = thr ? __ldg(thr + pc.g) : thr_imm;
+    FlatWalk w = flat_walk(pl, pc, V);
+    for (unsigned long long t = threadIdx.x; t < w.total; t += (unsigned long long)U * blockDim.x) {
+        float xv[U][V], gv[U][V];
+        int64_t off[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            off[k] = w.base + (int64_t)w.o * w.ostride + (int64_t)w.i * V;
+            if (t + (unsigned long long)k * blockDim.x < w.total) {
+                if (V == 4) {
+                    const float4 g4 = *reinterpret_cast<const float4*>(dy + off[k]);
+                    gv[k][0] = g4.x; gv[k][V > 1 ? 1 : 0] = g4.y; gv[k][V > 2 ? 2 : 0] = g4.z; gv[k][V > 3 ? 3 : 0] = g4.w;
+                    if (MASK != 0) {
+                        const float4 x4 = *reinterpret_cast<const float4*>(x + off[k]);
+                        xv[k][0] = x4.x; xv[k][V > 1 ? 1 : 0] = x4.y; xv[k][V > 2 ? 2 : 0] = x4.z; xv[k][V > 3 ? 3 : 0] = x4.w;
+                    }
+                } else {
+                    gv[k][0] = dy[off[k]];
+                    if (MASK != 0) xv[k][0] = x[off[k]];
+                }
+            } else {
+                off[k] = -1;
+            }
+            flat_walk_next(w);
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            if (off[k] < 0) continue;
+            float r[V];
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                r[e] = (MASK != 0) ? mask_grad<MASK>(xv[k][e], gv[k][e], T) : gv[k][e];
+                if (ADD) r[e] = __fadd_rn(dx[off[k] + e], r[e]);
+            }
+            if (V == 4) *reinterpret_cast<float4*>(dx + off[k]) = make_float4(r[0], r[V > 1 ? 1 : 0], r[V > 2 ? 2 : 0], r[V > 3 ? 3 : 0]);
+            else dx[off[k]] = r[0];
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------
@@ -766,6 +887,13 @@ static inline bool same_misalignment(const void* a, const void* b) {
             B2Q_LAUNCH_CHECK(ctx);
             return 0;
         }
+    }
+    // large grouped activations with short rows (14x14 / 7x7 maps): flattened (row, element) walk
+    if (ps.gamma == nullptr && fb.bias == nullptr && !a.codes && pl.P == 1 && inner < 2048 && n >= (1 << 18)) {
+        if (pl.vec == 4) b2q_launch(ctx, qdq_seg_flatidx_kernel<4>, grid, B2Q_THREADS, st, x, y, pl, a);
+        else b2q_launch(ctx, qdq_seg_flatidx_kernel<1>, grid, B2Q_THREADS, st, x, y, pl, a);
+        B2Q_LAUNCH_CHECK(ctx);
+        return 0;
     }
     if (pl.vec == 4) b2q_launch(ctx, qdq_seg_kernel<4>, grid, 128, st, x, y, pl, ps, fb, a);
     else b2q_launch(ctx, qdq_seg_kernel<1>, grid, 128, st, x, y, pl, ps, fb, a);
@@ -844,6 +972,17 @@ static int launch_bwd_mask(b2q_ctx* ctx, const float* x, const float* dy, float*
     SegPlan pl = b2q_seg_plan(dy, dx, outer, groups, inner, ctx->num_sms * 16);
     if (MASK != 0 && (((uintptr_t)x) & 15)) pl.vec = 1;
     const unsigned grid = (unsigned)(groups * pl.S * pl.P);
+    if (pl.P == 1 && inner < 2048 && n >= (1 << 18)) {   // short rows: flattened (row, element) walk
+        if (pl.vec == 4) {
+            if (add) b2q_launch(ctx, bwd_seg_flatidx_kernel<MASK, true, 4>, grid, B2Q_THREADS, st, x, dy, dx, pl, thr, thr_imm);
+            else b2q_launch(ctx, bwd_seg_flatidx_kernel<MASK, false, 4>, grid, B2Q_THREADS, st, x, dy, dx, pl, thr, thr_imm);
+        } else {
+            if (add) b2q_launch(ctx, bwd_seg_flatidx_kernel<MASK, true, 1>, grid, B2Q_THREADS, st, x, dy, dx, pl, thr, thr_imm);
+            else b2q_launch(ctx, bwd_seg_flatidx_kernel<MASK, false, 1>, grid, B2Q_THREADS, st, x, dy, dx, pl, thr, thr_imm);
+        }
+        B2Q_LAUNCH_CHECK(ctx);
+        return 0;
+    }
     if (add) b2q_launch(ctx, bwd_seg_kernel<MASK, true>, grid, 128, st, x, dy, dx, pl, thr, thr_imm);
     else b2q_launch(ctx, bwd_seg_kernel<MASK, false>, grid, 128, st, x, dy, dx, pl, thr, thr_imm);
     B2Q_LAUNCH_CHECK(ctx);

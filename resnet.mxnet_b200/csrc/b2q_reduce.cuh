@@ -385,9 +385,11 @@ __device__ __forceinline__ float prescale_factor(const Prescale& ps, int64_t row
 }
 
 // VEC: 1 / 4 / 8 = register-staged loads of that many floats; 16 / 17 = the TMA-staged ring above (17: float -> double
-// conversions on the integer pipe), `nst` stages of dynamic shared memory
+// conversions on the integer pipe), `nst` stages of dynamic shared memory; 2 / 3 = large activations with SHORT rows that
+// are not a multiple of eight floats (14x14 / 7x7 maps): the piece's (row, element) space flattened into one index,
+// walked incrementally, four 128-bit (2) or eight scalar (3) loads in flight per thread
 template <bool IS_MAX, int VEC>
-__global__ void __launch_bounds__(VEC >= 8 ? B2Q_THREADS : 128)
+__global__ void __launch_bounds__((VEC >= 8 || VEC == 2 || VEC == 3) ? B2Q_THREADS : 128)
 reduce_seg_kernel(const float* __restrict__ x, SegPlan pl, Prescale ps, b2q_slot* slot, UpdateArgs u, int nst) {
     b2q_pdl_sync();
     __shared__ double smem[32];
@@ -401,6 +403,41 @@ reduce_seg_kernel(const float* __restrict__ x, SegPlan pl, Prescale ps, b2q_slot
         unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_dyn + (size_t)nst * B2Q_STREAM_CH * 4);
         double unused = 0.0;
         seg_stream_accumulate<IS_MAX ? 1 : 0, VEC == 17>(x, pl, pc, s_buf, s_bar, nst, acc, unused, mx);
+    }
+    if (VEC == 2 || VEC == 3) {
+        constexpr int V = (VEC == 2) ? 4 : 1;
+        constexpr int U = (VEC == 2) ? 4 : 8;
+        const unsigned len = (unsigned)((pc.i1 - pc.i0) / V);
+        const unsigned long long total = (unsigned long long)(pc.o1 - pc.o0) * len;
+        const float* base = x + (pc.o0 * pl.groups + pc.g) * pl.inner + pc.i0;
+        const int64_t ostride = pl.groups * pl.inner;
+        const unsigned qT = blockDim.x / len, rT = blockDim.x % len;
+        unsigned o = threadIdx.x / len, i = threadIdx.x % len;
+        for (unsigned long long t = threadIdx.x; t < total; t += (unsigned long long)U * blockDim.x) {
+            float v[U][V];
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                const float* p = base + (int64_t)o * ostride + (int64_t)i * V;
+                if (t + (unsigned long long)k * blockDim.x < total) {
+                    if (V == 4) {
+                        const float4 t4 = *reinterpret_cast<const float4*>(p);
+                        v[k][0] = t4.x; v[k][V > 1 ? 1 : 0] = t4.y; v[k][V > 2 ? 2 : 0] = t4.z; v[k][V > 3 ? 3 : 0] = t4.w;
+                    } else {
+                        v[k][0] = *p;
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < V; ++e) v[k][e] = 0.f;
+                }
+                i += rT; o += qT;
+                if (i >= len) { i -= len; ++o; }
+            }
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+#pragma unroll
+                for (int e = 0; e < V; ++e) acc1<IS_MAX>(acc, mx, v[k][e]);
+            }
+        }
     }
     if (VEC == 8) {
         // 256-bit loads, four in flight per thread, over the piece's (row, word) space FLATTENED into one index: short
@@ -434,7 +471,7 @@ reduce_seg_kernel(const float* __restrict__ x, SegPlan pl, Prescale ps, b2q_slot
             }
         }
     }
-    for (int64_t o = pc.o0; VEC < 8 && o < pc.o1; ++o) {
+    for (int64_t o = pc.o0; (VEC == 1 || VEC == 4) && o < pc.o1; ++o) {
         const int64_t row = o * pl.groups + pc.g;
         const float* base = x + row * pl.inner;
         const float f = ps.gamma ? prescale_factor(ps, row) : 1.f;
@@ -598,6 +635,10 @@ static int launch_reduce(b2q_ctx* ctx, b2q_slot* slot, const float* x, int64_t o
         }
     } else if (vec8)
         b2q_launch(ctx, reduce_seg_kernel<IS_MAX, 8>, grid, B2Q_THREADS, st, x, pl, ps, slot, u, 0);
+    else if (ps.gamma == nullptr && pl.P == 1 && inner < 2048 && n >= (1 << 18)) {   // short rows: flattened walk
+        if (pl.vec == 4) b2q_launch(ctx, reduce_seg_kernel<IS_MAX, 2>, grid, B2Q_THREADS, st, x, pl, ps, slot, u, 0);
+        else b2q_launch(ctx, reduce_seg_kernel<IS_MAX, 3>, grid, B2Q_THREADS, st, x, pl, ps, slot, u, 0);
+    }
     else if (pl.vec == 4) b2q_launch(ctx, reduce_seg_kernel<IS_MAX, 4>, grid, 128, st, x, pl, ps, slot, u, 0);
     else b2q_launch(ctx, reduce_seg_kernel<IS_MAX, 1>, grid, 128, st, x, pl, ps, slot, u, 0);
     B2Q_LAUNCH_CHECK(ctx);

@@ -137,3 +137,36 @@ def test_guard_regions_around_medium_tensors(op_type):
             for i, b in enumerate(bufs):
                 a = lo + 1 if (k == 9 and i == 1) else lo
                 assert bool((b[:a] == canary).all()) and bool((b[a + n:] == canary).all()), (k, offset, i)
+
+
+@pytest.mark.parametrize("shape,gs", [((64, 64, 14, 14), 1), ((64, 64, 14, 14), 4), ((128, 96, 7, 7), 1), ((128, 96, 7, 7), 8),
+                                      ((96, 40, 9, 11), 5), ((40, 48, 13, 13), 2), ((33, 40, 9, 11), 1)])
+@pytest.mark.parametrize("req", ["write", "add"])
+def test_gdrq_grouped_activations_on_small_feature_maps(shape, gs, req):
+    """Grouped GDRQ_PY activations (GDRQ.py:88-118, :131-152) whose rows are not a multiple of eight floats -- 14x14, 7x7 and
+    odd maps: large tensors take the flattened (row, element) kernels (reduce_seg_kernel<.., 2|3>, qdq_seg_flatidx_kernel,
+    bwd_seg_flatidx_kernel); the last shape stays below their size limit and takes the row-at-a-time kernels.  Two
+    training steps against the oracle: alpha to 1e-6, and bit-exact output / gradient given the same alpha."""
+    import torch
+    rng = np.random.default_rng(hash((shape, gs)) % (1 << 31))
+    groups = shape[1] // gs
+    op, ref = _ops("GDRQ_PY", nbits=8, group_size=gs, is_weight=False, lamda=0.001, delay_quant=0, fix_alpha=False, ktimes=3)
+    aux_d, aux_r = [torch.ones(groups, device="cuda")], [np.ones(groups, F)]
+    for step in range(2):
+        x = (rng.standard_normal(shape) * (0.5 + step)).astype(F)
+        dy = rng.standard_normal(shape).astype(F)
+        xd, yd, yr = torch.from_numpy(x).cuda(), torch.zeros(shape, device="cuda"), np.zeros(shape, F)
+        op.forward(True, ["write"], [xd], [yd], aux_d)
+        ref.forward(True, ["write"], [x], [yr], aux_r)
+        np.testing.assert_allclose(aux_d[0].cpu().numpy(), aux_r[0], rtol=1e-6)
+        aux_r[0][...] = aux_d[0].cpu().numpy()        # same alpha on both sides from here on
+        c = np.where(np.abs(x) <= aux_r[0][None, :, None, None].repeat(gs, 1), x,
+                     (aux_r[0][None, :, None, None].repeat(gs, 1) * np.sign(x)).astype(F)).astype(F)
+        q = qo.mx_div(np.broadcast_to(aux_r[0][None, :, None, None].repeat(gs, 1), shape).astype(F), F(255))
+        want, _ = qo.qdq(c, q)
+        assert bits_equal(yd.cpu().numpy(), want)
+        g0 = rng.standard_normal(shape).astype(F)
+        gd, gr = torch.from_numpy(g0.copy()).cuda(), g0.copy()
+        op.backward([req], [torch.from_numpy(dy).cuda()], [xd], [yd], [gd], aux_d)
+        ref.backward([req], [dy], [x], [want], [gr], [aux_r[0]])
+        assert bits_equal(gd.cpu().numpy(), gr)

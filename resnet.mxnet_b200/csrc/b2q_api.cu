@@ -102,6 +102,7 @@ static int* option_slot(b2q_ctx* ctx, const char* key) {
     if (!strcmp(key, "bn_pieces_per_sm")) return &ctx->bn_pieces_per_sm;
     if (!strcmp(key, "peer_allreduce_blocks")) return &ctx->peer_allreduce_blocks;
     if (!strcmp(key, "peer_allreduce_blocks_per_sm")) return &ctx->peer_allreduce_blocks_per_sm;
+    if (!strcmp(key, "peer_publish_blocks_per_sm")) return &ctx->peer_publish_blocks_per_sm;
     if (!strcmp(key, "peer_stage_early")) return &ctx->peer_stage_early;
     if (!strcmp(key, "peer_timeout_ms")) return &ctx->peer_timeout_ms;
     return nullptr;

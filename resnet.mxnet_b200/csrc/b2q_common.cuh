@@ -88,6 +88,7 @@ struct b2q_ctx {
     int bn_pieces_per_sm = 8;        // pieces (blocks) per SM the batch-statistics launch is split into
     int peer_allreduce_blocks_per_sm = 2;   // grid cap of peer_allreduce_kernel
     int peer_allreduce_blocks = 148;        // > 0: absolute grid cap (96..148 measured best at 2 GPUs); 0: blocks_per_sm x SMs
+    int peer_publish_blocks_per_sm = 16;   // peer_mode 4: grid of the publishing reduction (one ticket per block)
     int peer_stage_early = 0;        // 1: issue the staging copies before the dependency wait instead of right after it
     int peer_timeout_ms = 600000;    // how long a sweep waits for a peer's statistic before it gives up (NaN output + flag)
     int timing = 0;

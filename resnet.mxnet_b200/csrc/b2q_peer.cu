@@ -245,6 +245,62 @@ qdq_peer_kernel(const float* __restrict__ x, float* __restrict__ y, FlatSplit sp
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// peer_mode 4: the deferred max reduction with ONE extra atomic per block -- a release ticket after the tagged atomicMax --
+// so that the block which finishes last can store this rank's statistic into every rank's mailbox from INSIDE the
+// reduction, instead of the sweep's block 0 doing it after the whole grid has drained, the dependent launch has been
+// released and the word has been read back (about 1 us of the 5 us the exchange adds per node).  The sweep
+// (qdq_peer2_kernel with `published` = 1) then only polls.  max|x| statistics only; the mean-based operators keep mode 1.
+// ------------------------------------------------------------------------------------------------------------------
+template <int UNROLL, int LDPOL>
+__global__ void __launch_bounds__(B2Q_THREADS)
+reduce_flat_publish_kernel(const float* __restrict__ x, FlatSplit sp, b2q_slot* slot, UpdateArgs u, PeerBoxes pb) {
+    b2q_pdl_sync();
+    __shared__ double smem[32];
+    double acc = 0.0;
+    float mx = 0.f;
+    const float* xb = x + sp.head;
+    const int64_t tile = (int64_t)B2Q_THREADS * UNROLL;
+    const int64_t ntiles = (sp.n8 + tile - 1) / tile;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t base = t * tile + threadIdx.x;
+        f8 v[UNROLL];
+#pragma unroll
+        for (int k = 0; k < UNROLL; ++k) {
+            const int64_t i = base + (int64_t)k * B2Q_THREADS;
+            if (i < sp.n8) v[k] = ld_f8<LDPOL>(xb + 8 * i);
+            else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[k].v[j] = 0.f;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < UNROLL; ++k) acc8<true>(acc, mx, v[k]);
+    }
+    if (blockIdx.x == 0) {  // the (at most 14) unaligned scalars
+        if ((int64_t)threadIdx.x < sp.head) acc1<true>(acc, mx, x[threadIdx.x]);
+        if ((int64_t)threadIdx.x < sp.tail) acc1<true>(acc, mx, x[sp.head + 8 * sp.n8 + threadIdx.x]);
+    }
+    const double r = block_reduce<true>((double)mx, smem);
+    if (threadIdx.x == 0) {
+        const unsigned int tag = slot->epoch + 1u;
+        atomicMax(&slot->max64, ((unsigned long long)tag << 32) | __float_as_uint((float)r));
+        if (blockIdx.x == 0) {
+            if (u.aux) slot->scale[0] = u.aux[0];             // snapshot of the old threshold
+            *u.seq_counter = *u.seq_counter + 1u;             // this call's sequence number, before block 0's ticket
+        }
+        if (b2q_take_ticket(&slot->ticket, gridDim.x - 1) == gridDim.x - 1) {
+            // every block's atomicMax and block 0's counter update are visible (release tickets, acquire here)
+            slot->ticket = 0;
+            const unsigned long long word = *((volatile unsigned long long*)&slot->max64);
+            const unsigned int seq = *((volatile unsigned int*)u.seq_counter);
+            const unsigned long long out = ((unsigned long long)seq << 32) | (word & 0xffffffffull);
+            for (int rk = 0; rk < pb.world; ++rk)
+                st_sys_u64(pb.box[rk] + (size_t)(seq & 1u) * B2Q_PEER_MAX_RANKS + pb.rank, out);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // peer_mode 1 (default): no ticket chain at all.
 //   kernel 1  the ordinary deferred reduction of the single-GPU forward (reduce_flat_kernel<.., FINALIZE=false>: one tagged
 //             atomicMax per block, or fp64 partial sums; block 0 snapshots the old aux and advances the call counter).
@@ -310,7 +366,7 @@ template <int CLIP, int UNROLL, int LDPOL, int STPOL>
 __global__ void __launch_bounds__(B2Q_THREADS)
 qdq_peer2_kernel(const float* __restrict__ x, float* __restrict__ y, FlatSplit sp, PeerBoxes pb, b2q_slot* slot,
                  UpdateArgs u, float qlevel, int fast, int reverse, int clip_with_fresh, int is_max, int n_partials,
-                 float count, unsigned long long timeout_ns) {
+                 float count, unsigned long long timeout_ns, int published) {
     __shared__ float s_stat;
     __shared__ double s_red[32];
     const float* xb = x + sp.head;
@@ -345,7 +401,7 @@ qdq_peer2_kernel(const float* __restrict__ x, float* __restrict__ y, FlatSplit s
             mine = s_stat;
             __syncthreads();
         }
-        if ((int)threadIdx.x < pb.world) {
+        if (!published && (int)threadIdx.x < pb.world) {   // peer_mode 4: the reduction's last block has done this already
             const unsigned long long word = ((unsigned long long)seq << 32) | __float_as_uint(mine);
             st_sys_u64(pb.box[threadIdx.x] + (size_t)(seq & 1u) * B2Q_PEER_MAX_RANKS + pb.rank, word);
         }
@@ -744,8 +800,20 @@ static int peer_quant_fwd(b2q_ctx* ctx, bool is_max, int upd_mode, float p0, flo
         ur.aux = aux;                       // the deferred reduction snapshots the old threshold into slot->scale[0]
         ur.seq_counter = &pb.state->seq;
         int np = 0;
-        int rc = is_max ? launch_reduce_deferred<true>(ctx, slot, x, n, ur, st, &np)
+        int rc = 0;
+        const int published = (mode == 4 && is_max) ? 1 : 0;
+        if (published) {   // the reduction's last block publishes (one release ticket per block on top of the atomicMax)
+            B2Q_REQUIRE(sp.head <= B2Q_THREADS, "peer path needs equally aligned float32 buffers");
+            const int64_t rgrid = b2q_flat_grid(ctx, sp.n8, B2Q_REDUCE_UNROLL, ctx->peer_publish_blocks_per_sm > 0 ? ctx->peer_publish_blocks_per_sm : ctx->reduce_deferred_blocks_per_sm);
+            b2q_timed_launch tl(ctx, B2Q_KIND_REDUCE_FLAT, 4.0 * (double)n, st);
+            b2q_launch(ctx, reduce_flat_publish_kernel<B2Q_REDUCE_UNROLL, B2Q_REDUCE_LDPOL>, (unsigned)rgrid, B2Q_THREADS, st, x,
+                       sp, slot, ur, pb);
+            B2Q_LAUNCH_CHECK(ctx);
+            np = (int)rgrid;
+        } else {
+            rc = is_max ? launch_reduce_deferred<true>(ctx, slot, x, n, ur, st, &np)
                         : launch_reduce_deferred<false>(ctx, slot, x, n, ur, st, &np);
+        }
         if (rc) return rc;
         B2Q_REQUIRE(np > 0, "peer path needs equally aligned float32 buffers");
         UpdateArgs u;
@@ -758,7 +826,7 @@ static int peer_quant_fwd(b2q_ctx* ctx, bool is_max, int upd_mode, float p0, flo
         const unsigned long long timeout_ns = (unsigned long long)(ctx->peer_timeout_ms > 0 ? ctx->peer_timeout_ms : 1) * 1000000ull;
         b2q_timed_launch tl(ctx, B2Q_KIND_QDQ_HOT, 8.0 * (double)n, st);
 #define B2Q_PEER2_SWEEP(C, S) b2q_launch(ctx, qdq_peer2_kernel<C, B2Q_QDQ_UNROLL, B2Q_QDQ_LDPOL, S>, (unsigned)grid, B2Q_THREADS, st, \
-            x, y, sp, pb, slot, u, qlevel, ctx->fast_div, rev, clip_with_fresh, is_max ? 1 : 0, np, (float)n, timeout_ns)
+            x, y, sp, pb, slot, u, qlevel, ctx->fast_div, rev, clip_with_fresh, is_max ? 1 : 0, np, (float)n, timeout_ns, published)
 #define B2Q_PEER2_SWEEP_S(C) do { if (stream_out) B2Q_PEER2_SWEEP(C, 1); else B2Q_PEER2_SWEEP(C, B2Q_QDQ_STPOL); } while (0)
 #define B2Q_PEER3_SWEEP(C, S, G) do {                                                                                  \
             const int64_t tiles_ = (sp.n8 + (int64_t)B2Q_THREADS * B2Q_QDQ_UNROLL - 1) / ((int64_t)B2Q_THREADS * B2Q_QDQ_UNROLL); \

@@ -153,7 +153,7 @@ def test_kernel_variants_bit_exact_at_full_size(T, co, shape, opts):
             ctx.set_option(k, v)
 
 
-@pytest.mark.parametrize("peer_mode", [1, 2, 3])
+@pytest.mark.parametrize("peer_mode", [1, 2, 3, 4])
 @pytest.mark.parametrize("shape", [SHAPES[0], SHAPES[2]], ids=[IDS[0], IDS[2]])
 def test_peer_kernels_world1_bit_exact_at_full_size(T, co, shape, peer_mode):
     """the fused peer-memory exchange kernels (reduce_peer_kernel / qdq_peer_kernel) on real shapes; at world 1 the max

@@ -33,7 +33,7 @@ def test_peer_exchange_world1_matches_plain_path():
         ex.close()
 
 
-@pytest.mark.parametrize("peer_mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("peer_mode", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("reverse_all", [False, True])
 def test_peer_sweep_variants_equal_plain_path_around_tile_edges(peer_mode, reverse_all):
     """peer_mode 2 / 3 give every block 2 / 3 tiles (one in registers, the others staged in shared memory by bulk

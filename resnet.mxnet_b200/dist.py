@@ -196,13 +196,15 @@ def pin_rank_to_host_cores(local_rank, local_world, device_index=None):
     except AttributeError:  # pragma: no cover
         return []
     cores = None
+
+    def numa_node_of(dev):
+        prop = torch.cuda.get_device_properties(dev)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
+        return int(open(path).read().strip())
+
     if device_index is not None and torch.cuda.is_available():
         try:
-            bus = torch.cuda.get_device_properties(device_index).pci_bus_id
-            dom = torch.cuda.get_device_properties(device_index).pci_domain_id
-            devid = torch.cuda.get_device_properties(device_index).pci_device_id
-            path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, devid)
-            node = int(open(path).read().strip())
+            node = numa_node_of(device_index)
             if node >= 0:
                 spans = open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(",")
                 on_node = []
@@ -210,10 +212,20 @@ def pin_rank_to_host_cores(local_rank, local_world, device_index=None):
                     lo, _, hi = sp.partition("-")
                     on_node += list(range(int(lo), int(hi or lo) + 1))
                 on_node = [c for c in on_node if c in allowed]
-                # ranks that share the node share its cores evenly, in rank order
-                same = [r for r in range(local_world)]
-                share = max(1, len(on_node) // max(1, len(same)))
-                k = local_rank % max(1, len(on_node) // share)
+                # the local ranks whose GPU hangs off the same node share its cores evenly, in rank order (local rank r
+                # drives device r, as torchrun sets it up)
+                same = []
+                for r in range(local_world):
+                    try:
+                        if numa_node_of(r) == node:
+                            same.append(r)
+                    except Exception:
+                        pass
+                if local_rank not in same:
+                    same.append(local_rank)
+                    same.sort()
+                share = max(1, len(on_node) // len(same))
+                k = same.index(local_rank)
                 if on_node:
                     cores = on_node[k * share:(k + 1) * share] or on_node
         except Exception:

@@ -170,3 +170,28 @@ def test_gdrq_grouped_activations_on_small_feature_maps(shape, gs, req):
         op.backward([req], [torch.from_numpy(dy).cuda()], [xd], [yd], [gd], aux_d)
         ref.backward([req], [dy], [x], [want], [gr], [aux_r[0]])
         assert bits_equal(gd.cpu().numpy(), gr)
+
+
+@pytest.mark.parametrize("shape", [(64, 64, 14, 14), (128, 96, 7, 7), (96, 40, 9, 11), (40, 48, 13, 13), (33, 40, 9, 11),
+                                   (70, 64, 12, 12), (64, 32, 28, 28)])
+def test_grouped_statistics_on_small_feature_maps(shape):
+    """b2q_absmax_f32 / b2q_meanabs_f32 per channel group on an (N, C, H, W) view whose rows are short and mostly not a
+    multiple of eight floats (flattened-walk kernels for the large ones): max|x| exactly, mean|x| = the correctly rounded
+    float32 of the exact sum divided by float32(count), as the oracle's mx_mean."""
+    import torch
+    from b200quant import _kernels as K
+    rng = np.random.default_rng(sum(shape))
+    x = (rng.standard_normal(shape) * 1.7).astype(F)
+    xd = torch.from_numpy(x).cuda()
+    for gs in (1, 4, 8):
+        if shape[1] % gs:
+            continue
+        groups = shape[1] // gs
+        view = (shape[0], groups, gs * shape[2] * shape[3])
+        mx, mean = torch.zeros(groups, device="cuda"), torch.zeros(groups, device="cuda")
+        K.absmax(xd, mx, view)
+        K.meanabs(xd, mean, view)
+        xg = np.abs(x).reshape(shape[0], groups, -1)
+        assert bits_equal(mx.cpu().numpy(), xg.max(axis=(0, 2)))
+        want = np.array([qo.mx_mean(xg[:, g, :]) for g in range(groups)], F)
+        assert bits_equal(mean.cpu().numpy(), want)

@@ -52,10 +52,15 @@ int b2q_stream_synchronize(b2q_ctx* ctx, void* stream);
  * descending addresses to reuse what the reduction left in L2), "fast_div" (reciprocal fast path on/off),
  * "peer_reduce_blocks_per_sm" (grid of the max reduction in the peer-memory exchange), "pdl" (programmatic dependent
  * launch between consecutive whole-tensor kernels on/off), "timing" (see b2q_timing_read), "resident" (single-launch
- * forward for tensors that fit on chip), "peer_mode" (1: ticket-free exchange kernels, 0: the first-generation ones),
- * "peer_timeout_ms", "host_ste_copy" (host-buffer straight-through backward copied host to host instead of through the
- * GPU), "dorefa_tanh_max" (DoReFa: element-wise max of |tanh| instead of tanhf(max|w|)).
- * Results never depend on them. */
+ * forward for tensors that fit on chip), "peer_mode" (1: ticket-free exchange kernels, 0: the first-generation ones,
+ * 2 / 3: further tiles staged in shared memory during the wait, 4: the reduction's last block publishes),
+ * "peer_stage_early", "peer_publish_blocks_per_sm", "peer_allreduce_blocks" / "peer_allreduce_blocks_per_sm" (grid of
+ * b2q_peer_allreduce_*), "peer_timeout_ms", "host_ste_copy" (host-buffer straight-through backward copied host to host
+ * instead of through the GPU), "dorefa_tanh_max" (DoReFa: element-wise max of |tanh| instead of tanhf(max|w|)),
+ * "cluster_fwd" / "cluster_max_elems" / "cluster_max_elems_mean" / "cluster_words_per_cta" (single-launch cluster
+ * forward for small tensors), "reverse_min_mb", "bn_variant" / "bn_pieces_per_sm" (batch-statistics kernel),
+ * "stream_reduce" / "stream_stages" (TMA-staged reduction ring), "stream_icvt" (float -> double conversions on the
+ * integer pipe).  Results never depend on them (the mean-based statistics to within the order of an exact double sum). */
 int b2q_set_option(b2q_ctx* ctx, const char* key, int value);
 int b2q_get_option(b2q_ctx* ctx, const char* key, int* value);
 /* number of kernels this library has launched through ctx since creation (bench.py's gpu_launches) */

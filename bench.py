@@ -638,6 +638,36 @@ def forward_by_size(ctx, sizes, peak_gbs):
     return out
 
 
+def forward_by_size_in_stream(torch, nodes, peak_gbs, reps=3):
+    """The same table measured WITHOUT events between the kernels: all activation nodes of one size run their forward
+    back to back (programmatic dependent launch intact, as in the step), two events around the whole group.  Nodes of a
+    size are distinct tensors (groups above the L2 size by construction for all but the smallest sizes).  Single-rank
+    kernels only (at N > 1 the exchange makes every node wait for its peers, which is not a property of a size)."""
+    by_size = {}
+    for nd in nodes:
+        if nd["kind"] == "act":
+            by_size.setdefault(nd["n"], []).append(nd)
+    out = {}
+    for n in sorted(by_size, reverse=True):
+        group = by_size[n]
+
+        def run():
+            for nd in group:
+                nd["op"].forward(True, ["write"], [nd["x"]], [nd["y"]], [nd["aux"]])
+        run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / (reps * len(group))
+        out["%d" % n] = {"mb": round(4 * n / 1e6, 1), "nodes": len(group), "us": round(us, 2),
+                         "frac_of_peak_on_12B_per_elem": round(12.0 * n / us / 1e3 / peak_gbs, 4)}
+    return out
+
+
 def measure_kernels(torch, ctx, step, reps, peak_gbs, act_sizes=None):
     ctx.set_option("timing", 1)
     ctx.timing_read(0, reset=True)
@@ -974,6 +1004,12 @@ def main():
     kernels, kinds = measure_kernels(torch, ctx, step, 0 if args.profile else min(args.steps, 5), peak_gbs,
                                      act_sizes=[nd["n"] for nd in nodes if nd["kind"] == "act"])
     fwd_by_size = kernels.pop("forward_by_activation_size", None)
+    fwd_by_size_stream = None
+    if world == 1 and not args.profile:
+        try:
+            fwd_by_size_stream = forward_by_size_in_stream(torch, nodes, peak_gbs)
+        except Exception as e:  # pragma: no cover
+            fwd_by_size_stream = {"error": str(e).splitlines()[0][:160]}
     traffic, traffic_note = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_dominant_kernel.json")) as f:
@@ -1005,6 +1041,11 @@ def main():
             "hbm_frac_whole_step": alg_bytes_step / (ms_eager / args.steps / 1e3) / 1e9 / peak_gbs,
             "hbm_frac_whole_step_best_mode": alg_bytes_step / (best_ms / args.steps / 1e3) / 1e9 / peak_gbs,
             "roofline": roofline, "kernels": kernels, "forward_by_activation_size": fwd_by_size,
+            "forward_by_activation_size_in_stream": fwd_by_size_stream,
+            "forward_by_size_note": "forward_by_activation_size: from the per-launch event records (the events break the "
+                                    "programmatic dependent launch between reduction and sweep, so small and mid sizes read "
+                                    "low); ..._in_stream: all nodes of a size back to back with no event in between, as in "
+                                    "the step",
             "kernels_note": "event-timed per launch in a separate pass, all tensor sizes pooled (54 of the launches per "
                             "kind are weight tensors of a few KB..MB that cost a launch each); a kernel that follows a "
                             "sweep also pays for the write-back of the output lines its predecessor left dirty in L2 "

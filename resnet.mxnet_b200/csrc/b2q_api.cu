@@ -95,6 +95,7 @@ static int* option_slot(b2q_ctx* ctx, const char* key) {
     if (!strcmp(key, "resident")) return &ctx->resident;
     if (!strcmp(key, "resident_max_mb")) return &ctx->resident_max_mb;
     if (!strcmp(key, "peer_mode")) return &ctx->peer_mode;
+    if (!strcmp(key, "seg_masked")) return &ctx->seg_masked;
     if (!strcmp(key, "stream_reduce")) return &ctx->stream_reduce;
     if (!strcmp(key, "stream_stages")) return &ctx->stream_stages;
     if (!strcmp(key, "stream_icvt")) return &ctx->stream_icvt;

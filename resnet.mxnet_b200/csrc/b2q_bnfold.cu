@@ -58,6 +58,12 @@ bnstat_fold_kernel(const float* __restrict__ y, SegPlan pl, b2q_slot* slot, floa
         unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_dyn + (size_t)nst * B2Q_STREAM_CH * 4);
         float unused = 0.f;
         seg_stream_accumulate<2, VEC == 17>(y, pl, pc, s_buf, s_bar, nst, s, ss, unused);
+    } else if (VEC == 5) {   // rows that are not a multiple of eight floats: masked aligned 256-bit words (b2q_reduce.cuh)
+        double s1 = 0.0, q0 = 0.0, q1 = 0.0;
+        seg_masked_words<2>(y, pl.outer * pl.groups * pl.inner, pl, pc,
+                            [&](const f8& w) { acc8_sq_seq<0>(s, s1, q0, q1, w); });
+        s += s1;
+        ss = q0 + q1;
     } else if (VEC == 8) {
         const unsigned wpr = (unsigned)((pc.i1 - pc.i0) >> 3);
         const unsigned total = (unsigned)(pc.o1 - pc.o0) * wpr;
@@ -200,6 +206,8 @@ static int launch_bnstat(b2q_ctx* ctx, const float* y, int64_t n, int64_t c, int
     b2q_timed_launch tl(ctx, B2Q_KIND_OTHER, 4.0 * (double)(n * c * hw), st);
     const bool vec8 = (hw % 8 == 0) && (pl.part % 8 == 0) && ((((uintptr_t)y) & 31) == 0);
     const bool vec4 = !vec8 && (hw % 4 == 0) && (pl.part % 4 == 0) && ((((uintptr_t)y) & 15) == 0);
+    const bool masked = !vec8 && !vec4 && ctx->seg_masked && pl.P == 1 && hw >= 8 && hw < 2048 && ((((uintptr_t)y) & 31) == 0) &&
+                        n * c * hw >= (1 << 18);
     if (vec8 && ctx->stream_reduce && b2q_stream_ok(pl)) {
         const int nst = b2q_stream_stages(ctx);
         const size_t smem = b2q_stream_smem(nst);
@@ -215,7 +223,8 @@ static int launch_bnstat(b2q_ctx* ctx, const float* y, int64_t n, int64_t c, int
     }
     // (loads in flight per thread, resident blocks per SM); option bn_variant
 #define B2Q_BN_LAUNCH(U, B) do {                                                                                          \
-        if (vec4) b2q_launch(ctx, bnstat_fold_kernel<4, U, B, 0>, grid, B2Q_THREADS, st, y, pl, slot, scale, mean, var, f, 0);     \
+        if (masked) b2q_launch(ctx, bnstat_fold_kernel<5, U, B, 0>, grid, B2Q_THREADS, st, y, pl, slot, scale, mean, var, f, 0);  \
+        else if (vec4) b2q_launch(ctx, bnstat_fold_kernel<4, U, B, 0>, grid, B2Q_THREADS, st, y, pl, slot, scale, mean, var, f, 0); \
         else if (!vec8) b2q_launch(ctx, bnstat_fold_kernel<1, U, B, 0>, grid, B2Q_THREADS, st, y, pl, slot, scale, mean, var, f, 0);  \
         else if (ctx->stream_icvt == 1)                                                                                    \
             b2q_launch(ctx, bnstat_fold_kernel<8, U, B, 1>, grid, B2Q_THREADS, st, y, pl, slot, scale, mean, var, f, 0);       \

@@ -81,6 +81,7 @@ struct b2q_ctx {
                                      // 0 = off: measured neutral in the step, profiles/r02s_cluster_sweep.log)
     int cluster_max_elems_mean = 147456;   // ... and for the mean-based ones
     int cluster_words_per_cta = 1024;   // grow the cluster (1/2/4/8 CTAs) while a CTA would hold more 256-bit words than this
+    int seg_masked = 1;              // batch statistics over rows that are not a multiple of 4 floats: masked aligned 256-bit words
     int stream_reduce = 0;           // 1: segmented / batch-statistics reductions through the TMA-staged ring when eligible (measured slower)
     int stream_stages = 4;           // 16 KB stages per block of that ring
     int stream_icvt = 0;             // float -> double conversions of the statistics kernels: 0 XU pipe, 1 integer pipe, 2 half / half

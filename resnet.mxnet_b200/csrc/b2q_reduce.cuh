@@ -373,6 +373,57 @@ __device__ __forceinline__ void seg_stream_accumulate(const float* __restrict__ 
     acc2 = q0 + q1;
 }
 
+// Rows that are NOT a multiple of eight floats (7x7 = 49, 14x14 = 196, ...) with 256-bit loads all the same: every
+// ALIGNED 256-bit word that overlaps a row of the piece is loaded whole and the elements outside the row are zeroed
+// (neutral for sums, sums of squares and max|x|; a select, so a neighbour's NaN does not leak in).  The (row, word) space is
+// flattened into one index walked incrementally; U words in flight per thread.  x must be 32-byte aligned and hold
+// n_total elements (the last word of the tensor is read element-wise if it would cross the end).  A 49-float row costs
+// 7-8 words for 6.1 words of payload, and its edge words are shared with the neighbouring rows (another block's, an L2
+// hit) -- against eight times fewer load instructions and eight times the bytes in flight of the scalar walk.
+// Measured (profiles/r02v_bnstat_small_maps.md): batch statistics on 7x7 maps 0.25 -> 0.32 / 0.21 -> 0.25 of the copy
+// peak; on 14x14 maps (rows a multiple of four floats) the 128-bit walk is faster (0.56 vs 0.49), and the grouped
+// mean|x| / max|x| reductions do not gain -- so only the statistics kernel uses it, and only for rows that are not a
+// multiple of four floats.
+template <int U, typename F>
+__device__ __forceinline__ void seg_masked_words(const float* __restrict__ x, int64_t n_total, const SegPlan& pl,
+                                                 const SegPiece& pc, F&& f) {
+    const int64_t len = pc.i1 - pc.i0;
+    const unsigned wpr = (unsigned)((len + 14) >> 3);             // upper bound of the words overlapping one row
+    const unsigned long long total = (unsigned long long)(pc.o1 - pc.o0) * wpr;
+    const int64_t row0 = (pc.o0 * pl.groups + pc.g) * pl.inner + pc.i0;
+    const int64_t ostride = pl.groups * pl.inner;
+    const unsigned qT = blockDim.x / wpr, rT = blockDim.x % wpr;
+    unsigned o = threadIdx.x / wpr, j = threadIdx.x % wpr;
+    for (unsigned long long t = threadIdx.x; t < total; t += (unsigned long long)U * blockDim.x) {
+        f8 v[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const int64_t start = row0 + (int64_t)o * ostride;
+            const int64_t wbase = (start & ~(int64_t)7) + 8 * (int64_t)j;
+            const int lo = (int)(start - wbase);                   // elements [lo, hi) of the word belong to the row
+            const int64_t hi64 = start + len - wbase;
+            const int hi = hi64 > 8 ? 8 : (int)hi64;
+            if (t + (unsigned long long)k * blockDim.x < total && hi > 0) {
+                if (wbase + 8 <= n_total) {
+                    v[k] = ld_f8<1>(x + wbase);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[k].v[e] = (wbase + e < n_total) ? x[wbase + e] : 0.f;
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[k].v[e] = (e < lo || e >= hi) ? 0.f : v[k].v[e];
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[k].v[e] = 0.f;
+            }
+            j += rT; o += qT;
+            if (j >= wpr) { j -= wpr; ++o; }
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) f(v[k]);
+    }
+}
+
 struct Prescale {  // fold-BN factor gamma/sqrt(var+eps) per row (o*groups+g); gamma == nullptr: none
     const float* gamma;
     const float* var;

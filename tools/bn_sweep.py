@@ -35,7 +35,7 @@ def timeit(fn, reps=12):
     return e0.elapsed_time(e1) / reps
 
 
-CONFIGS = [dict()]
+CONFIGS = [dict(seg_masked=0), dict(seg_masked=1)]
 
 for cshape, wshape in (((256, 64, 64, 64), (64, 64, 3, 3)), ((256, 1024, 16, 16), (1024, 512, 1, 1)),
                        ((128, 512, 28, 28), (512, 128, 1, 1)), ((256, 1024, 14, 14), (1024, 256, 1, 1)),

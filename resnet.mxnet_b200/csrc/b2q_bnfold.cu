@@ -140,21 +140,24 @@ bnstat_fold_kernel(const float* __restrict__ y, SegPlan pl, b2q_slot* slot, floa
     const double bss = block_reduce<false>(ss, smem);
     const int SP = pl.S * pl.P;
     const int c = (int)pc.g;
-    if (threadIdx.x == 0) {
-        slot->partial[2 * blockIdx.x] = bs;
-        slot->partial[2 * blockIdx.x + 1] = bss;
-        s_ticket = b2q_take_ticket(&slot->row_ticket[c], (unsigned)SP - 1u);
+    double S = bs, SS = bss;     // one piece per channel (small feature maps with many channels): this block owns the
+    if (SP > 1) {                // channel -- no partials, no ticket, no second reduction
+        if (threadIdx.x == 0) {
+            slot->partial[2 * blockIdx.x] = bs;
+            slot->partial[2 * blockIdx.x + 1] = bss;
+            s_ticket = b2q_take_ticket(&slot->row_ticket[c], (unsigned)SP - 1u);
+        }
+        __syncthreads();
+        if (s_ticket != (unsigned)SP - 1u) return;
+        // ---- this block completes channel c: statistics in a fixed order ----
+        double a = 0.0, b = 0.0;
+        for (int l = threadIdx.x; l < SP; l += blockDim.x) {
+            a += __ldcg(&slot->partial[2 * ((int64_t)c * SP + l)]);
+            b += __ldcg(&slot->partial[2 * ((int64_t)c * SP + l) + 1]);
+        }
+        S = block_reduce<false>(a, smem);
+        SS = block_reduce<false>(b, smem);
     }
-    __syncthreads();
-    if (s_ticket != (unsigned)SP - 1u) return;
-    // ---- this block completes channel c: statistics in a fixed order ----
-    double a = 0.0, b = 0.0;
-    for (int l = threadIdx.x; l < SP; l += blockDim.x) {
-        a += __ldcg(&slot->partial[2 * ((int64_t)c * SP + l)]);
-        b += __ldcg(&slot->partial[2 * ((int64_t)c * SP + l) + 1]);
-    }
-    const double S = block_reduce<false>(a, smem);
-    const double SS = block_reduce<false>(b, smem);
     if (threadIdx.x == 0) {
         const double n = (double)(pl.outer * pl.inner);
         const float mean = __fmul_rn(scale, (float)S);
@@ -164,7 +167,7 @@ bnstat_fold_kernel(const float* __restrict__ y, SegPlan pl, b2q_slot* slot, floa
         s_val[1] = __fmul_rn(scale, (float)(dev < 0.0 ? 0.0 : dev));   // NaN (a NaN / Inf in the channel) stays NaN
         mean_out[c] = s_val[0];
         var_out[c] = s_val[1];
-        slot->row_ticket[c] = 0;
+        if (SP > 1) slot->row_ticket[c] = 0;
     }
     __syncthreads();
     if (f.w == nullptr) return;
@@ -197,6 +200,9 @@ static int launch_bnstat(b2q_ctx* ctx, const float* y, int64_t n, int64_t c, int
     B2Q_REQUIRE(y && mean && var && n >= 1 && c >= 1 && hw >= 1, "bad argument");
     B2Q_REQUIRE(c <= B2Q_MAX_GROUPS, "too many channels (max 8192)");
     SegPlan pl = b2q_seg_plan(y, nullptr, n, c, hw, ctx->num_sms * (ctx->bn_pieces_per_sm > 0 ? ctx->bn_pieces_per_sm : 16));
+    // many small channels (7x7 / 14x14 maps with >= 4 channels per SM, <= 256 KB each): one block per channel, which then
+    // needs no partials, ticket or second reduction
+    if (c >= 4 * (int64_t)ctx->num_sms && n * hw * 4 <= (256 << 10) && pl.P == 1) pl.S = 1;
     while ((int64_t)c * pl.S * pl.P > B2Q_MAX_PIECES / 2 && pl.S > 1) --pl.S;   // two partials per piece
     B2Q_REQUIRE((int64_t)c * pl.S * pl.P <= B2Q_MAX_PIECES / 2, "activation too large for one statistics launch");
     // fl(C / size) as batch_norm_v1-inl.h computes it: two float operands
